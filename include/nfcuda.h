@@ -1,0 +1,194 @@
+/*
+ * libnfcuda -- C ABI of the B200-native (sm_100a) training hot path of NormalizingFlows.jl.
+ *
+ * This is the drop-in boundary described in SURVEY.md section 8(b).  A Julia package extension
+ * binds these symbols with `ccall` (see INTEGRATION.md and julia/NormalizingFlowsNFCUDAExt.jl) and
+ * plugs them in behind the reference's own seam
+ *     _prepare_gradient / _value_and_gradient        (reference src/optimize.jl:8-14)
+ * so that `train_flow(elbo, flow, logp, n; ADbackend=AutoNFCUDA())`
+ *                                                      (reference src/NormalizingFlows.jl:54-86)
+ * runs on the GPU with `optimize`, Optimisers.jl and the destructure'd theta untouched.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative nf_status on failure; the message is
+ *     available from nf_last_error() (thread local).  Nothing throws or aborts across the ABI.
+ *   - the caller owns every host buffer; the library owns all device memory behind opaque handles.
+ *   - batches are Julia `d x N` column-major arrays == row-major [N][d]: each sample's d numbers are
+ *     contiguous.  theta / grad are flat vectors in `Optimisers.destructure` order (reference
+ *     src/NormalizingFlows.jl:67) with element type = the flow's dtype.
+ *   - layers are listed in theta order, i.e. the order of `Ls` handed to `create_flow(Ls, q0)`
+ *     (reference src/flows/utils.jl:23-26); the transform applies Ls[end] first.
+ *   - mask indices are 0-based here (Julia side subtracts 1).
+ *   - `scale` multiplies the returned value and gradient: pass -1.0 to obtain the loss
+ *     `-vo(rng, re(theta), args...)` of reference src/NormalizingFlows.jl:69 and its gradient.
+ *   - `*_dev` variants take device pointers (same layout) on the flow's device and enqueue on the
+ *     flow's stream; they are what a multi-GPU host uses before its gradient all-reduce.
+ *   - there is no CPU fallback: every entry point fails with NF_ERR_CUDA when no sm_100 device is
+ *     usable.
+ */
+#ifndef NFCUDA_H
+#define NFCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFCUDA_VERSION 100
+
+#if defined(__GNUC__)
+#define NF_API __attribute__((visibility("default")))
+#else
+#define NF_API
+#endif
+
+typedef struct nf_flow_s*   nf_flow_t;
+typedef struct nf_target_s* nf_target_t;
+
+typedef enum nf_status {
+  NF_OK              =  0,
+  NF_ERR_INVALID     = -1,   /* bad argument / unsupported configuration */
+  NF_ERR_CUDA        = -2,   /* CUDA runtime / driver error, or no usable device */
+  NF_ERR_OOM         = -3,   /* device allocation failed */
+  NF_ERR_UNSUPPORTED = -4    /* valid request this build cannot run (e.g. dim too large for a kernel) */
+} nf_status;
+
+typedef enum nf_dtype { NF_F32 = 0, NF_F64 = 1 } nf_dtype;
+
+/* Layer kinds.  PLANAR/RADIAL: Bijectors.PlanarLayer/RadialLayer built by planarflow/radialflow
+ * (reference src/flows/planar_radial.jl:21-29,52-60).  AFFINE_COUPLING: reference
+ * src/flows/realnvp.jl:33-110.  SPLINE_COUPLING: reference src/flows/neuralspline.jl:35-140.
+ * SHIFT/SCALE: Bijectors.Shift/Scale, the flow of the reference's analytic tests
+ * (reference test/objectives.jl:9, test/interface.jl:22-24). */
+typedef enum nf_layer_kind {
+  NF_PLANAR          = 1,   /* theta: w(d), u(d), b(1)        */
+  NF_RADIAL          = 2,   /* theta: alpha_(1), beta(1), z0(d) */
+  NF_AFFINE_COUPLING = 3,   /* theta: s-chain, t-chain; chain = W1(:),b1,W2(:),b2,...  (W out x in, column major) */
+  NF_SPLINE_COUPLING = 4,   /* theta: nn-chain with (3K-1)*n_mask outputs */
+  NF_SHIFT           = 5,   /* theta: a(d) */
+  NF_SCALE           = 6    /* theta: a(d) */
+} nf_layer_kind;
+
+typedef struct nf_layer_desc {
+  int        kind;       /* nf_layer_kind */
+  const int* mask_idx;   /* couplings: 0-based indices of the TRANSFORMED coordinates (PartitionMask idx) */
+  int        n_mask;
+  const int* hdims;      /* couplings: hidden widths of the conditioner MLP(s) (`hdims` of fnn, reference src/flows/utils.jl:71-100) */
+  int        n_hidden;
+  int        K;          /* spline: number of bins   (reference src/flows/neuralspline.jl:37) */
+  double     B;          /* spline: domain half-width (reference src/flows/neuralspline.jl:39) */
+} nf_layer_desc;
+
+/* Built-in target log-densities with device-side logp and score (reference example/targets/*.jl). */
+typedef enum nf_target_kind {
+  NF_TARGET_BANANA       = 1,  /* params: b, var            (banana.jl:77-83)           */
+  NF_TARGET_FUNNEL       = 2,  /* params: mu, sigma         (neal_funnel.jl:54-61)      */
+  NF_TARGET_WARPED_GAUSS = 3,  /* params: sigma1, sigma2    (warped_gaussian.jl:81-87)  */
+  NF_TARGET_CROSS        = 4,  /* params: mu, sigma; dim = 2m -> product of m Cross blocks (cross.jl:30-38) */
+  NF_TARGET_DIAG_NORMAL  = 5   /* params: mu[dim], sigma[dim] (standard deviations; MvNormal(mu, Diagonal(sigma.^2))) */
+} nf_target_kind;
+
+/* MMA issue mode of the coupling-MLP contractions (fp32 flows).  BF16X3 is the parity mode. */
+typedef enum nf_mma_mode {
+  NF_MMA_SIMT    = 0,  /* CUDA-core FMA GEMMs in the flow dtype (the only mode for NF_F64)            */
+  NF_MMA_BF16X3  = 1,  /* tcgen05 kind::f16, operands split hi+lo bf16, 3 products, fp32 accumulate   */
+  NF_MMA_BF16X1  = 2   /* tcgen05 single bf16 pass: NOT parity-grade, offered for throughput studies  */
+} nf_mma_mode;
+
+/* ---- library / device ------------------------------------------------------------------------ */
+NF_API int         nf_version(void);
+NF_API const char* nf_last_error(void);
+/* Select the CUDA device this thread's subsequent handles live on; checks for compute capability 10.x. */
+NF_API int         nf_init(int device);
+NF_API int         nf_device_count(int* count);
+NF_API int         nf_synchronize(void);
+
+/* ---- flow ------------------------------------------------------------------------------------ */
+/* Replaces: create_flow / planarflow / radialflow / realnvp / nsf structure + Optimisers.destructure layout
+ * (reference src/flows/utils.jl:23-26, src/NormalizingFlows.jl:67). */
+NF_API int     nf_flow_create(nf_flow_t* out, const nf_layer_desc* layers, int n_layers, int dim, int dtype);
+NF_API void    nf_flow_destroy(nf_flow_t flow);
+NF_API int64_t nf_flow_num_params(nf_flow_t flow);
+NF_API int     nf_flow_dim(nf_flow_t flow);
+/* Base distribution q0 = MvNormal(mu, Diagonal(sigma.^2)); NULL -> zeros / ones.  double arrays of length dim. */
+NF_API int     nf_flow_set_base(nf_flow_t flow, const double* mu, const double* sigma);
+/* nf_mma_mode for the coupling MLPs; default NF_MMA_BF16X3 for NF_F32 flows, NF_MMA_SIMT for NF_F64. */
+NF_API int     nf_flow_set_mma_mode(nf_flow_t flow, int mode);
+/* Cap (bytes) on the activation workspace; batches larger than fits are processed in sample chunks. */
+NF_API int     nf_flow_set_workspace_limit(nf_flow_t flow, size_t bytes);
+/* Offset (in elements) of layer `layer`'s parameters inside theta. */
+NF_API int64_t nf_flow_param_offset(nf_flow_t flow, int layer);
+
+/* ---- targets --------------------------------------------------------------------------------- */
+NF_API int  nf_target_create(nf_target_t* out, int kind, int dim, const double* params, int n_params);
+NF_API void nf_target_destroy(nf_target_t target);
+
+/* ---- objectives: value and gradient ---------------------------------------------------------- */
+/* Replaces _value_and_gradient(loss, prep, ad, theta, rng, logp, n) for vo = elbo / elbo_batch
+ * (reference src/optimize.jl:12-14,86; src/objectives/elbo.jl:4-7,31-34,65-70,89-97).
+ * z0_host: N x dim base draws (NULL -> drawn on device with Philox keyed by `seed`, replacing
+ * _device_specific_rand, reference src/NormalizingFlows.jl:100-127, ext/NormalizingFlowsCUDAExt.jl:7-48).
+ * value_out: scale * mean_j elbo_j.  grad_host_out: scale * d/dtheta (P elements of the flow dtype; may be NULL). */
+NF_API int nf_elbo_value_and_grad(nf_flow_t flow, nf_target_t target, const void* theta_host, int64_t N,
+                           const void* z0_host, uint64_t seed, double scale,
+                           double* value_out, void* grad_host_out);
+NF_API int nf_elbo_value_and_grad_dev(nf_flow_t flow, nf_target_t target, const void* theta_dev, int64_t N,
+                               const void* z0_dev, uint64_t seed, double scale,
+                               double* value_out, void* grad_dev_out);
+/* Un-normalised sums for sample-sharded data parallelism: writes the SUM over the N local samples of
+ * elbo_j into sums_dev_out[P] and of d elbo_j/dtheta into sums_dev_out[0..P) (P+1 elements of the flow
+ * dtype, device memory) so that one all-reduce of P+1 numbers followed by a division by N_total
+ * finishes the step. */
+NF_API int nf_elbo_sums_dev(nf_flow_t flow, nf_target_t target, const void* theta_dev, int64_t N,
+                     const void* z0_dev, uint64_t seed, void* sums_dev_out);
+/* Per-sample ELBO terms elbo_j = logp(T(x_j)) - log q0(x_j) + logdet_j (reference elbo.jl:65-70). */
+NF_API int nf_elbo_terms(nf_flow_t flow, nf_target_t target, const void* theta_host, int64_t N,
+                  const void* z0_host, void* elbos_host_out);
+
+/* Replaces _value_and_gradient for vo = loglikelihood (reference src/objectives/loglikelihood.jl:26-33):
+ * value = scale * mean_j logpdf(flow, xs_j), gradient through the inverse flow. */
+NF_API int nf_loglik_value_and_grad(nf_flow_t flow, const void* theta_host, int64_t N, const void* xs_host,
+                             double scale, double* value_out, void* grad_host_out);
+NF_API int nf_loglik_value_and_grad_dev(nf_flow_t flow, const void* theta_dev, int64_t N, const void* xs_dev,
+                                 double scale, double* value_out, void* grad_dev_out);
+
+/* ---- transform / density API ------------------------------------------------------------------ */
+/* with_logabsdet_jacobian(flow.transform, xs): y_out N x dim, logdet_out N (either may be NULL).
+ * (reference src/flows/realnvp.jl:77-83, src/flows/neuralspline.jl:102-108; Bijectors planar/radial) */
+NF_API int nf_forward(nf_flow_t flow, const void* theta_host, int64_t N, const void* x_host,
+               void* y_host_out, void* logdet_host_out);
+/* with_logabsdet_jacobian(inverse(flow.transform), ys) (reference realnvp.jl:99-110, neuralspline.jl:133-140). */
+NF_API int nf_inverse(nf_flow_t flow, const void* theta_host, int64_t N, const void* y_host,
+               void* x_host_out, void* logdet_host_out);
+/* logpdf(flow, ys) (Bijectors TransformedDistribution; used by reference test/flow.jl:15-16). */
+NF_API int nf_logpdf(nf_flow_t flow, const void* theta_host, int64_t N, const void* y_host, void* logpdf_host_out);
+/* rand(flow, N): base draws on device (Philox, `seed`) pushed through the flow in one batched pass;
+ * replaces the per-column loop of reference ext/NormalizingFlowsCUDAExt.jl:65-74. */
+NF_API int nf_sample(nf_flow_t flow, const void* theta_host, int64_t N, uint64_t seed, void* y_host_out);
+/* randn draws N x dim ~ q0 (replaces _device_specific_rand for MvNormal, reference ext:41-48). */
+NF_API int nf_base_sample(nf_flow_t flow, int64_t N, uint64_t seed, void* z_host_out);
+
+/* Two-phase API for an arbitrary user log-density evaluated by the caller (SURVEY section 7 'Arbitrary Julia logp'):
+ * nf_forward_stash runs the flow and keeps the activations; the caller evaluates logp(y) and
+ * d logp/dy; nf_backward returns  sum_j [ gy_j . dy_j/dtheta + gld_j * dlogdet_j/dtheta ]. */
+NF_API int nf_forward_stash(nf_flow_t flow, const void* theta_host, int64_t N, const void* x_host,
+                     void* y_host_out, void* logdet_host_out);
+NF_API int nf_backward(nf_flow_t flow, const void* gy_host, const void* gld_host_or_null, void* grad_host_out);
+
+/* ---- test hooks (exercised by tests/, not by the Julia shim) ---------------------------------- */
+/* Spline bin indices of every spline coupling for a forward pass over x_host: bins_out is
+ * [n_spline_layers][N][n_mask] int32, in application order.  Bit-exactness check of BASELINE north_star. */
+NF_API int nf_spline_bins(nf_flow_t flow, const void* theta_host, int64_t N, const void* x_host, int32_t* bins_out);
+/* Bin search alone on caller-supplied knots: knots [M][K+1], v [M] -> bins [M] (searchsortedfirst - 1). */
+NF_API int nf_rqs_bin_search(int dtype, const void* knots_host, const void* v_host, int64_t M, int K, int32_t* bins_out);
+/* Number of kernels launched by this thread's library calls since the last reset (bench.py `gpu_launches`). */
+NF_API int64_t nf_launch_count(int reset);
+/* Duration (ms, CUDA events on the flow's stream) of the device work of the last value_and_grad call. */
+NF_API double  nf_last_device_ms(nf_flow_t flow);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFCUDA_H */

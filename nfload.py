@@ -1,0 +1,26 @@
+"""Loader for the package directory `normalizingflows.jl_b200/` (its name is not a Python identifier)."""
+import importlib.util
+import os
+import sys
+
+_ROOT = os.path.dirname(os.path.abspath(__file__))
+_NAME = "normalizingflows_jl_b200"
+
+
+def load():
+    if _NAME in sys.modules:
+        return sys.modules[_NAME]
+    pkg_dir = os.path.join(_ROOT, "normalizingflows.jl_b200")
+    spec = importlib.util.spec_from_file_location(_NAME, os.path.join(pkg_dir, "__init__.py"),
+                                                  submodule_search_locations=[pkg_dir])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[_NAME] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build(force=False):
+    spec = importlib.util.spec_from_file_location("_nf_build", os.path.join(_ROOT, "normalizingflows.jl_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force)

@@ -1,0 +1,467 @@
+// K1/K2 -- fused forward + logdet + target + backward kernel for flows made only of elementwise
+// layers (PlanarLayer, RadialLayer, Shift, Scale): SURVEY section 8 rows a9, a10, a15, a16.
+//
+// One launch turns Z0 [N x d] into the ELBO partial sums and the per-layer gradient partial sums;
+// nothing of size N is written.  Each thread owns S samples whose state lives in registers, the
+// per-layer parameter table is staged in shared memory, the per-sample/per-layer scalar needed by
+// the backward sweep (tanh(a) for planar, r for radial) is stashed in shared memory, and the
+// per-parameter gradient sums are reduced warp-shuffle -> shared atomics -> one partial row per CTA
+// (finished deterministically by ew_finalize_kernel).
+//
+// Math (reference-side definitions):
+//   planar  (Bijectors.PlanarLayer, restated in reference test/ext/CUDA/cuda.jl:12-30; App. A.1)
+//   radial  (Bijectors.RadialLayer; App. A.2)
+//   elbo_j = logp(T(x_j)) - log q0(x_j) + logdet_j          (reference src/objectives/elbo.jl:4-7,65-70)
+#include "flow.hpp"
+#include "targets.cuh"
+
+namespace nf {
+
+// per-layer table entry: [c0 c1 c2 c3 | v0[DP] | v1[DP]]
+//   planar: c0 = b, c1 = m = w.u_hat ; v0 = w, v1 = u_hat
+//   radial: c0 = alpha, c1 = beta_hat ; v0 = z0
+//   shift : v0 = a
+//   scale : c0 = sum log|a| ; v0 = a, v1 = 1/a
+template <int DP> constexpr int ew_stride() { return 4 + 2 * DP; }
+template <int DP> constexpr int ew_nacc() { return 2 * DP + 2; }
+
+template <typename T, int DP>
+__global__ void ew_prep_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
+                               T* __restrict__ table) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  using N = Num<T>;
+  const T* p = theta + meta[l].theta_off;
+  T* e = table + (size_t)l * ew_stride<DP>();
+  for (int k = 0; k < ew_stride<DP>(); ++k) e[k] = 0;
+  T* v0 = e + 4;
+  T* v1 = e + 4 + DP;
+  switch (meta[l].kind) {
+    case NF_PLANAR: {  // theta: w(d), u(d), b
+      const T* w = p; const T* u = p + d;
+      T s = 0, n = 0;
+      for (int k = 0; k < d; ++k) { s += w[k] * u[k]; n += w[k] * w[k]; }
+      const T kappa = (softplus_stable<T>(-s) - 1) / n;
+      for (int k = 0; k < d; ++k) { v0[k] = w[k]; v1[k] = u[k] + kappa * w[k]; }
+      e[0] = p[2 * d];
+      e[1] = softplus_stable<T>(s) - 1;
+      break;
+    }
+    case NF_RADIAL: {  // theta: alpha_, beta, z0(d)
+      const T alpha = softplus_stable<T>(p[0]);
+      e[0] = alpha;
+      e[1] = -alpha + softplus_stable<T>(p[1]);
+      for (int k = 0; k < d; ++k) v0[k] = p[2 + k];
+      break;
+    }
+    case NF_SHIFT:
+      for (int k = 0; k < d; ++k) v0[k] = p[k];
+      break;
+    case NF_SCALE: {
+      T sl = 0;
+      for (int k = 0; k < d; ++k) { v0[k] = p[k]; v1[k] = 1 / p[k]; sl += N::log(N::abs(p[k])); }
+      for (int k = d; k < DP; ++k) { v0[k] = 1; v1[k] = 1; }
+      e[0] = sl;
+      break;
+    }
+  }
+}
+
+enum : int { EW_GRAD = 1, EW_TARGET = 2, EW_WRITE_Y = 4, EW_WRITE_LD = 8, EW_WRITE_TERMS = 16, EW_GEN_Z0 = 32 };
+
+template <typename T> struct EwArgs {
+  const T* z0;          // [N, d] (ignored with EW_GEN_Z0)
+  const T* table;       // [L, stride]
+  const int* kinds;     // [L]
+  const T* base;        // mu[d], sigma[d] or nullptr
+  T base_c0;            // -d/2 log2pi - sum log sigma
+  TargetParams<T> tp;
+  T* y_out;             // [N, d]
+  T* ld_out;            // [N]
+  T* terms_out;         // [N]
+  T* gpart;             // [grid, L * nacc]
+  double* epart;        // [grid]
+  int64_t N;
+  int L, d, flags;
+  uint64_t seed;
+};
+
+template <typename T, int DP, int S>
+__global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
+  using N_ = Num<T>;
+  constexpr int STR = ew_stride<DP>();
+  constexpr int NACC = ew_nacc<DP>();
+  const int L = a.L, d = a.d, tid = threadIdx.x, nthr = blockDim.x;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* s_tab = reinterpret_cast<T*>(smem_raw);                 // L*STR
+  T* s_acc = s_tab + (size_t)L * STR;                        // L*NACC
+  T* s_stash = s_acc + (size_t)L * NACC;                     // L*S*nthr
+  int* s_kind = reinterpret_cast<int*>(s_stash + (size_t)L * S * nthr);  // L
+  for (int i = tid; i < L * STR; i += nthr) s_tab[i] = a.table[i];
+  for (int i = tid; i < L * NACC; i += nthr) s_acc[i] = 0;
+  for (int i = tid; i < L; i += nthr) s_kind[i] = a.kinds[i];
+  __syncthreads();
+
+  const bool want_grad = a.flags & EW_GRAD;
+  T elbo_local = 0;
+  const int64_t group = (int64_t)nthr * S;
+  const int64_t ngroups = (a.N + group - 1) / group;
+
+  for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
+    T z[S][DP], ld[S], lq[S];
+    bool live[S];
+    // ---- load base draws, base log-density (a15) ----
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int64_t j = gi * group + (int64_t)s * nthr + tid;
+      live[s] = j < a.N;
+      const int64_t jj = live[s] ? j : 0;
+      T q = 0;
+      if (!(a.flags & EW_GEN_Z0) && DP == 2 && d == 2 && sizeof(T) == 4) {
+        const float2 v = reinterpret_cast<const float2*>(a.z0)[jj];
+        z[s][0] = v.x; z[s][1] = v.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          if (k < d) z[s][k] = (a.flags & EW_GEN_Z0) ? philox_randn<T>(a.seed, (uint64_t)jj * d + k) : a.z0[jj * d + k];
+          else z[s][k] = 0;
+        }
+      }
+      if (a.base) {
+#pragma unroll
+        for (int k = 0; k < DP; ++k)
+          if (k < d) {
+            if (a.flags & EW_GEN_Z0) { q += z[s][k] * z[s][k]; z[s][k] = z[s][k] * a.base[d + k] + a.base[k]; }
+            else { const T u = (z[s][k] - a.base[k]) / a.base[d + k]; q += u * u; }
+          }
+      } else {
+#pragma unroll
+        for (int k = 0; k < DP; ++k) q += z[s][k] * z[s][k];
+      }
+      lq[s] = a.base_c0 - q / 2;
+      ld[s] = 0;
+    }
+    // ---- forward sweep: layers applied last-to-first (create_flow, reference src/flows/utils.jl:23-26) ----
+    for (int l = L - 1; l >= 0; --l) {
+      const T* e = s_tab + (size_t)l * STR;
+      const int kind = s_kind[l];
+      if (kind == NF_PLANAR) {
+        const T b = e[0], m = e[1];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          T dot = b;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) dot += e[4 + k] * z[s][k];
+          const T t = N_::tanh(dot);
+#pragma unroll
+          for (int k = 0; k < DP; ++k) z[s][k] += e[4 + DP + k] * t;
+          ld[s] += N_::log1p(m * (1 - t * t));
+          s_stash[((size_t)l * S + s) * nthr + tid] = t;
+        }
+      } else if (kind == NF_RADIAL) {
+        const T alpha = e[0], bh = e[1];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          T r2 = 0, df[DP];
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { df[k] = (k < d) ? z[s][k] - e[4 + k] : T(0); r2 += df[k] * df[k]; }
+          const T r = N_::sqrt(r2);
+          const T h = 1 / (alpha + r);
+          const T g = bh * h;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) z[s][k] += g * df[k];
+          ld[s] += T(d - 1) * N_::log1p(g) + N_::log1p(g - g * h * r);
+          s_stash[((size_t)l * S + s) * nthr + tid] = r;
+        }
+      } else if (kind == NF_SHIFT) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int k = 0; k < DP; ++k) z[s][k] += e[4 + k];
+      } else {  // NF_SCALE
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+          for (int k = 0; k < DP; ++k) z[s][k] *= e[4 + k];
+          ld[s] += e[0];
+        }
+      }
+    }
+    // ---- outputs of a pure forward pass ----
+    if (a.flags & (EW_WRITE_Y | EW_WRITE_LD)) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int64_t j = gi * group + (int64_t)s * nthr + tid;
+        if (!live[s]) continue;
+        if (a.flags & EW_WRITE_Y)
+#pragma unroll
+          for (int k = 0; k < DP; ++k)
+            if (k < d) a.y_out[j * d + k] = z[s][k];
+        if (a.flags & EW_WRITE_LD) a.ld_out[j] = ld[s];
+      }
+    }
+    if (!(a.flags & EW_TARGET)) continue;
+    // ---- target log-density + score (a16), ELBO term ----
+    T gy[S][DP];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int k = 0; k < DP; ++k) gy[s][k] = 0;
+      const T lp = target_logp_score<T, DP>(a.tp, z[s], gy[s]);
+      const T term = lp - lq[s] + ld[s];
+      if (live[s]) {
+        elbo_local += term;
+        if (a.flags & EW_WRITE_TERMS) a.terms_out[gi * group + (int64_t)s * nthr + tid] = term;
+      } else {
+#pragma unroll
+        for (int k = 0; k < DP; ++k) gy[s][k] = 0;
+      }
+    }
+    if (!want_grad) continue;
+    // ---- backward sweep (reverse of application order); dELBO/dlogdet = 1 per live sample ----
+    const int lane = tid & 31;
+    for (int l = 0; l < L; ++l) {
+      const T* e = s_tab + (size_t)l * STR;
+      T* acc = s_acc + (size_t)l * NACC;
+      const int kind = s_kind[l];
+      if (kind == NF_PLANAR) {
+        const T m = e[1];
+        T ga[S], tt[S];
+        T g_m = 0, g_b = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const T t = s_stash[((size_t)l * S + s) * nthr + tid];
+          const T w8 = live[s] ? T(1) : T(0);
+          const T psi = 1 - t * t, den = 1 + m * psi;
+          T ug = 0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { z[s][k] -= e[4 + DP + k] * t; ug += e[4 + DP + k] * gy[s][k]; }
+          const T gt = ug - w8 * 2 * t * m / den;
+          ga[s] = psi * gt; tt[s] = t;
+          g_m += w8 * psi / den; g_b += ga[s];
+        }
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          T gu = 0, gw = 0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            gu += tt[s] * gy[s][k];
+            gw += z[s][k] * ga[s];
+            gy[s][k] += e[4 + k] * ga[s];
+          }
+          if (k < d) {
+            gu = warp_sum(gu); gw = warp_sum(gw);
+            if (lane == 0) { atomicAdd(&acc[k], gu); atomicAdd(&acc[DP + k], gw); }
+          }
+        }
+        g_m = warp_sum(g_m); g_b = warp_sum(g_b);
+        if (lane == 0) { atomicAdd(&acc[2 * DP], g_m); atomicAdd(&acc[2 * DP + 1], g_b); }
+      } else if (kind == NF_RADIAL) {
+        const T alpha = e[0], bh = e[1];
+        T g_al = 0, g_bh = 0, gz0[DP];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) gz0[k] = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const T r = s_stash[((size_t)l * S + s) * nthr + tid];
+          const T w8 = live[s] ? T(1) : T(0);
+          const T h = 1 / (alpha + r), g = bh * h;
+          const T ifac = 1 / (1 + g);
+          T df[DP], gd = 0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) {
+            df[k] = (k < d) ? (z[s][k] - e[4 + k]) * ifac : T(0);
+            gd += gy[s][k] * df[k];
+            z[s][k] = (k < d) ? e[4 + k] + df[k] : T(0);
+          }
+          const T A = 1 + g, Bq = 1 + alpha * bh * h * h;
+          const T dld_dh = T(d - 1) * bh / A + 2 * alpha * bh * h / Bq;
+          // through r: g(r) = bh*h(r), h' = -h^2
+          const T coef_r = (gd * (-bh * h * h) + w8 * (-h * h) * dld_dh);
+          g_al += gd * (-bh * h * h) + w8 * ((-h * h) * dld_dh + bh * h * h / Bq);
+          g_bh += gd * h + w8 * (T(d - 1) * h / A + alpha * h * h / Bq);
+          const T ir = r > 0 ? 1 / r : T(0);
+#pragma unroll
+          for (int k = 0; k < DP; ++k) {
+            const T gnew = (1 + g) * gy[s][k] + coef_r * df[k] * ir;
+            gz0[k] += gy[s][k] - gnew;
+            gy[s][k] = gnew;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DP; ++k)
+          if (k < d) {
+            const T v = warp_sum(gz0[k]);
+            if (lane == 0) atomicAdd(&acc[k], v);
+          }
+        g_al = warp_sum(g_al); g_bh = warp_sum(g_bh);
+        if (lane == 0) { atomicAdd(&acc[2 * DP], g_al); atomicAdd(&acc[2 * DP + 1], g_bh); }
+      } else if (kind == NF_SHIFT) {
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          T v = 0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) { v += gy[s][k]; z[s][k] -= e[4 + k]; }
+          if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+        }
+      } else {  // NF_SCALE
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          T v = 0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            z[s][k] *= e[4 + DP + k];
+            v += gy[s][k] * z[s][k];
+            gy[s][k] *= e[4 + k];
+          }
+          if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+        }
+      }
+    }
+  }
+  // ---- per-CTA partials ----
+  __syncthreads();
+  if (a.gpart)
+    for (int i = tid; i < L * NACC; i += nthr) a.gpart[(size_t)blockIdx.x * L * NACC + i] = s_acc[i];
+  if (a.epart) {
+    double ev = warp_sum((double)elbo_local);
+    __shared__ double s_e[32];
+    if ((tid & 31) == 0) s_e[tid >> 5] = ev;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int w = 0; w < (nthr + 31) / 32; ++w) t += s_e[w];
+      a.epart[blockIdx.x] = t;
+    }
+  }
+}
+
+// Deterministic cross-CTA reduction + chain rule from the reduced per-layer sums to theta order.
+// One thread per layer; gsum[P+1] receives UNSCALED sums (gradient sums then the ELBO sum at [P]).
+template <typename T, int DP>
+__global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
+                                   const T* __restrict__ gpart, const double* __restrict__ epart, int nblocks,
+                                   int64_t N, int64_t P, int want_grad, double* __restrict__ gsum) {
+  constexpr int NACC = ew_nacc<DP>();
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l == 0) {
+    double e = 0;
+    for (int b = 0; b < nblocks; ++b) e += epart[b];
+    gsum[P] = e;
+  }
+  if (l >= L || !want_grad) return;
+  double G[NACC];
+  for (int i = 0; i < NACC; ++i) G[i] = 0;
+  for (int b = 0; b < nblocks; ++b)
+    for (int i = 0; i < NACC; ++i) G[i] += (double)gpart[((size_t)b * L + l) * NACC + i];
+  const T* p = theta + meta[l].theta_off;
+  double* g = gsum + meta[l].theta_off;
+  switch (meta[l].kind) {
+    case NF_PLANAR: {  // App. A.1 hand backward through u_hat(u, w)
+      const T* w = p; const T* u = p + d;
+      double s = 0, n = 0, gk = 0;
+      for (int k = 0; k < d; ++k) { s += (double)w[k] * u[k]; n += (double)w[k] * w[k]; gk += (double)w[k] * G[k]; }
+      const double m = softplus_stable<double>(s) - 1;
+      const double kappa = (m - s) / n;
+      const double g_m = G[2 * DP] + gk / n;
+      const double g_s = -gk / n + sigmoid_stable<double>(s) * g_m;
+      const double g_n = -kappa * gk / n;
+      for (int k = 0; k < d; ++k) {
+        g[k] = G[DP + k] + kappa * G[k] + g_s * u[k] + 2 * g_n * w[k];   // w
+        g[d + k] = G[k] + g_s * w[k];                                     // u
+      }
+      g[2 * d] = G[2 * DP + 1];                                           // b
+      break;
+    }
+    case NF_RADIAL: {
+      const double sa = sigmoid_stable<double>((double)p[0]), sb = sigmoid_stable<double>((double)p[1]);
+      g[0] = sa * (G[2 * DP] - G[2 * DP + 1]);
+      g[1] = sb * G[2 * DP + 1];
+      for (int k = 0; k < d; ++k) g[2 + k] = G[k];
+      break;
+    }
+    case NF_SHIFT:
+      for (int k = 0; k < d; ++k) g[k] = G[k];
+      break;
+    case NF_SCALE:
+      for (int k = 0; k < d; ++k) g[k] = G[k] + (double)N / (double)p[k];
+      break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DP, int S>
+static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, const T* z0_dev, uint64_t seed,
+                     int flags, T* y_out, T* ld_out, T* terms_out, double* gsum_dev) {
+  const int L = (int)f.layers.size(), d = f.dim;
+  constexpr int STR = ew_stride<DP>(), NACC = ew_nacc<DP>();
+  const int threads = 128;
+  const size_t smem = ((size_t)L * STR + (size_t)L * NACC + (size_t)L * S * threads) * sizeof(T) + (size_t)L * sizeof(int) + 16;
+  if (smem > 200 * 1024) {
+    set_error("elementwise flow with %d layers needs %zu B of shared memory (limit 200 KiB)", L, smem);
+    return NF_ERR_UNSUPPORTED;
+  }
+  auto kern = ew_flow_kernel<T, DP, S>;
+  NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t group = (int64_t)threads * S;
+  int max_blocks = 0;
+  NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kern, threads, smem));
+  if (max_blocks < 1) max_blocks = 1;
+  const int grid = (int)std::min<int64_t>(ceil_div(N, group), (int64_t)kNumSMs * max_blocks);
+
+  T* table = (T*)f.ws_alloc((size_t)L * STR * sizeof(T));
+  T* gpart = (T*)f.ws_alloc((size_t)grid * L * NACC * sizeof(T));
+  double* epart = (double*)f.ws_alloc((size_t)grid * sizeof(double));
+  if (!table || !gpart || !epart) return NF_ERR_OOM;
+
+  ew_prep_kernel<T, DP><<<(L + 63) / 64, 64, 0, f.stream>>>(theta_dev, f.d_ew_meta, L, d, table);
+  NF_LAUNCH_CHECK();
+  EwArgs<T> a{};
+  a.z0 = z0_dev; a.table = table; a.kinds = f.d_ew_kinds;
+  a.base = f.base_is_standard ? nullptr : (const T*)f.d_base;
+  a.base_c0 = (T)f.base_c0;
+  if (tgt) a.tp = tgt->params<T>();
+  a.y_out = y_out; a.ld_out = ld_out; a.terms_out = terms_out;
+  a.gpart = gpart; a.epart = epart; a.N = N; a.L = L; a.d = d;
+  a.flags = flags | (z0_dev ? 0 : EW_GEN_Z0);
+  a.seed = seed;
+  kern<<<grid, threads, smem, f.stream>>>(a);
+  NF_LAUNCH_CHECK();
+  if (gsum_dev) {
+    ew_finalize_kernel<T, DP><<<(L + 63) / 64, 64, 0, f.stream>>>(theta_dev, f.d_ew_meta, L, d, gpart, epart, grid, N,
+                                                                 f.P, (flags & EW_GRAD) ? 1 : 0, gsum_dev);
+    NF_LAUNCH_CHECK();
+  }
+  return NF_OK;
+}
+
+template <typename T>
+int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
+           bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev) {
+  int flags = 0;
+  if (tgt) flags |= EW_TARGET;
+  if (want_grad) flags |= EW_GRAD;
+  if (y_out) flags |= EW_WRITE_Y;
+  if (ld_out) flags |= EW_WRITE_LD;
+  if (terms_out) flags |= EW_WRITE_TERMS;
+  const int d = f.dim;
+#define NF_EW_CASE(DPV, SV)                                                                              \
+  return ew_launch<T, DPV, SV>(f, tgt, (const T*)theta_dev, N, (const T*)z0_dev, seed, flags, (T*)y_out, \
+                               (T*)ld_out, (T*)terms_out, gsum_dev)
+  if (d <= 2) NF_EW_CASE(2, 4);
+  if (d <= 4) NF_EW_CASE(4, 2);
+  if (d <= 8) NF_EW_CASE(8, 1);
+  if (d <= 16) NF_EW_CASE(16, 1);
+  if (d <= 32) NF_EW_CASE(32, 1);
+  if (d <= 64) NF_EW_CASE(64, 1);
+#undef NF_EW_CASE
+  set_error("elementwise (planar/radial) flows support dim <= 64 in this build, got %d", d);
+  return NF_ERR_UNSUPPORTED;
+}
+
+template int ew_run<float>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*);
+template int ew_run<double>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*);
+
+}  // namespace nf

@@ -1,0 +1,116 @@
+// Host-side flow / target descriptors of libnfcuda.
+//
+// A Flow mirrors `transformed(q0, reduce(∘, Ls))` (reference src/flows/utils.jl:23-26): `layers` is Ls
+// in theta (= Optimisers.destructure, reference src/NormalizingFlows.jl:67) order; the transform
+// applies layers.back() first.
+#pragma once
+#include "common.cuh"
+#include "targets.cuh"
+#include <algorithm>
+#include <memory>
+
+namespace nf {
+
+struct EwLayerMeta {
+  int kind;
+  int64_t theta_off;
+};
+
+// fnn(in, hdims, out; output_activation) of reference src/flows/utils.jl:71-100.
+// dims = [in, h1, ..., out]; Dense i has W (dims[i+1] x dims[i], column major in theta == row-major
+// [dims[i]][dims[i+1]]) at w_off[i] and bias at b_off[i].
+struct MLPDesc {
+  std::vector<int> dims;
+  std::vector<int64_t> w_off, b_off;   // absolute offsets into theta
+  int out_act = 0;                     // 0 none, 1 tanh
+  int n_dense() const { return (int)dims.size() - 1; }
+  int64_t n_params() const {
+    int64_t n = 0;
+    for (int i = 0; i + 1 < (int)dims.size(); ++i) n += (int64_t)dims[i] * dims[i + 1] + dims[i + 1];
+    return n;
+  }
+};
+
+struct LayerDesc {
+  int kind = 0;
+  int64_t theta_off = 0, n_params = 0;
+  // couplings (PartitionMask, App. A.3): idx1 = transformed coordinates, idx2 = sorted complement
+  std::vector<int> idx1, idx2;
+  int* d_idx1 = nullptr;
+  int* d_idx2 = nullptr;
+  std::vector<MLPDesc> mlps;           // affine: {s, t}; spline: {nn}
+  int K = 0;
+  double B = 0;
+};
+
+struct Workspace {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+};
+
+struct Flow {
+  int dim = 0, dtype = NF_F32, device = 0;
+  std::vector<LayerDesc> layers;
+  int64_t P = 0;
+  bool all_elementwise = true, any_elementwise = false;
+  int mma_mode = NF_MMA_SIMT;
+  size_t ws_limit = (size_t)64 << 30;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0;
+
+  // base distribution q0 = MvNormal(mu, Diagonal(sigma^2))
+  bool base_is_standard = true;
+  std::vector<double> base_mu, base_sigma;
+  void* d_base = nullptr;              // dtype[2*dim]: mu then sigma
+  double base_c0 = 0;
+
+  // elementwise-path metadata
+  EwLayerMeta* d_ew_meta = nullptr;
+  int* d_ew_kinds = nullptr;
+
+  // persistent device buffers
+  void* d_theta = nullptr;             // dtype[P]
+  double* d_gsum = nullptr;            // double[P+1] un-normalised gradient sums + ELBO sum
+  void* d_out = nullptr;               // dtype[P+1] scaled outputs
+  void* h_pinned = nullptr;            // pinned staging (P+1 of dtype + 1 double)
+  size_t h_pinned_bytes = 0;
+
+  Workspace ws;
+  void ws_reset() { ws.off = 0; }
+  void* ws_alloc(size_t bytes);        // bump allocation, 256 B aligned; nullptr (+error) when exhausted
+  int ws_reserve(size_t bytes);        // make sure capacity >= bytes (reallocates; invalidates pointers)
+
+  // layered path: chunk size chosen by general_plan_workspace, opaque per-flow state
+  int64_t chunk_N = 0;
+  void* gen_state = nullptr;
+
+  // state kept by nf_forward_stash for nf_backward
+  int64_t stash_N = 0;
+
+  size_t esize() const { return dtype == NF_F64 ? 8 : 4; }
+};
+
+struct Target {
+  int kind = 0, dim = 0;
+  std::vector<double> p;
+  double c0 = 0;
+  void* d_vec_f32 = nullptr;
+  void* d_vec_f64 = nullptr;
+  template <typename T> TargetParams<T> params() const {
+    TargetParams<T> tp;
+    tp.kind = kind; tp.dim = dim;
+    tp.p0 = p.size() > 0 ? (T)p[0] : T(0);
+    tp.p1 = p.size() > 1 ? (T)p[1] : T(0);
+    tp.c0 = (T)c0;
+    tp.vec = (const T*)(sizeof(T) == 4 ? d_vec_f32 : d_vec_f64);
+    return tp;
+  }
+};
+
+// elementwise.cu
+template <typename T>
+int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
+           bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev);
+
+}  // namespace nf

@@ -1,0 +1,512 @@
+// Layered execution of flows with coupling layers: orchestrates per-layer kernels over sample chunks.
+//
+//   ELBO  (reference src/objectives/elbo.jl:65-70,89-92):  x0 -> [layers, last first] -> y ; head ; backward sweep
+//   LOGLIK(reference src/objectives/loglikelihood.jl:26-33): y -> [inverse layers, first first] -> x0 ; head ; backward
+//
+// Conditioner MLPs (fnn, reference src/flows/utils.jl:71-100) run either on the CUDA-core GEMM
+// (NF_MMA_SIMT: Float64 flows and validation) or on the tcgen05 GEMM of tc_gemm.cu (Float32).
+#include "general.hpp"
+#include "kernels_coupling.cuh"
+#include "tc_gemm.hpp"
+
+namespace nf {
+
+namespace {
+
+struct LayerBufs {
+  void* act0 = nullptr;                       // gathered conditioner input x2 [n, cbar]
+  std::vector<std::vector<void*>> acts;       // acts[m][i-1] = output of Dense i-1 (post activation), i = 1..n_dense
+};
+
+struct Chunk {
+  int64_t n = 0;
+  bool stash = false;
+  std::vector<void*> X;                       // stash: L+1 states; else input + 2 ping-pong buffers
+  void* xin(int state) const { return stash ? X[state] : (state == 0 ? X[0] : X[1 + ((state - 1) & 1)]); }
+  void* xout(int state) const { return stash ? X[state + 1] : X[1 + (state & 1)]; }
+  void* ld = nullptr;
+  void* G = nullptr;
+  void* gld = nullptr;                        // optional per-sample d/dlogdet (two-phase API)
+  std::vector<LayerBufs> lb;                  // stash: one per layer; else a single shared set at [0]
+  void* ga[3] = {nullptr, nullptr, nullptr};  // backward temporaries (width = max MLP width)
+  int n_states = 0;
+};
+
+struct GenState {
+  Chunk stash_chunk;     // kept alive between nf_forward_stash and nf_backward
+  bool has_stash = false;
+};
+
+inline bool is_coupling(int kind) { return kind == NF_AFFINE_COUPLING || kind == NF_SPLINE_COUPLING; }
+
+int max_width(const Flow& f) {
+  int w = 1;
+  for (auto& L : f.layers)
+    for (auto& m : L.mlps)
+      for (int v : m.dims) w = std::max(w, v);
+  return w;
+}
+
+// bytes of one activation buffer holding `width` features for n samples
+size_t act_bytes(const Flow& f, int64_t n, int width, bool final_out) {
+  if (f.mma_mode == NF_MMA_SIMT || final_out) return (size_t)n * width * f.esize();
+  return tc_act_bytes(n, width);
+}
+
+size_t per_sample_bytes(const Flow& f, bool stash) {
+  const size_t es = f.esize();
+  const int L = (int)f.layers.size();
+  size_t b = 0;
+  b += (size_t)(stash ? L + 1 : 3) * f.dim * es;   // X
+  b += 2 * es;                                      // ld, gld
+  b += (size_t)f.dim * es;                          // G
+  size_t layer_max = 0, layer_sum = 0;
+  for (auto& Ld : f.layers) {
+    if (!is_coupling(Ld.kind)) continue;
+    size_t lbts = act_bytes(f, 1024, (int)Ld.idx2.size(), false);
+    for (auto& m : Ld.mlps)
+      for (int i = 1; i < (int)m.dims.size(); ++i) lbts += act_bytes(f, 1024, m.dims[i], i + 1 == (int)m.dims.size());
+    layer_sum += lbts;
+    layer_max = std::max(layer_max, lbts);
+  }
+  b += (stash ? layer_sum : layer_max) / 1024 + 1;
+  b += 3 * act_bytes(f, 1024, max_width(f), false) / 1024 + 3 * (size_t)max_width(f) * es;
+  return b;
+}
+
+int alloc_chunk(Flow& f, Chunk& c, int64_t n, bool stash, const void* x0_alias) {
+  const size_t es = f.esize();
+  const int L = (int)f.layers.size();
+  c.n = n; c.stash = stash;
+  c.n_states = stash ? L + 1 : 3;
+  c.X.assign(c.n_states, nullptr);
+  for (int i = 0; i < c.n_states; ++i) {
+    if (i == 0 && x0_alias) { c.X[0] = const_cast<void*>(x0_alias); continue; }
+    c.X[i] = f.ws_alloc((size_t)n * f.dim * es);
+    if (!c.X[i]) return NF_ERR_OOM;
+  }
+  c.ld = f.ws_alloc((size_t)n * es);
+  c.G = f.ws_alloc((size_t)n * f.dim * es);
+  if (!c.ld || !c.G) return NF_ERR_OOM;
+  const int nlb = stash ? L : 1;
+  c.lb.assign(nlb, LayerBufs());
+  if (stash) {
+    for (int li = 0; li < L; ++li) {
+      const LayerDesc& Ld = f.layers[li];
+      if (!is_coupling(Ld.kind)) continue;
+      LayerBufs& b = c.lb[li];
+      b.act0 = f.ws_alloc(act_bytes(f, n, (int)Ld.idx2.size(), false));
+      if (!b.act0) return NF_ERR_OOM;
+      b.acts.resize(Ld.mlps.size());
+      for (size_t m = 0; m < Ld.mlps.size(); ++m) {
+        const MLPDesc& md = Ld.mlps[m];
+        for (int i = 1; i < (int)md.dims.size(); ++i) {
+          void* p = f.ws_alloc(act_bytes(f, n, md.dims[i], i + 1 == (int)md.dims.size()));
+          if (!p) return NF_ERR_OOM;
+          b.acts[m].push_back(p);
+        }
+      }
+    }
+  } else {
+    // one shared set sized for the widest layer
+    LayerBufs& b = c.lb[0];
+    int cb = 1; size_t nm = 0; std::vector<std::vector<int>> w;
+    for (auto& Ld : f.layers) {
+      if (!is_coupling(Ld.kind)) continue;
+      cb = std::max(cb, (int)Ld.idx2.size());
+      nm = std::max(nm, Ld.mlps.size());
+    }
+    b.act0 = f.ws_alloc(act_bytes(f, n, cb, false));
+    if (!b.act0) return NF_ERR_OOM;
+    b.acts.resize(nm);
+    for (size_t m = 0; m < nm; ++m) {
+      size_t nd = 0;
+      for (auto& Ld : f.layers) if (m < Ld.mlps.size()) nd = std::max(nd, Ld.mlps[m].dims.size() - 1);
+      for (size_t i = 1; i <= nd; ++i) {
+        size_t bytes = 0;
+        for (auto& Ld : f.layers)
+          if (m < Ld.mlps.size() && i < Ld.mlps[m].dims.size()) {
+            bytes = std::max(bytes, act_bytes(f, n, Ld.mlps[m].dims[i], false));
+            bytes = std::max(bytes, act_bytes(f, n, Ld.mlps[m].dims[i], true));
+          }
+        void* p = f.ws_alloc(bytes);
+        if (!p) return NF_ERR_OOM;
+        b.acts[m].push_back(p);
+      }
+    }
+  }
+  return NF_OK;
+}
+
+int alloc_backward_tmps(Flow& f, Chunk& c) {
+  const int mw = max_width(f);
+  for (int i = 0; i < 3; ++i) {
+    size_t bytes = std::max(act_bytes(f, c.n, mw, false), (size_t)c.n * mw * f.esize());
+    c.ga[i] = f.ws_alloc(bytes);
+    if (!c.ga[i]) return NF_ERR_OOM;
+  }
+  return NF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core MLP forward / backward
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool TA, bool TB, typename Epi>
+int launch_simt_gemm(Flow& f, const T* A, int64_t lda, const T* B, int64_t ldb, int64_t M, int N, int64_t K, int64_t ksplit,
+                     const Epi& epi) {
+  if (ksplit <= 0) ksplit = K;
+  dim3 grid((unsigned)ceil_div(M, 64), (unsigned)ceil_div(N, 64), (unsigned)ceil_div(K, ksplit));
+  simt_gemm_kernel<T, TA, TB, Epi><<<grid, 256, 0, f.stream>>>(A, lda, B, ldb, M, N, K, ksplit, epi);
+  NF_LAUNCH_CHECK();
+  return NF_OK;
+}
+
+template <typename T>
+int simt_mlp_forward(Flow& f, const MLPDesc& md, const T* theta, int64_t n, const T* act0, std::vector<void*>& acts) {
+  const T* in = act0;
+  const int nd = md.n_dense();
+  for (int i = 0; i < nd; ++i) {
+    T* out = (T*)acts[i];
+    const int act = (i + 1 < nd) ? ACT_LRELU : (md.out_act ? ACT_TANH : ACT_NONE);
+    EpiBiasAct<T> epi{out, md.dims[i + 1], theta + md.b_off[i], act};
+    NF_TRY((launch_simt_gemm<T, false, false>(f, in, md.dims[i], theta + md.w_off[i], md.dims[i + 1], n, md.dims[i + 1],
+                                              md.dims[i], 0, epi)));
+    in = out;
+  }
+  return NF_OK;
+}
+
+// g_last: gradient w.r.t. the pre-activation of the last Dense [n, out].  Accumulates parameter
+// gradient sums into gsum (theta order) and scatter-adds the conditioner-input gradient into G[:, idx2].
+template <typename T>
+int simt_mlp_backward(Flow& f, const MLPDesc& md, const T* theta, int64_t n, const T* act0, std::vector<void*>& acts,
+                      T* g_last, T* tmp0, T* tmp1, T* G, int d, const int* d_idx2, double* gsum) {
+  const int nd = md.n_dense();
+  T* g = g_last;
+  for (int i = nd - 1; i >= 0; --i) {
+    const T* in = (i == 0) ? act0 : (const T*)acts[i - 1];
+    const int kin = md.dims[i], kout = md.dims[i + 1];
+    {
+      const int64_t rpb = 512;
+      colsum_atomic_kernel<T><<<(unsigned)ceil_div(n, rpb), 256, 0, f.stream>>>(g, n, kout, rpb, gsum + md.b_off[i]);
+      NF_LAUNCH_CHECK();
+    }
+    {  // wgrad: dWt[k][o] = sum_n in[n][k] g[n][o]
+      EpiAtomicDouble<T> epi{gsum + md.w_off[i], kout};
+      NF_TRY((launch_simt_gemm<T, true, false>(f, in, kin, g, kout, kin, kout, n, 2048, epi)));
+    }
+    if (i > 0) {  // dgrad into hidden: gin[n][k] = (sum_o g[n][o] Wt[k][o]) * lrelu'(h[n][k])
+      T* gin = (g == tmp0) ? tmp1 : tmp0;
+      EpiMaskLrelu<T> epi{gin, kin, in, kin};
+      NF_TRY((launch_simt_gemm<T, false, true>(f, g, kout, theta + md.w_off[i], kout, n, kin, kout, 0, epi)));
+      g = gin;
+    } else {
+      EpiScatterAdd<T> epi{G, d, d_idx2};
+      NF_TRY((launch_simt_gemm<T, false, true>(f, g, kout, theta + md.w_off[i], kout, n, kin, kout, 0, epi)));
+    }
+  }
+  return NF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one coupling layer, forward (INV = false: y = T(x)) or inverse direction
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool INV>
+int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, int64_t n, const T* Xin, T* Xout, T* ld,
+                   int32_t* bins) {
+  const int d = f.dim, c = (int)Ld.idx1.size(), cbar = (int)Ld.idx2.size();
+  const bool tc = f.mma_mode != NF_MMA_SIMT;
+  if (tc) {
+    NF_TRY(tc_gather_split(f, (const float*)Xin, d, Ld.d_idx2, cbar, n, b.act0));
+    for (size_t m = 0; m < Ld.mlps.size(); ++m) NF_TRY(tc_mlp_forward(f, Ld, (int)m, n, b.act0, b.acts[m]));
+  } else {
+    gather_cols_kernel<T><<<(unsigned)ceil_div(n * cbar, 256), 256, 0, f.stream>>>(Xin, d, Ld.d_idx2, cbar, n, (T*)b.act0);
+    NF_LAUNCH_CHECK();
+    for (size_t m = 0; m < Ld.mlps.size(); ++m) NF_TRY(simt_mlp_forward<T>(f, Ld.mlps[m], theta, n, (const T*)b.act0, b.acts[m]));
+  }
+  if (Ld.kind == NF_AFFINE_COUPLING) {
+    affine_apply_kernel<T, INV><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
+        Xin, (const T*)b.acts[0].back(), (const T*)b.acts[1].back(), Ld.d_idx1, c, d, n, Xout, ld);
+  } else {
+    rqs_apply_kernel<T, INV><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
+        Xin, (const T*)b.acts[0].back(), Ld.d_idx1, c, d, Ld.K, (T)Ld.B, n, Xout, ld, bins);
+  }
+  NF_LAUNCH_CHECK();
+  return NF_OK;
+}
+
+template <typename T, bool INV>
+int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, Chunk& c, const T* Xin, const T* Xout) {
+  const int d = f.dim, cc = (int)Ld.idx1.size();
+  const int64_t n = c.n;
+  const bool tc = f.mma_mode != NF_MMA_SIMT;
+  T* G = (T*)c.G;
+  const T* gld = (const T*)c.gld;
+  T* gA = (T*)c.ga[0];
+  T* gB = (T*)c.ga[1];
+  T* gC = (T*)c.ga[2];
+  if (Ld.kind == NF_AFFINE_COUPLING) {
+    // gA <- d/d(pre-tanh s), gB <- d/dt
+    affine_bwd_kernel<T, INV><<<(unsigned)ceil_div(n * cc, 256), 256, 0, f.stream>>>(
+        G, INV ? Xout : Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, n, gA, gB);
+    NF_LAUNCH_CHECK();
+    if (tc) {
+      NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, c.ga[2], (float*)G, f.d_gsum));
+      NF_TRY(tc_mlp_backward(f, Ld, 1, n, b.act0, b.acts[1], (float*)gB, c.ga[2], (float*)G, f.d_gsum));
+    } else {
+      // s network: temporaries gC + (gA after it has been consumed is NOT safe) -> use a dedicated pair
+      NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gA, G, d, Ld.d_idx2, f.d_gsum));
+      NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[1], theta, n, (const T*)b.act0, b.acts[1], gB, gC, gB, G, d, Ld.d_idx2, f.d_gsum));
+    }
+  } else {
+    rqs_bwd_kernel<T, INV><<<(unsigned)ceil_div(n * cc, 128), 128, 0, f.stream>>>(
+        G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA);
+    NF_LAUNCH_CHECK();
+    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, c.ga[2], (float*)G, f.d_gsum));
+    else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, G, d, Ld.d_idx2, f.d_gsum));
+  }
+  return NF_OK;
+}
+
+template <typename T>
+int check_supported(const Flow& f) {
+  for (auto& L : f.layers)
+    if (!is_coupling(L.kind)) {
+      set_error("flows mixing elementwise layers (planar/radial/shift/scale) with coupling layers are not supported in this build");
+      return NF_ERR_UNSUPPORTED;
+    }
+  return NF_OK;
+}
+
+// forward sweep of one chunk (application order: last layer first).  Leaves the result in c.X[last].
+template <typename T>
+int sweep_forward(Flow& f, Chunk& c, const T* theta, int32_t* bins, int64_t bins_chunk_off, int64_t N_total) {
+  const int L = (int)f.layers.size();
+  NF_CUDA(cudaMemsetAsync(c.ld, 0, (size_t)c.n * sizeof(T), f.stream));
+  int state = 0;
+  int64_t bins_layer_off = 0;   // bins layout [spline layer in application order][N_total][c]
+  for (int li = L - 1; li >= 0; --li) {
+    const LayerDesc& Ld = f.layers[li];
+    LayerBufs& b = c.stash ? c.lb[li] : c.lb[0];
+    const T* Xin = (const T*)c.xin(state);
+    T* Xout = (T*)c.xout(state);
+    int32_t* bl = nullptr;
+    if (bins && Ld.kind == NF_SPLINE_COUPLING) {
+      bl = bins + bins_layer_off + bins_chunk_off * (int64_t)Ld.idx1.size();
+      bins_layer_off += N_total * (int64_t)Ld.idx1.size();
+    }
+    NF_TRY((coupling_apply<T, false>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, bl)));
+    ++state;
+  }
+  return NF_OK;
+}
+
+// inverse sweep (first layer first).
+template <typename T>
+int sweep_inverse(Flow& f, Chunk& c, const T* theta) {
+  const int L = (int)f.layers.size();
+  NF_CUDA(cudaMemsetAsync(c.ld, 0, (size_t)c.n * sizeof(T), f.stream));
+  int state = 0;
+  for (int li = 0; li < L; ++li) {
+    const LayerDesc& Ld = f.layers[li];
+    LayerBufs& b = c.stash ? c.lb[li] : c.lb[0];
+    const T* Xin = (const T*)c.xin(state);
+    T* Xout = (T*)c.xout(state);
+    NF_TRY((coupling_apply<T, true>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, nullptr)));
+    ++state;
+  }
+  return NF_OK;
+}
+
+template <typename T>
+int sweep_backward_fwd(Flow& f, Chunk& c, const T* theta) {   // backward of the forward sweep
+  const int L = (int)f.layers.size();
+  int state = L;
+  for (int li = 0; li < L; ++li) {   // layer 0 was applied last
+    NF_TRY((coupling_backward<T, false>(f, f.layers[li], c.lb[li], theta, c, (const T*)c.X[state - 1], (const T*)c.X[state])));
+    --state;
+  }
+  return NF_OK;
+}
+
+template <typename T>
+int sweep_backward_inv(Flow& f, Chunk& c, const T* theta) {   // backward of the inverse sweep
+  const int L = (int)f.layers.size();
+  int state = L;
+  for (int li = L - 1; li >= 0; --li) {   // layer L-1's inverse was applied last
+    NF_TRY((coupling_backward<T, true>(f, f.layers[li], c.lb[li], theta, c, (const T*)c.X[state - 1], (const T*)c.X[state])));
+    --state;
+  }
+  return NF_OK;
+}
+
+template <typename T>
+int run_typed(Flow& f, const GeneralJob& job) {
+  NF_TRY(check_supported<T>(f));
+  const T* theta = (const T*)job.theta_dev;
+  const int d = f.dim, L = (int)f.layers.size();
+  const int64_t N = job.N;
+  const bool grad = job.want_grad;
+  const bool stash = grad || job.op == OP_FORWARD_STASH;
+  const int64_t Nc = std::min<int64_t>(N, f.chunk_N > 0 ? f.chunk_N : N);
+  if (job.op == OP_FORWARD_STASH) NF_REQUIRE(Nc >= N, "nf_forward_stash: batch of %lld does not fit the workspace limit", (long long)N);
+  if (job.op == OP_ELBO || job.op == OP_LOGLIK) NF_CUDA(cudaMemsetAsync(f.d_gsum, 0, (f.P + 1) * sizeof(double), f.stream));
+  if (f.mma_mode != NF_MMA_SIMT) NF_TRY(tc_prepare_weights(f, (const float*)theta));
+  const T* base = f.base_is_standard ? nullptr : (const T*)f.d_base;
+  const size_t ws_mark = f.ws.off;
+  for (int64_t c0 = 0; c0 < N; c0 += Nc) {
+    const int64_t n = std::min(Nc, N - c0);
+    f.ws.off = ws_mark;
+    Chunk c;
+    const T* in = job.in_dev ? (const T*)job.in_dev + c0 * d : nullptr;
+    NF_TRY(alloc_chunk(f, c, n, stash, in));
+    if (!in) {
+      base_sample_kernel<T><<<(unsigned)ceil_div(n * d, 256), 256, 0, f.stream>>>((T*)c.X[0], base, d, n, job.seed, c0);
+      NF_LAUNCH_CHECK();
+    }
+    const int last = stash ? L : 1 + ((L - 1) & 1);
+    switch (job.op) {
+      case OP_ELBO: {
+        NF_REQUIRE(job.tgt, "ELBO needs a target");
+        NF_TRY(sweep_forward<T>(f, c, theta, nullptr, 0, N));
+        T* terms = job.terms_out ? (T*)job.terms_out + c0 : nullptr;
+        elbo_head_kernel<T><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
+            (const T*)c.X[last], (const T*)c.X[0], (const T*)c.ld, job.tgt->params<T>(), base, (T)f.base_c0, d, n,
+            (T*)c.G, terms, f.d_gsum + f.P);
+        NF_LAUNCH_CHECK();
+        if (grad) {
+          NF_TRY(alloc_backward_tmps(f, c));
+          NF_TRY(sweep_backward_fwd<T>(f, c, theta));
+        }
+        break;
+      }
+      case OP_LOGLIK: {
+        NF_TRY(sweep_inverse<T>(f, c, theta));
+        T* terms = job.terms_out ? (T*)job.terms_out + c0 : nullptr;
+        loglik_head_kernel<T><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
+            (const T*)c.X[last], (const T*)c.ld, base, (T)f.base_c0, d, n, grad ? (T*)c.G : nullptr, terms, f.d_gsum + f.P);
+        NF_LAUNCH_CHECK();
+        if (grad) {
+          NF_TRY(alloc_backward_tmps(f, c));
+          NF_TRY(sweep_backward_inv<T>(f, c, theta));
+        }
+        break;
+      }
+      case OP_FORWARD:
+      case OP_FORWARD_STASH:
+      case OP_INVERSE: {
+        if (job.op == OP_INVERSE) NF_TRY(sweep_inverse<T>(f, c, theta));
+        else NF_TRY(sweep_forward<T>(f, c, theta, job.bins_out, c0, N));
+        if (job.y_out)
+          NF_CUDA(cudaMemcpyAsync((T*)job.y_out + c0 * d, c.X[last], (size_t)n * d * sizeof(T), cudaMemcpyDeviceToDevice, f.stream));
+        if (job.ld_out)
+          NF_CUDA(cudaMemcpyAsync((T*)job.ld_out + c0, c.ld, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, f.stream));
+        if (job.op == OP_FORWARD_STASH) {
+          GenState* gs = (GenState*)f.gen_state;
+          if (!gs) { gs = new GenState(); f.gen_state = gs; }
+          gs->stash_chunk = c;
+          gs->has_stash = true;
+        }
+        break;
+      }
+      default:
+        set_error("unknown op %d", job.op);
+        return NF_ERR_INVALID;
+    }
+  }
+  return NF_OK;
+}
+
+template <typename T>
+int backward_from_stash_typed(Flow& f, const void* gy_host, const void* gld_host) {
+  GenState* gs = (GenState*)f.gen_state;
+  NF_REQUIRE(gs && gs->has_stash, "no stashed forward pass");
+  Chunk& c = gs->stash_chunk;
+  const size_t es = sizeof(T);
+  NF_CUDA(cudaMemsetAsync(f.d_gsum, 0, (f.P + 1) * sizeof(double), f.stream));
+  NF_CUDA(cudaMemcpyAsync(c.G, gy_host, (size_t)c.n * f.dim * es, cudaMemcpyHostToDevice, f.stream));
+  c.gld = f.ws_alloc((size_t)c.n * es);
+  if (!c.gld) return NF_ERR_OOM;
+  if (gld_host) NF_CUDA(cudaMemcpyAsync(c.gld, gld_host, (size_t)c.n * es, cudaMemcpyHostToDevice, f.stream));
+  else NF_CUDA(cudaMemsetAsync(c.gld, 0, (size_t)c.n * es, f.stream));
+  NF_TRY(alloc_backward_tmps(f, c));
+  if (f.mma_mode != NF_MMA_SIMT) NF_TRY(tc_prepare_weights(f, (const float*)f.d_theta));
+  NF_TRY(sweep_backward_fwd<T>(f, c, (const T*)f.d_theta));
+  gs->has_stash = false;
+  return NF_OK;
+}
+
+}  // namespace
+
+int general_plan_workspace(Flow& f, int op, int64_t N, size_t extra_bytes) {
+  if (f.all_elementwise) {
+    f.chunk_N = N;
+    return f.ws_reserve(extra_bytes + ((size_t)16 << 20));
+  }
+  const bool stash = (op == OP_ELBO || op == OP_LOGLIK || op == OP_FORWARD_STASH);
+  const size_t per = per_sample_bytes(f, stash);
+  const size_t fixed = extra_bytes + ((size_t)32 << 20) + tc_weight_bytes(f);
+  size_t budget = f.ws_limit > fixed ? f.ws_limit - fixed : 0;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    const size_t avail = free_b + f.ws.cap;
+    const size_t cap = avail > fixed + ((size_t)1 << 30) ? avail - fixed - ((size_t)1 << 30) : avail / 2;
+    budget = std::min(budget, cap);
+  }
+  int64_t Nc = (int64_t)(budget / per);
+  if (Nc >= N) Nc = N;
+  else {
+    Nc = (Nc / 1024) * 1024;
+    NF_REQUIRE(Nc >= 1024, "workspace limit too small: %zu B per sample, budget %zu B", per, budget);
+  }
+  f.chunk_N = Nc;
+  return f.ws_reserve(fixed + per * (size_t)(Nc + 1024));
+}
+
+int general_run(Flow& f, const GeneralJob& job) {
+  if (f.all_elementwise) {
+    set_error("operation %d is not implemented for purely elementwise (planar/radial) flows in this build", job.op);
+    return NF_ERR_UNSUPPORTED;
+  }
+  return f.dtype == NF_F32 ? run_typed<float>(f, job) : run_typed<double>(f, job);
+}
+
+int general_backward_from_stash(Flow& f, const void* gy_host, const void* gld_host) {
+  return f.dtype == NF_F32 ? backward_from_stash_typed<float>(f, gy_host, gld_host)
+                           : backward_from_stash_typed<double>(f, gy_host, gld_host);
+}
+
+void general_release(Flow& f) {
+  delete (GenState*)f.gen_state;
+  f.gen_state = nullptr;
+  tc_release(f);
+}
+
+int base_sample_dev(Flow& f, int64_t N, uint64_t seed, void* z_dev) {
+  const int d = f.dim;
+  if (f.dtype == NF_F32)
+    base_sample_kernel<float><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>((float*)z_dev, f.base_is_standard ? nullptr : (const float*)f.d_base, d, N, seed, 0);
+  else
+    base_sample_kernel<double><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>((double*)z_dev, f.base_is_standard ? nullptr : (const double*)f.d_base, d, N, seed, 0);
+  NF_LAUNCH_CHECK();
+  return NF_OK;
+}
+
+int rqs_bin_search_host(int dtype, const void* knots_host, const void* v_host, int64_t M, int K, int32_t* bins_out) {
+  const size_t es = dtype == NF_F64 ? 8 : 4;
+  void *dk = nullptr, *dv = nullptr;
+  int32_t* db = nullptr;
+  NF_CUDA(cudaMalloc(&dk, (size_t)M * (K + 1) * es));
+  NF_CUDA(cudaMalloc(&dv, (size_t)M * es));
+  NF_CUDA(cudaMalloc((void**)&db, (size_t)M * sizeof(int32_t)));
+  NF_CUDA(cudaMemcpy(dk, knots_host, (size_t)M * (K + 1) * es, cudaMemcpyHostToDevice));
+  NF_CUDA(cudaMemcpy(dv, v_host, (size_t)M * es, cudaMemcpyHostToDevice));
+  if (dtype == NF_F64) rqs_bin_search_kernel<double><<<(unsigned)ceil_div(M, 256), 256>>>((const double*)dk, (const double*)dv, M, K, db);
+  else rqs_bin_search_kernel<float><<<(unsigned)ceil_div(M, 256), 256>>>((const float*)dk, (const float*)dv, M, K, db);
+  NF_LAUNCH_CHECK();
+  NF_CUDA(cudaMemcpy(bins_out, db, (size_t)M * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  cudaFree(dk); cudaFree(dv); cudaFree(db);
+  return NF_OK;
+}
+
+}  // namespace nf

@@ -1,0 +1,479 @@
+// Device kernels of the layered coupling path: CUDA-core GEMMs with fused epilogues (the Float64 /
+// validation mainloop; Float32 flows use the tcgen05 mainloop of tc_gemm.cu), the affine-coupling
+// and rational-quadratic-spline elementwise kernels, target / base kernels.
+//
+// Reference rows: a8 fnn/Dense (src/flows/utils.jl:71-100), a11 AffineCoupling
+// (src/flows/realnvp.jl:57-110), a12/a13 NeuralSplineCoupling + MonotonicSplines RQS
+// (src/flows/neuralspline.jl:65-140; App. A.4), a14 PartitionMask, a15 base logpdf, a16 targets.
+#pragma once
+#include "common.cuh"
+#include "targets.cuh"
+
+namespace nf {
+
+// ---------------------------------------------------------------------------------------------
+// epilogues of the CUDA-core GEMM:  C(m, n) = sum_k A(m, k) B(k, n)
+// ---------------------------------------------------------------------------------------------
+enum : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_TANH = 2 };
+
+template <typename T> struct EpiBiasAct {       // Dense forward: act(W x + b)
+  T* C; int ldc; const T* bias; int act;
+  __device__ __forceinline__ void operator()(int64_t m, int n, T v) const {
+    v += bias[n];
+    if (act == ACT_LRELU) v = v > 0 ? v : T(0.01) * v;
+    else if (act == ACT_TANH) v = Num<T>::tanh(v);
+    C[m * ldc + n] = v;
+  }
+};
+template <typename T> struct EpiMaskLrelu {     // dgrad into a hidden layer: multiply by leakyrelu'(h)
+  T* C; int ldc; const T* ref; int ldr;
+  __device__ __forceinline__ void operator()(int64_t m, int n, T v) const {
+    C[m * ldc + n] = ref[m * ldr + n] > 0 ? v : T(0.01) * v;
+  }
+};
+template <typename T> struct EpiScatterAdd {    // dgrad into the conditioner input: G[:, idx2] += .
+  T* G; int ldg; const int* idx;
+  __device__ __forceinline__ void operator()(int64_t m, int n, T v) const { G[m * ldg + idx[n]] += v; }
+};
+template <typename T> struct EpiAtomicDouble {  // wgrad partial -> double accumulators in theta order
+  double* g; int ldg;
+  __device__ __forceinline__ void operator()(int64_t m, int n, T v) const { atomicAdd(&g[m * ldg + n], (double)v); }
+};
+
+template <typename T, bool TA, bool TB, typename Epi>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B,
+                                                        int64_t ldb, int64_t M, int N, int64_t K, int64_t ksplit, Epi epi) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ T As[BK][BM + 4];
+  __shared__ T Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * ksplit;
+  const int64_t kend = kbeg + ksplit < K ? kbeg + ksplit : K;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int mm, kk;
+      if (TA) { mm = e & 63; kk = e >> 6; } else { kk = e & 15; mm = e >> 4; }
+      const int64_t gm = m0 + mm, gk = k0 + kk;
+      T v = 0;
+      if (gm < M && gk < kend) v = TA ? A[gk * lda + gm] : A[gm * lda + gk];
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int nn, kk;
+      if (TB) { kk = e & 15; nn = e >> 4; } else { nn = e & 63; kk = e >> 6; }
+      const int gn = n0 + nn;
+      const int64_t gk = k0 + kk;
+      T v = 0;
+      if (gn < N && gk < kend) v = TB ? B[(int64_t)gn * ldb + gk] : B[gk * ldb + gn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t m = m0 + ty * 4 + i;
+      const int n = n0 + tx * 4 + j;
+      if (m < M && n < N) epi(m, n, acc[i][j]);
+    }
+}
+
+// column sums of g [N x n] -> double atomics (bias gradients)
+template <typename T>
+__global__ void colsum_atomic_kernel(const T* __restrict__ g, int64_t N, int n, int64_t rows_per_block, double* __restrict__ out) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < N ? r0 + rows_per_block : N;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    T s = 0;
+    for (int64_t r = r0; r < r1; ++r) s += g[r * n + c];
+    atomicAdd(&out[c], (double)s);
+  }
+}
+
+template <typename T>
+__global__ void gather_cols_kernel(const T* __restrict__ X, int d, const int* __restrict__ idx, int n, int64_t N, T* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * n) return;
+  const int64_t r = e / n;
+  const int k = (int)(e - r * n);
+  out[e] = X[r * d + idx[k]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// AffineCoupling (reference src/flows/realnvp.jl:57-110)
+//   forward : y1 = exp(s) .* x1 .+ t,  logjac = sum(s)            (:77-83)
+//   inverse : x1 = (y1 .- t) .* exp.(-s), logjac = -sum(s)        (:99-110)
+// S holds s AFTER the tanh output activation (|s| < 1), Tt holds t.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool INV>
+__global__ void affine_apply_kernel(const T* __restrict__ Xin, const T* __restrict__ S, const T* __restrict__ Tt,
+                                    const int* __restrict__ idx1, int c, int d, int64_t N, T* __restrict__ Xout,
+                                    T* __restrict__ ld) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const T* xi = Xin + r * d;
+  T* xo = Xout + r * d;
+  for (int j = 0; j < d; ++j) xo[j] = xi[j];
+  T sum = 0;
+  for (int k = 0; k < c; ++k) {
+    const T s = S[r * c + k], t = Tt[r * c + k];
+    const int j = idx1[k];
+    if (!INV) xo[j] = Num<T>::exp(s) * xi[j] + t;
+    else xo[j] = (xi[j] - t) * Num<T>::exp(-s);
+    sum += s;
+  }
+  if (ld) ld[r] += INV ? -sum : sum;
+}
+
+// Backward of the coupling arithmetic.  In: G = d/dXout (in place -> d/dXin on idx1 columns; the idx2
+// columns receive the conditioner contribution later), gld = d/dlogdet per sample (nullptr -> 1).
+// Out: gS = gradient w.r.t. the PRE-tanh output of the s network, gT = gradient w.r.t. t.
+// X1src: Xin for the forward direction (x1), Xout for the inverse direction (x1 = output).
+template <typename T, bool INV>
+__global__ void affine_bwd_kernel(T* __restrict__ G, const T* __restrict__ X1src, const T* __restrict__ S,
+                                  const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int64_t N,
+                                  T* __restrict__ gS, T* __restrict__ gT) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * c) return;
+  const int64_t r = e / c;
+  const int k = (int)(e - r * c);
+  const int j = idx1[k];
+  const T s = S[e];
+  const T go = G[r * d + j];
+  const T x1 = X1src[r * d + j];
+  const T gl = gld ? gld[r] : T(1);
+  T gs, gt, gi;
+  if (!INV) {
+    const T es = Num<T>::exp(s);
+    gi = go * es; gs = go * x1 * es + gl; gt = go;
+  } else {
+    const T ems = Num<T>::exp(-s);
+    gi = go * ems; gt = -gi; gs = -go * x1 - gl;
+  }
+  G[r * d + j] = gi;
+  gS[e] = gs * (1 - s * s);   // through tanh
+  gT[e] = gt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rational-quadratic spline coupling (MonotonicSplines v0.3.3 semantics)
+// theta_raw row layout per sample: coordinate i owns rows [i*(3K-1), (i+1)*(3K-1)) = K width logits,
+// K height logits, K-1 derivative logits ("block" layout; see oracle RQS_PARAM_LAYOUT).
+// Knots: sequential left-to-right softmax sum and cumsum, knot = (2B)*cumsum - B with no FMA contraction.
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+template <typename T> __device__ __forceinline__ T add_rn(T a, T b);
+template <> __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+template <typename T> __device__ __forceinline__ T div_rn(T a, T b);
+template <> __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+template <> __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+template <typename T> struct RqsBin {
+  int k;            // searchsortedfirst - 1 : number of knots strictly below v; inside iff 1 <= k <= K
+  T x0, x1, y0, y1, d0, d1;
+  T cx0, cx1, cy0, cy1;   // cumulative softmax mass at the two knots (for the softmax backward)
+  T Sw, Sh;               // softmax denominators
+};
+
+// Locate the bin of v along `logits_search` (widths for forward, heights for inverse) and fetch the
+// matching knots of the other family plus the two derivatives.
+template <typename T, bool INV>
+__device__ __forceinline__ void rqs_locate(const T* __restrict__ tw, const T* __restrict__ th, const T* __restrict__ td,
+                                           int K, T B, T v, RqsBin<T>& b) {
+  using N = Num<T>;
+  const T* ts = INV ? th : tw;   // searched family
+  const T* to = INV ? tw : th;   // other family
+  T Ss = 0, So = 0;
+  for (int k = 0; k < K; ++k) { Ss = add_rn(Ss, N::exp(ts[k])); So = add_rn(So, N::exp(to[k])); }
+  const T twoB = 2 * B;
+  T cs = 0, prev = -B, prevc = 0;
+  int bin = K + 1;
+  T s0 = 0, s1 = 0, c0 = 0, c1 = 0;
+  if (!(prev < v)) { bin = 0; }
+  else {
+    for (int k = 1; k <= K; ++k) {
+      cs = add_rn(cs, div_rn(N::exp(ts[k - 1]), Ss));
+      const T knot = add_rn(mul_rn(twoB, cs), -B);
+      if (!(knot < v)) { bin = k; s0 = prev; s1 = knot; c0 = prevc; c1 = cs; break; }
+      prev = knot; prevc = cs;
+    }
+  }
+  b.k = bin;
+  if (bin < 1 || bin > K) return;
+  // other family's knots bin-1, bin
+  T co = 0, o0 = -B, o1 = 0, oc0 = 0, oc1 = 0;
+  for (int k = 1; k <= bin; ++k) {
+    co = add_rn(co, div_rn(N::exp(to[k - 1]), So));
+    const T knot = add_rn(mul_rn(twoB, co), -B);
+    if (k == bin - 1) { o0 = knot; oc0 = co; }
+    if (k == bin) { o1 = knot; oc1 = co; }
+  }
+  if (!INV) { b.x0 = s0; b.x1 = s1; b.cx0 = c0; b.cx1 = c1; b.y0 = o0; b.y1 = o1; b.cy0 = oc0; b.cy1 = oc1; b.Sw = Ss; b.Sh = So; }
+  else      { b.y0 = s0; b.y1 = s1; b.cy0 = c0; b.cy1 = c1; b.x0 = o0; b.x1 = o1; b.cx0 = oc0; b.cx1 = oc1; b.Sh = Ss; b.Sw = So; }
+  // derivatives: d[0] = d[K] = 1, d[j] = log(exp(td[j-1]) + 1)
+  b.d0 = (bin - 1 == 0) ? T(1) : N::log(N::exp(td[bin - 2]) + 1);
+  b.d1 = (bin == K) ? T(1) : N::log(N::exp(td[bin - 1]) + 1);
+}
+
+template <typename T>
+__device__ __forceinline__ void rqs_eval_fwd(const RqsBin<T>& b, T x, T& y, T& lj) {
+  using N = Num<T>;
+  const T dx = b.x1 - b.x0, dy = b.y1 - b.y0;
+  const T s = dy / dx;
+  const T xi = (x - b.x0) / dx, om = 1 - xi;
+  const T den = s + (b.d1 + b.d0 - 2 * s) * xi * om;
+  y = b.y0 + dy * (s * xi * xi + b.d0 * xi * om) / den;
+  lj = N::log(N::abs(s * s * (b.d1 * xi * xi + 2 * s * xi * om + b.d0 * om * om))) - 2 * N::log(N::abs(den));
+}
+
+template <typename T>
+__device__ __forceinline__ void rqs_eval_inv(const RqsBin<T>& b, T y, T& x, T& lj, T& xi_out) {
+  using N = Num<T>;
+  const T dx = b.x1 - b.x0, dy = b.y1 - b.y0;
+  const T s = dy / dx;
+  const T yr = y - b.y0;
+  const T t = b.d1 + b.d0 - 2 * s;
+  const T qa = dy * (s - b.d0) + yr * t;
+  const T qb = dy * b.d0 - yr * t;
+  const T qc = -s * yr;
+  const T xi = 2 * qc / (-qb - N::sqrt(qb * qb - 4 * qa * qc));
+  const T om = 1 - xi;
+  const T den = s + t * xi * om;
+  x = xi * dx + b.x0;
+  lj = -(N::log(N::abs(s * s * (b.d1 * xi * xi + 2 * s * xi * om + b.d0 * om * om))) - 2 * N::log(N::abs(den)));
+  xi_out = xi;
+}
+
+// one thread per sample; loops over the c transformed coordinates
+template <typename T, bool INV>
+__global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict__ raw, const int* __restrict__ idx1,
+                                 int c, int d, int K, T B, int64_t N, T* __restrict__ Xout, T* __restrict__ ld,
+                                 int32_t* __restrict__ bins) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const int P3 = 3 * K - 1;
+  const T* xi = Xin + r * d;
+  T* xo = Xout + r * d;
+  for (int j = 0; j < d; ++j) xo[j] = xi[j];
+  T sum = 0;
+  for (int i = 0; i < c; ++i) {
+    const T* tw = raw + (r * c + i) * P3;
+    const T v = xi[idx1[i]];
+    RqsBin<T> b;
+    rqs_locate<T, INV>(tw, tw + K, tw + 2 * K, K, B, v, b);
+    if (bins) bins[r * c + i] = b.k;
+    if (b.k >= 1 && b.k <= K) {
+      T o, lj, tmp;
+      if (!INV) rqs_eval_fwd(b, v, o, lj); else rqs_eval_inv(b, v, o, lj, tmp);
+      xo[idx1[i]] = o;
+      sum += lj;
+    }
+  }
+  if (ld) ld[r] += sum;
+}
+
+// Backward of the spline coupling arithmetic: G (in place on idx1 columns) and graw = d/dtheta_raw.
+// Vsrc = the spline input (Xin): x1 for forward, y1 for inverse.
+template <typename T, bool INV>
+__global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restrict__ raw,
+                               const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int K, T B,
+                               int64_t N, T* __restrict__ graw) {
+  using Nm = Num<T>;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * c) return;
+  const int64_t r = e / c;
+  const int i = (int)(e - r * c);
+  const int P3 = 3 * K - 1;
+  const T* tw = raw + e * P3;
+  const T* th = tw + K;
+  const T* td = tw + 2 * K;
+  T* gw = graw + e * P3;
+  T* gh = gw + K;
+  T* gd = gw + 2 * K;
+  for (int k = 0; k < P3; ++k) gw[k] = 0;
+  const int j = idx1[i];
+  const T v = Vsrc[r * d + j];
+  const T go = G[r * d + j];
+  const T gl = gld ? gld[r] : T(1);
+  RqsBin<T> b;
+  rqs_locate<T, INV>(tw, th, td, K, B, v, b);
+  if (b.k < 1 || b.k > K) return;   // identity tail: dy/dx = 1, no parameter gradient; G unchanged
+  const T dx = b.x1 - b.x0, dy = b.y1 - b.y0;
+  const T s = dy / dx;
+  T x, xi;
+  if (!INV) { x = v; xi = (x - b.x0) / dx; }
+  else { T lj_; rqs_eval_inv(b, v, x, lj_, xi); }
+  const T om = 1 - xi;
+  const T tt = b.d1 + b.d0 - 2 * s;
+  const T den = s + tt * xi * om;
+  const T num = s * xi * xi + b.d0 * xi * om;
+  const T q = b.d1 * xi * xi + 2 * s * xi * om + b.d0 * om * om;
+  // d(logJ)/d(xi) at fixed parameters
+  const T lj_xi = (2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om) / q - 2 * tt * (om - xi) / den;
+  T gy, glj;       // effective upstream gradients on the FORWARD map y = F(x), logJ(x)
+  T g_in = 0;      // gradient w.r.t. the spline input
+  if (!INV) {
+    gy = go; glj = gl;
+  } else {
+    // x = F^{-1}(y): dx/dy = 1/F_x, dx/dparams = -F_params/F_x, lj_inv = -lj(x(y, p), p)
+    // L = go*x - gl*lj(x,p):  dL/dy = (go - gl*lj_x)/F_x =: a,  dL/dp = -a*F_p - gl*lj_p
+    const T Fx = s * s * q / (den * den);
+    const T a = (go - gl * (lj_xi / dx)) / Fx;
+    gy = -a; glj = -gl; g_in = a;
+  }
+  // accumulate gradients of  gy*y + glj*lj  w.r.t. (x0,x1,y0,y1,d0,d1) and xi
+  T g_y0 = gy, g_dy = gy * num / den;
+  const T g_num = gy * dy / den;
+  T g_den = -gy * dy * num / (den * den) - 2 * glj / den;
+  T g_s = 2 * glj / s;
+  const T g_q = glj / q;
+  T g_d1 = g_q * xi * xi, g_d0 = g_q * om * om;
+  g_s += g_q * 2 * xi * om;
+  T g_xi = g_q * (2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om);
+  g_s += g_num * xi * xi; g_d0 += g_num * xi * om; g_xi += g_num * (2 * s * xi + b.d0 * (om - xi));
+  g_s += g_den * (1 - 2 * xi * om); g_d1 += g_den * xi * om; g_d0 += g_den * xi * om; g_xi += g_den * tt * (om - xi);
+  T g_x0 = -g_xi / dx, g_dx = -g_xi * xi / dx;
+  if (!INV) g_in = g_xi / dx;
+  g_dy += g_s / dx; g_dx += -g_s * s / dx;
+  const T g_y1 = g_dy; g_y0 -= g_dy;
+  const T g_x1 = g_dx; g_x0 -= g_dx;
+  G[r * d + j] = g_in;
+  // knots -> logits: X_j = 2B c_j - B, c_j = sum_{k<=j} p_k, p = softmax(t)
+  const T twoB = 2 * B;
+  {
+    const T a0 = (b.k - 1 >= 1) ? g_x0 : T(0);   // knot 0 is the constant -B
+    const T a1 = g_x1;
+    const T dotp = twoB * (a0 * b.cx0 + a1 * b.cx1);
+    for (int k = 1; k <= K; ++k) {
+      const T p = Nm::exp(tw[k - 1]) / b.Sw;
+      const T gp = twoB * ((k <= b.k - 1 ? a0 : T(0)) + (k <= b.k ? a1 : T(0)));
+      gw[k - 1] = p * (gp - dotp);
+    }
+  }
+  {
+    const T a0 = (b.k - 1 >= 1) ? g_y0 : T(0);
+    const T a1 = g_y1;
+    const T dotp = twoB * (a0 * b.cy0 + a1 * b.cy1);
+    for (int k = 1; k <= K; ++k) {
+      const T p = Nm::exp(th[k - 1]) / b.Sh;
+      const T gp = twoB * ((k <= b.k - 1 ? a0 : T(0)) + (k <= b.k ? a1 : T(0)));
+      gh[k - 1] = p * (gp - dotp);
+    }
+  }
+  if (b.k - 1 >= 1) { const T ex = Nm::exp(td[b.k - 2]); gd[b.k - 2] = g_d0 * ex / (ex + 1); }
+  if (b.k <= K - 1) { const T ex = Nm::exp(td[b.k - 1]); gd[b.k - 1] = g_d1 * ex / (ex + 1); }
+}
+
+template <typename T>
+__global__ void rqs_bin_search_kernel(const T* __restrict__ knots, const T* __restrict__ v, int64_t M, int K, int32_t* __restrict__ bins) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M) return;
+  const T* kn = knots + e * (K + 1);
+  int k = 0;
+  for (int i = 0; i <= K; ++i) k += (kn[i] < v[e]) ? 1 : 0;
+  bins[e] = k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// objective heads
+// ---------------------------------------------------------------------------------------------
+// ELBO head (reference src/objectives/elbo.jl:65-70): term = logp(y) - logq0(x0) + logdet; G = dlogp/dy.
+template <typename T>
+__global__ void elbo_head_kernel(const T* __restrict__ Y, const T* __restrict__ X0, const T* __restrict__ ld,
+                                 TargetParams<T> tp, const T* __restrict__ base, T base_c0, int d, int64_t N,
+                                 T* __restrict__ G, T* __restrict__ terms, double* __restrict__ sum_out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double term = 0;
+  if (r < N) {
+    const T lp = target_logp_score<T, 0>(tp, Y + r * d, G + r * d);
+    T q = 0;
+    for (int k = 0; k < d; ++k) {
+      const T u = base ? (X0[r * d + k] - base[k]) / base[d + k] : X0[r * d + k];
+      q += u * u;
+    }
+    const T t = lp - (base_c0 - q / 2) + ld[r];
+    if (terms) terms[r] = t;
+    term = (double)t;
+  }
+  term = warp_sum(term);
+  __shared__ double sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) s += sh[w];
+    atomicAdd(sum_out, s);
+  }
+}
+
+// log-likelihood head (reference src/objectives/loglikelihood.jl:26-33 via Bijectors logpdf):
+// term = logq0(x0) + logdet_inv; G = dlogq0/dx0.
+template <typename T>
+__global__ void loglik_head_kernel(const T* __restrict__ X0, const T* __restrict__ ld, const T* __restrict__ base,
+                                   T base_c0, int d, int64_t N, T* __restrict__ G, T* __restrict__ terms,
+                                   double* __restrict__ sum_out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double term = 0;
+  if (r < N) {
+    T q = 0;
+    for (int k = 0; k < d; ++k) {
+      const T is = base ? 1 / base[d + k] : T(1);
+      const T u = base ? (X0[r * d + k] - base[k]) * is : X0[r * d + k];
+      q += u * u;
+      if (G) G[r * d + k] = -u * is;
+    }
+    const T t = (base_c0 - q / 2) + ld[r];
+    if (terms) terms[r] = t;
+    term = (double)t;
+  }
+  term = warp_sum(term);
+  __shared__ double sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) s += sh[w];
+    atomicAdd(sum_out, s);
+  }
+}
+
+// K7: base draws x = mu + sigma .* randn  (reference ext/NormalizingFlowsCUDAExt.jl:43-48)
+template <typename T>
+__global__ void base_sample_kernel(T* __restrict__ Z, const T* __restrict__ base, int d, int64_t N, uint64_t seed, int64_t row0) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * d) return;
+  const int k = (int)(e % d);
+  T z = philox_randn<T>(seed, (uint64_t)(row0 * d + e));
+  if (base) z = z * base[d + k] + base[k];
+  Z[e] = z;
+}
+
+}  // namespace nf

@@ -1,0 +1,612 @@
+// libnfcuda C ABI (include/nfcuda.h): handle management, host<->device staging, dispatch.
+#include "flow.hpp"
+#include "general.hpp"
+#include <cstring>
+#include <mutex>
+
+namespace nf {
+
+static thread_local std::string g_last_error;
+thread_local int64_t g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+void* Flow::ws_alloc(size_t bytes) {
+  const size_t a = (ws.off + 255) & ~(size_t)255;
+  if (a + bytes > ws.cap) {
+    set_error("workspace exhausted: need %zu B at offset %zu, capacity %zu B", bytes, a, ws.cap);
+    return nullptr;
+  }
+  ws.off = a + bytes;
+  return ws.base + a;
+}
+
+int Flow::ws_reserve(size_t bytes) {
+  if (bytes <= ws.cap) return NF_OK;
+  if (ws.base) { NF_CUDA(cudaStreamSynchronize(stream)); NF_CUDA(cudaFree(ws.base)); ws.base = nullptr; ws.cap = 0; }
+  bytes = (size_t)round_up((int64_t)bytes, 1 << 20);
+  NF_CUDA(cudaMalloc((void**)&ws.base, bytes));
+  ws.cap = bytes;
+  return NF_OK;
+}
+
+template <typename T>
+__global__ void scale_out_kernel(const double* __restrict__ gsum, int64_t n, double factor, T* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (T)(gsum[i] * factor);
+}
+
+static int check_device() {
+  int dev = 0;
+  NF_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  NF_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("libnfcuda is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+    return NF_ERR_CUDA;
+  }
+  return NF_OK;
+}
+
+static int build_mlp(MLPDesc& m, int n_in, const int* hdims, int n_hidden, int n_out, int out_act, int64_t& off) {
+  m.dims.clear();
+  m.dims.push_back(n_in);
+  for (int i = 0; i < n_hidden; ++i) {
+    NF_REQUIRE(hdims[i] > 0, "hidden width must be positive");
+    m.dims.push_back(hdims[i]);
+  }
+  m.dims.push_back(n_out);
+  m.out_act = out_act;
+  for (int i = 0; i + 1 < (int)m.dims.size(); ++i) {
+    m.w_off.push_back(off); off += (int64_t)m.dims[i] * m.dims[i + 1];
+    m.b_off.push_back(off); off += m.dims[i + 1];
+  }
+  return NF_OK;
+}
+
+static int upload_base(Flow& f) {
+  const int d = f.dim;
+  f.base_is_standard = true;
+  double c0 = -0.5 * d * NF_LOG2PI;
+  for (int k = 0; k < d; ++k) {
+    if (f.base_mu[k] != 0.0 || f.base_sigma[k] != 1.0) f.base_is_standard = false;
+    c0 -= std::log(f.base_sigma[k]);
+  }
+  f.base_c0 = c0;
+  if (!f.d_base) NF_CUDA(cudaMalloc(&f.d_base, 2 * d * sizeof(double)));
+  if (f.dtype == NF_F32) {
+    std::vector<float> h(2 * d);
+    for (int k = 0; k < d; ++k) { h[k] = (float)f.base_mu[k]; h[d + k] = (float)f.base_sigma[k]; }
+    NF_CUDA(cudaMemcpy(f.d_base, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  } else {
+    std::vector<double> h(2 * d);
+    for (int k = 0; k < d; ++k) { h[k] = f.base_mu[k]; h[d + k] = f.base_sigma[k]; }
+    NF_CUDA(cudaMemcpy(f.d_base, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return NF_OK;
+}
+
+static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers, int dim, int dtype) {
+  NF_REQUIRE(out && descs, "null argument");
+  NF_REQUIRE(n_layers > 0 && dim > 0, "need at least one layer and dim > 0");
+  NF_REQUIRE(dtype == NF_F32 || dtype == NF_F64, "dtype must be NF_F32 or NF_F64");
+  NF_TRY(check_device());
+  std::unique_ptr<Flow> f(new Flow());
+  f->dim = dim; f->dtype = dtype;
+  NF_CUDA(cudaGetDevice(&f->device));
+  int64_t off = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    const nf_layer_desc& ds = descs[i];
+    LayerDesc L;
+    L.kind = ds.kind; L.theta_off = off;
+    switch (ds.kind) {
+      case NF_PLANAR: off += 2 * dim + 1; f->any_elementwise = true; break;
+      case NF_RADIAL: off += dim + 2; f->any_elementwise = true; break;
+      case NF_SHIFT: case NF_SCALE: off += dim; f->any_elementwise = true; break;
+      case NF_AFFINE_COUPLING: case NF_SPLINE_COUPLING: {
+        f->all_elementwise = false;
+        NF_REQUIRE(ds.mask_idx && ds.n_mask > 0 && ds.n_mask < dim, "layer %d: coupling needs 0 < n_mask < dim", i);
+        NF_REQUIRE(ds.hdims && ds.n_hidden > 0, "layer %d: coupling needs hidden widths", i);
+        std::vector<char> used(dim, 0);
+        for (int k = 0; k < ds.n_mask; ++k) {
+          NF_REQUIRE(ds.mask_idx[k] >= 0 && ds.mask_idx[k] < dim && !used[ds.mask_idx[k]], "layer %d: bad mask index", i);
+          used[ds.mask_idx[k]] = 1;
+          L.idx1.push_back(ds.mask_idx[k]);
+        }
+        for (int k = 0; k < dim; ++k) if (!used[k]) L.idx2.push_back(k);
+        const int c = ds.n_mask, cbar = dim - c;
+        if (ds.kind == NF_AFFINE_COUPLING) {
+          L.mlps.resize(2);
+          NF_TRY(build_mlp(L.mlps[0], cbar, ds.hdims, ds.n_hidden, c, 1, off));   // s: ... tanh (realnvp.jl:50)
+          NF_TRY(build_mlp(L.mlps[1], cbar, ds.hdims, ds.n_hidden, c, 0, off));   // t          (realnvp.jl:51)
+        } else {
+          NF_REQUIRE(ds.K >= 2 && ds.B > 0, "layer %d: spline needs K >= 2 and B > 0", i);
+          NF_REQUIRE(ds.K <= 64, "layer %d: K <= 64 supported", i);
+          L.K = ds.K; L.B = ds.B;
+          L.mlps.resize(1);
+          NF_TRY(build_mlp(L.mlps[0], cbar, ds.hdims, ds.n_hidden, (3 * ds.K - 1) * c, 0, off));  // neuralspline.jl:55-56
+        }
+        NF_CUDA(cudaMalloc((void**)&L.d_idx1, c * sizeof(int)));
+        NF_CUDA(cudaMalloc((void**)&L.d_idx2, cbar * sizeof(int)));
+        NF_CUDA(cudaMemcpy(L.d_idx1, L.idx1.data(), c * sizeof(int), cudaMemcpyHostToDevice));
+        NF_CUDA(cudaMemcpy(L.d_idx2, L.idx2.data(), cbar * sizeof(int), cudaMemcpyHostToDevice));
+        break;
+      }
+      default:
+        set_error("layer %d: unknown kind %d", i, ds.kind);
+        return NF_ERR_INVALID;
+    }
+    L.n_params = off - L.theta_off;
+    f->layers.push_back(std::move(L));
+  }
+  f->P = off;
+  f->mma_mode = (dtype == NF_F32) ? NF_MMA_BF16X3 : NF_MMA_SIMT;
+  if (const char* e = getenv("NFCUDA_MMA")) {
+    if (!strcmp(e, "simt")) f->mma_mode = NF_MMA_SIMT;
+    else if (!strcmp(e, "bf16x1") && dtype == NF_F32) f->mma_mode = NF_MMA_BF16X1;
+    else if (!strcmp(e, "bf16x3") && dtype == NF_F32) f->mma_mode = NF_MMA_BF16X3;
+  }
+  NF_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  NF_CUDA(cudaEventCreate(&f->ev0));
+  NF_CUDA(cudaEventCreate(&f->ev1));
+  f->base_mu.assign(dim, 0.0);
+  f->base_sigma.assign(dim, 1.0);
+  NF_TRY(upload_base(*f));
+  {
+    std::vector<EwLayerMeta> meta(n_layers);
+    std::vector<int> kinds(n_layers);
+    for (int i = 0; i < n_layers; ++i) { meta[i].kind = f->layers[i].kind; meta[i].theta_off = f->layers[i].theta_off; kinds[i] = f->layers[i].kind; }
+    NF_CUDA(cudaMalloc((void**)&f->d_ew_meta, n_layers * sizeof(EwLayerMeta)));
+    NF_CUDA(cudaMalloc((void**)&f->d_ew_kinds, n_layers * sizeof(int)));
+    NF_CUDA(cudaMemcpy(f->d_ew_meta, meta.data(), n_layers * sizeof(EwLayerMeta), cudaMemcpyHostToDevice));
+    NF_CUDA(cudaMemcpy(f->d_ew_kinds, kinds.data(), n_layers * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  const size_t es = f->esize();
+  NF_CUDA(cudaMalloc(&f->d_theta, (f->P + 1) * es));
+  NF_CUDA(cudaMalloc((void**)&f->d_gsum, (f->P + 1) * sizeof(double)));
+  NF_CUDA(cudaMalloc(&f->d_out, (f->P + 1) * es));
+  f->h_pinned_bytes = (f->P + 1) * es + 64;
+  NF_CUDA(cudaMallocHost(&f->h_pinned, f->h_pinned_bytes));
+  NF_TRY(f->ws_reserve((size_t)8 << 20));
+  *out = reinterpret_cast<nf_flow_t>(f.release());
+  return NF_OK;
+}
+
+static void flow_destroy(Flow* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  general_release(*f);
+  for (auto& L : f->layers) { cudaFree(L.d_idx1); cudaFree(L.d_idx2); }
+  cudaFree(f->d_base); cudaFree(f->d_ew_meta); cudaFree(f->d_ew_kinds);
+  cudaFree(f->d_theta); cudaFree(f->d_gsum); cudaFree(f->d_out); cudaFreeHost(f->h_pinned);
+  cudaFree(f->ws.base);
+  if (f->ev0) cudaEventDestroy(f->ev0);
+  if (f->ev1) cudaEventDestroy(f->ev1);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+// One objective / transform evaluation on device buffers.
+struct Job {
+  int op = OP_ELBO;
+  const Target* tgt = nullptr;
+  const void* theta_dev = nullptr;
+  const void* in_dev = nullptr;       // z0 / x / y; nullptr -> device Philox draws (OP_ELBO / OP_FORWARD)
+  int64_t N = 0;
+  uint64_t seed = 0;
+  bool want_grad = false;
+  void* y_out = nullptr;              // [N, d]
+  void* ld_out = nullptr;             // [N]
+  void* terms_out = nullptr;          // [N]
+  int32_t* bins_out = nullptr;
+};
+
+// Runs the job; leaves un-normalised sums in f.d_gsum (gradient sums [0,P), objective sum at [P]).
+static int run_job(Flow& f, const Job& j) {
+  NF_REQUIRE(j.N > 0, "N must be positive");
+  if (f.all_elementwise && (j.op == OP_ELBO || j.op == OP_FORWARD)) {
+    if (f.dtype == NF_F32)
+      return ew_run<float>(f, j.tgt, j.theta_dev, j.N, j.in_dev, j.seed, j.want_grad, j.y_out, j.ld_out, j.terms_out,
+                           j.op == OP_ELBO ? f.d_gsum : nullptr);
+    return ew_run<double>(f, j.tgt, j.theta_dev, j.N, j.in_dev, j.seed, j.want_grad, j.y_out, j.ld_out, j.terms_out,
+                          j.op == OP_ELBO ? f.d_gsum : nullptr);
+  }
+  GeneralJob g;
+  g.op = j.op; g.tgt = j.tgt; g.theta_dev = j.theta_dev; g.in_dev = j.in_dev; g.N = j.N; g.seed = j.seed;
+  g.want_grad = j.want_grad; g.y_out = j.y_out; g.ld_out = j.ld_out; g.terms_out = j.terms_out; g.bins_out = j.bins_out;
+  return general_run(f, g);
+}
+
+static int scale_outputs(Flow& f, double factor, void* out_dev, int64_t n) {
+  const int threads = 256;
+  const int blocks = (int)ceil_div(n, threads);
+  if (f.dtype == NF_F32) scale_out_kernel<float><<<blocks, threads, 0, f.stream>>>(f.d_gsum, n, factor, (float*)out_dev);
+  else scale_out_kernel<double><<<blocks, threads, 0, f.stream>>>(f.d_gsum, n, factor, (double*)out_dev);
+  NF_LAUNCH_CHECK();
+  return NF_OK;
+}
+
+// value+grad with everything already on the device
+static int value_and_grad_dev(Flow& f, int op, const Target* tgt, const void* theta_dev, int64_t N, const void* in_dev,
+                              uint64_t seed, double scale, double* value_out, void* grad_dev_out) {
+  Job j;
+  j.op = op; j.tgt = tgt; j.theta_dev = theta_dev; j.in_dev = in_dev; j.N = N; j.seed = seed;
+  j.want_grad = grad_dev_out != nullptr;
+  NF_CUDA(cudaEventRecord(f.ev0, f.stream));
+  NF_TRY(run_job(f, j));
+  const double factor = scale / (double)N;
+  if (grad_dev_out) NF_TRY(scale_outputs(f, factor, grad_dev_out, f.P));
+  NF_CUDA(cudaEventRecord(f.ev1, f.stream));
+  double vsum = 0;
+  NF_CUDA(cudaMemcpyAsync(&vsum, f.d_gsum + f.P, sizeof(double), cudaMemcpyDeviceToHost, f.stream));
+  NF_CUDA(cudaStreamSynchronize(f.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, f.ev0, f.ev1);
+  f.last_ms = ms;
+  if (value_out) *value_out = vsum * factor;
+  return NF_OK;
+}
+
+static int value_and_grad_host(Flow& f, int op, const Target* tgt, const void* theta_host, int64_t N, const void* in_host,
+                               uint64_t seed, double scale, double* value_out, void* grad_host_out) {
+  NF_REQUIRE(theta_host, "theta is null");
+  NF_REQUIRE(N > 0, "N must be positive");
+  NF_CUDA(cudaSetDevice(f.device));
+  const size_t es = f.esize();
+  f.ws_reset();
+  const size_t in_bytes = in_host ? (size_t)N * f.dim * es : 0;
+  NF_TRY(general_plan_workspace(f, op, N, in_bytes));
+  NF_CUDA(cudaMemcpyAsync(f.d_theta, theta_host, f.P * es, cudaMemcpyHostToDevice, f.stream));
+  void* in_dev = nullptr;
+  if (in_host) {
+    in_dev = f.ws_alloc(in_bytes);
+    if (!in_dev) return NF_ERR_OOM;
+    NF_CUDA(cudaMemcpyAsync(in_dev, in_host, in_bytes, cudaMemcpyHostToDevice, f.stream));
+  }
+  NF_TRY(value_and_grad_dev(f, op, tgt, f.d_theta, N, in_dev, seed, scale, value_out, grad_host_out ? f.d_out : nullptr));
+  if (grad_host_out) {
+    NF_CUDA(cudaMemcpyAsync(f.h_pinned, f.d_out, f.P * es, cudaMemcpyDeviceToHost, f.stream));
+    NF_CUDA(cudaStreamSynchronize(f.stream));
+    memcpy(grad_host_out, f.h_pinned, f.P * es);
+  }
+  return NF_OK;
+}
+
+// forward / inverse / logpdf style calls with host buffers
+static int transform_host(Flow& f, int op, const Target* tgt, const void* theta_host, int64_t N, const void* in_host,
+                          uint64_t seed, void* y_host, void* ld_host, void* terms_host, int32_t* bins_host, size_t bins_count) {
+  NF_REQUIRE(theta_host, "theta is null");
+  NF_REQUIRE(N > 0, "N must be positive");
+  NF_CUDA(cudaSetDevice(f.device));
+  const size_t es = f.esize();
+  f.ws_reset();
+  const size_t mat = (size_t)N * f.dim * es, vec = (size_t)N * es;
+  NF_TRY(general_plan_workspace(f, op, N, 2 * mat + 2 * vec + bins_count * sizeof(int32_t) + 4096));
+  NF_CUDA(cudaMemcpyAsync(f.d_theta, theta_host, f.P * es, cudaMemcpyHostToDevice, f.stream));
+  Job j;
+  j.op = op; j.tgt = tgt; j.theta_dev = f.d_theta; j.N = N; j.seed = seed;
+  if (in_host) {
+    void* in_dev = f.ws_alloc(mat);
+    if (!in_dev) return NF_ERR_OOM;
+    NF_CUDA(cudaMemcpyAsync(in_dev, in_host, mat, cudaMemcpyHostToDevice, f.stream));
+    j.in_dev = in_dev;
+  }
+  if (y_host) { j.y_out = f.ws_alloc(mat); if (!j.y_out) return NF_ERR_OOM; }
+  if (ld_host) { j.ld_out = f.ws_alloc(vec); if (!j.ld_out) return NF_ERR_OOM; }
+  if (terms_host) { j.terms_out = f.ws_alloc(vec); if (!j.terms_out) return NF_ERR_OOM; }
+  if (bins_host) { j.bins_out = (int32_t*)f.ws_alloc(bins_count * sizeof(int32_t)); if (!j.bins_out) return NF_ERR_OOM; }
+  NF_TRY(run_job(f, j));
+  if (y_host) NF_CUDA(cudaMemcpyAsync(y_host, j.y_out, mat, cudaMemcpyDeviceToHost, f.stream));
+  if (ld_host) NF_CUDA(cudaMemcpyAsync(ld_host, j.ld_out, vec, cudaMemcpyDeviceToHost, f.stream));
+  if (terms_host) NF_CUDA(cudaMemcpyAsync(terms_host, j.terms_out, vec, cudaMemcpyDeviceToHost, f.stream));
+  if (bins_host) NF_CUDA(cudaMemcpyAsync(bins_host, j.bins_out, bins_count * sizeof(int32_t), cudaMemcpyDeviceToHost, f.stream));
+  NF_CUDA(cudaStreamSynchronize(f.stream));
+  return NF_OK;
+}
+
+}  // namespace nf
+
+using namespace nf;
+
+#define NF_FLOW(h) (*reinterpret_cast<nf::Flow*>(h))
+#define NF_CHECK_HANDLE(h)                                  \
+  do {                                                      \
+    if (!(h)) { nf::set_error("null handle"); return NF_ERR_INVALID; } \
+  } while (0)
+
+extern "C" {
+
+int nf_version(void) { return NFCUDA_VERSION; }
+const char* nf_last_error(void) { return g_last_error.c_str(); }
+
+int nf_device_count(int* count) {
+  NF_REQUIRE(count, "null argument");
+  NF_CUDA(cudaGetDeviceCount(count));
+  return NF_OK;
+}
+
+int nf_init(int device) {
+  int n = 0;
+  NF_CUDA(cudaGetDeviceCount(&n));
+  NF_REQUIRE(device >= 0 && device < n, "device %d out of range (found %d CUDA devices)", device, n);
+  NF_CUDA(cudaSetDevice(device));
+  return check_device();
+}
+
+int nf_synchronize(void) {
+  NF_CUDA(cudaDeviceSynchronize());
+  return NF_OK;
+}
+
+int nf_flow_create(nf_flow_t* out, const nf_layer_desc* layers, int n_layers, int dim, int dtype) {
+  return flow_create(out, layers, n_layers, dim, dtype);
+}
+void nf_flow_destroy(nf_flow_t flow) { flow_destroy(reinterpret_cast<Flow*>(flow)); }
+int64_t nf_flow_num_params(nf_flow_t flow) { return flow ? NF_FLOW(flow).P : -1; }
+int nf_flow_dim(nf_flow_t flow) { return flow ? NF_FLOW(flow).dim : -1; }
+int64_t nf_flow_param_offset(nf_flow_t flow, int layer) {
+  if (!flow || layer < 0 || layer >= (int)NF_FLOW(flow).layers.size()) return -1;
+  return NF_FLOW(flow).layers[layer].theta_off;
+}
+
+int nf_flow_set_base(nf_flow_t flow, const double* mu, const double* sigma) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  NF_CUDA(cudaSetDevice(f.device));
+  for (int k = 0; k < f.dim; ++k) {
+    f.base_mu[k] = mu ? mu[k] : 0.0;
+    f.base_sigma[k] = sigma ? sigma[k] : 1.0;
+    NF_REQUIRE(f.base_sigma[k] > 0, "base sigma must be positive");
+  }
+  return upload_base(f);
+}
+
+int nf_flow_set_mma_mode(nf_flow_t flow, int mode) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  NF_REQUIRE(mode == NF_MMA_SIMT || mode == NF_MMA_BF16X3 || mode == NF_MMA_BF16X1, "unknown mma mode %d", mode);
+  NF_REQUIRE(f.dtype == NF_F32 || mode == NF_MMA_SIMT, "Float64 flows only support NF_MMA_SIMT");
+  f.mma_mode = mode;
+  return NF_OK;
+}
+
+int nf_flow_set_workspace_limit(nf_flow_t flow, size_t bytes) {
+  NF_CHECK_HANDLE(flow);
+  NF_REQUIRE(bytes >= ((size_t)64 << 20), "workspace limit must be at least 64 MiB");
+  NF_FLOW(flow).ws_limit = bytes;
+  return NF_OK;
+}
+
+int nf_target_create(nf_target_t* out, int kind, int dim, const double* params, int n_params) {
+  NF_REQUIRE(out, "null argument");
+  NF_REQUIRE(dim > 0, "dim must be positive");
+  std::unique_ptr<Target> t(new Target());
+  t->kind = kind; t->dim = dim;
+  for (int i = 0; i < n_params; ++i) t->p.push_back(params[i]);
+  switch (kind) {
+    case NF_TARGET_BANANA:
+      NF_REQUIRE(n_params == 2 && dim >= 2 && params[1] > 0, "Banana(dim>=2; b, var>0)");
+      t->c0 = -(std::log(params[1]) / dim + NF_LOG2PI) * dim / 2;
+      break;
+    case NF_TARGET_FUNNEL:
+      NF_REQUIRE(n_params == 2 && dim >= 2 && params[1] > 0, "Funnel(dim>=2; mu, sigma>0)");
+      t->c0 = -0.5 * NF_LOG2PI - std::log(params[1]) - (dim - 1) / 2.0 * NF_LOG2PI;
+      break;
+    case NF_TARGET_WARPED_GAUSS:
+      NF_REQUIRE(n_params == 2 && dim == 2 && params[0] > 0 && params[1] > 0, "WarpedGauss(dim=2; sigma1>0, sigma2>0)");
+      t->c0 = -NF_LOG2PI - std::log(params[0]) - std::log(params[1]);
+      break;
+    case NF_TARGET_CROSS:
+      NF_REQUIRE(n_params == 2 && dim % 2 == 0 && params[1] > 0, "Cross(dim even; mu, sigma>0)");
+      t->c0 = (dim / 2) * (std::log(0.25) - NF_LOG2PI - std::log(params[1]));
+      break;
+    case NF_TARGET_DIAG_NORMAL: {
+      NF_REQUIRE(n_params == 2 * dim, "DiagNormal needs mu[dim], sigma[dim]");
+      double c0 = -0.5 * dim * NF_LOG2PI;
+      std::vector<float> hf(2 * dim);
+      for (int k = 0; k < dim; ++k) {
+        NF_REQUIRE(params[dim + k] > 0, "sigma must be positive");
+        c0 -= std::log(params[dim + k]);
+      }
+      for (int k = 0; k < 2 * dim; ++k) hf[k] = (float)params[k];
+      t->c0 = c0;
+      NF_CUDA(cudaMalloc(&t->d_vec_f32, 2 * dim * sizeof(float)));
+      NF_CUDA(cudaMalloc(&t->d_vec_f64, 2 * dim * sizeof(double)));
+      NF_CUDA(cudaMemcpy(t->d_vec_f32, hf.data(), 2 * dim * sizeof(float), cudaMemcpyHostToDevice));
+      NF_CUDA(cudaMemcpy(t->d_vec_f64, params, 2 * dim * sizeof(double), cudaMemcpyHostToDevice));
+      break;
+    }
+    default:
+      set_error("unknown target kind %d", kind);
+      return NF_ERR_INVALID;
+  }
+  *out = reinterpret_cast<nf_target_t>(t.release());
+  return NF_OK;
+}
+
+void nf_target_destroy(nf_target_t target) {
+  Target* t = reinterpret_cast<Target*>(target);
+  if (!t) return;
+  cudaFree(t->d_vec_f32); cudaFree(t->d_vec_f64);
+  delete t;
+}
+
+static int check_target(const Flow& f, const Target* t) {
+  NF_REQUIRE(t, "null target");
+  NF_REQUIRE(t->dim == f.dim, "target dim %d != flow dim %d", t->dim, f.dim);
+  return NF_OK;
+}
+
+int nf_elbo_value_and_grad(nf_flow_t flow, nf_target_t target, const void* theta_host, int64_t N, const void* z0_host,
+                           uint64_t seed, double scale, double* value_out, void* grad_host_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  const Target* t = reinterpret_cast<Target*>(target);
+  NF_TRY(check_target(f, t));
+  return value_and_grad_host(f, OP_ELBO, t, theta_host, N, z0_host, seed, scale, value_out, grad_host_out);
+}
+
+int nf_elbo_value_and_grad_dev(nf_flow_t flow, nf_target_t target, const void* theta_dev, int64_t N, const void* z0_dev,
+                               uint64_t seed, double scale, double* value_out, void* grad_dev_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  const Target* t = reinterpret_cast<Target*>(target);
+  NF_TRY(check_target(f, t));
+  NF_REQUIRE(theta_dev, "theta is null");
+  NF_CUDA(cudaSetDevice(f.device));
+  f.ws_reset();
+  NF_TRY(general_plan_workspace(f, OP_ELBO, N, 0));
+  return value_and_grad_dev(f, OP_ELBO, t, theta_dev, N, z0_dev, seed, scale, value_out, grad_dev_out);
+}
+
+int nf_elbo_sums_dev(nf_flow_t flow, nf_target_t target, const void* theta_dev, int64_t N, const void* z0_dev,
+                     uint64_t seed, void* sums_dev_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  const Target* t = reinterpret_cast<Target*>(target);
+  NF_TRY(check_target(f, t));
+  NF_REQUIRE(theta_dev && sums_dev_out, "null argument");
+  NF_CUDA(cudaSetDevice(f.device));
+  f.ws_reset();
+  NF_TRY(general_plan_workspace(f, OP_ELBO, N, 0));
+  Job j;
+  j.op = OP_ELBO; j.tgt = t; j.theta_dev = theta_dev; j.in_dev = z0_dev; j.N = N; j.seed = seed; j.want_grad = true;
+  NF_CUDA(cudaEventRecord(f.ev0, f.stream));
+  NF_TRY(run_job(f, j));
+  NF_TRY(scale_outputs(f, 1.0, sums_dev_out, f.P + 1));
+  NF_CUDA(cudaEventRecord(f.ev1, f.stream));
+  NF_CUDA(cudaStreamSynchronize(f.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, f.ev0, f.ev1);
+  f.last_ms = ms;
+  return NF_OK;
+}
+
+int nf_elbo_terms(nf_flow_t flow, nf_target_t target, const void* theta_host, int64_t N, const void* z0_host,
+                  void* elbos_host_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  const Target* t = reinterpret_cast<Target*>(target);
+  NF_TRY(check_target(f, t));
+  NF_REQUIRE(z0_host && elbos_host_out, "null argument");
+  return transform_host(f, OP_ELBO, t, theta_host, N, z0_host, 0, nullptr, nullptr, elbos_host_out, nullptr, 0);
+}
+
+int nf_loglik_value_and_grad(nf_flow_t flow, const void* theta_host, int64_t N, const void* xs_host, double scale,
+                             double* value_out, void* grad_host_out) {
+  NF_CHECK_HANDLE(flow);
+  NF_REQUIRE(xs_host, "xs is null");
+  return value_and_grad_host(NF_FLOW(flow), OP_LOGLIK, nullptr, theta_host, N, xs_host, 0, scale, value_out, grad_host_out);
+}
+
+int nf_loglik_value_and_grad_dev(nf_flow_t flow, const void* theta_dev, int64_t N, const void* xs_dev, double scale,
+                                 double* value_out, void* grad_dev_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  NF_REQUIRE(theta_dev && xs_dev, "null argument");
+  NF_CUDA(cudaSetDevice(f.device));
+  f.ws_reset();
+  NF_TRY(general_plan_workspace(f, OP_LOGLIK, N, 0));
+  return value_and_grad_dev(f, OP_LOGLIK, nullptr, theta_dev, N, xs_dev, 0, scale, value_out, grad_dev_out);
+}
+
+int nf_forward(nf_flow_t flow, const void* theta_host, int64_t N, const void* x_host, void* y_host_out, void* logdet_host_out) {
+  NF_CHECK_HANDLE(flow);
+  NF_REQUIRE(x_host, "x is null");
+  return transform_host(NF_FLOW(flow), OP_FORWARD, nullptr, theta_host, N, x_host, 0, y_host_out, logdet_host_out, nullptr, nullptr, 0);
+}
+
+int nf_inverse(nf_flow_t flow, const void* theta_host, int64_t N, const void* y_host, void* x_host_out, void* logdet_host_out) {
+  NF_CHECK_HANDLE(flow);
+  NF_REQUIRE(y_host, "y is null");
+  return transform_host(NF_FLOW(flow), OP_INVERSE, nullptr, theta_host, N, y_host, 0, x_host_out, logdet_host_out, nullptr, nullptr, 0);
+}
+
+int nf_logpdf(nf_flow_t flow, const void* theta_host, int64_t N, const void* y_host, void* logpdf_host_out) {
+  NF_CHECK_HANDLE(flow);
+  NF_REQUIRE(y_host && logpdf_host_out, "null argument");
+  return transform_host(NF_FLOW(flow), OP_LOGLIK, nullptr, theta_host, N, y_host, 0, nullptr, nullptr, logpdf_host_out, nullptr, 0);
+}
+
+int nf_sample(nf_flow_t flow, const void* theta_host, int64_t N, uint64_t seed, void* y_host_out) {
+  NF_CHECK_HANDLE(flow);
+  NF_REQUIRE(y_host_out, "null argument");
+  return transform_host(NF_FLOW(flow), OP_FORWARD, nullptr, theta_host, N, nullptr, seed, y_host_out, nullptr, nullptr, nullptr, 0);
+}
+
+int nf_base_sample(nf_flow_t flow, int64_t N, uint64_t seed, void* z_host_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  NF_REQUIRE(z_host_out && N > 0, "bad argument");
+  NF_CUDA(cudaSetDevice(f.device));
+  f.ws_reset();
+  const size_t mat = (size_t)N * f.dim * f.esize();
+  NF_TRY(f.ws_reserve(mat + 4096));
+  void* z = f.ws_alloc(mat);
+  if (!z) return NF_ERR_OOM;
+  NF_TRY(base_sample_dev(f, N, seed, z));
+  NF_CUDA(cudaMemcpyAsync(z_host_out, z, mat, cudaMemcpyDeviceToHost, f.stream));
+  NF_CUDA(cudaStreamSynchronize(f.stream));
+  return NF_OK;
+}
+
+int nf_forward_stash(nf_flow_t flow, const void* theta_host, int64_t N, const void* x_host, void* y_host_out,
+                     void* logdet_host_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  NF_REQUIRE(x_host, "x is null");
+  NF_REQUIRE(!f.all_elementwise, "two-phase API is implemented for coupling flows; elementwise flows use the fused ELBO kernel");
+  int s = transform_host(f, OP_FORWARD_STASH, nullptr, theta_host, N, x_host, 0, y_host_out, logdet_host_out, nullptr, nullptr, 0);
+  if (s == NF_OK) f.stash_N = N;
+  return s;
+}
+
+int nf_backward(nf_flow_t flow, const void* gy_host, const void* gld_host_or_null, void* grad_host_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  NF_REQUIRE(gy_host && grad_host_out, "null argument");
+  NF_REQUIRE(f.stash_N > 0, "nf_backward needs a preceding nf_forward_stash");
+  NF_CUDA(cudaSetDevice(f.device));
+  const size_t es = f.esize();
+  NF_TRY(general_backward_from_stash(f, gy_host, gld_host_or_null));
+  NF_TRY(scale_outputs(f, 1.0, f.d_out, f.P));
+  NF_CUDA(cudaMemcpyAsync(f.h_pinned, f.d_out, f.P * es, cudaMemcpyDeviceToHost, f.stream));
+  NF_CUDA(cudaStreamSynchronize(f.stream));
+  memcpy(grad_host_out, f.h_pinned, f.P * es);
+  f.stash_N = 0;
+  return NF_OK;
+}
+
+int nf_spline_bins(nf_flow_t flow, const void* theta_host, int64_t N, const void* x_host, int32_t* bins_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  NF_REQUIRE(x_host && bins_out, "null argument");
+  size_t count = 0;
+  for (auto& L : f.layers) if (L.kind == NF_SPLINE_COUPLING) count += (size_t)N * L.idx1.size();
+  NF_REQUIRE(count > 0, "flow has no spline couplings");
+  return transform_host(f, OP_FORWARD, nullptr, theta_host, N, x_host, 0, nullptr, nullptr, nullptr, bins_out, count);
+}
+
+int nf_rqs_bin_search(int dtype, const void* knots_host, const void* v_host, int64_t M, int K, int32_t* bins_out) {
+  NF_REQUIRE(knots_host && v_host && bins_out && M > 0 && K >= 1, "bad argument");
+  NF_TRY(check_device());
+  return rqs_bin_search_host(dtype, knots_host, v_host, M, K, bins_out);
+}
+
+int64_t nf_launch_count(int reset) {
+  const int64_t c = g_launch_count;
+  if (reset) g_launch_count = 0;
+  return c;
+}
+
+double nf_last_device_ms(nf_flow_t flow) { return flow ? NF_FLOW(flow).last_ms : -1.0; }
+
+}  // extern "C"

@@ -1,0 +1,21 @@
+// tcgen05 / TMEM GEMM path for the coupling-MLP contractions of Float32 flows (kernel K3).
+#pragma once
+#include "flow.hpp"
+
+namespace nf {
+
+// bytes of a split-bf16 activation buffer (hi and lo planes, rows padded to 128, features to 64)
+size_t tc_act_bytes(int64_t n, int width);
+// bytes of the per-flow prepared weight planes
+size_t tc_weight_bytes(const Flow& f);
+// theta -> transposed / split bf16 weight planes (once per call, before any tc_mlp_*)
+int tc_prepare_weights(Flow& f, const float* theta_dev);
+// x2 = X[:, idx2] -> split planes
+int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* act0);
+int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts);
+// g_last: fp32 [n, out] gradient w.r.t. the last Dense's pre-activation; scratch: one activation-sized buffer
+int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts, float* g_last,
+                    void* scratch, float* G, double* gsum);
+void tc_release(Flow& f);
+
+}  // namespace nf

@@ -1,0 +1,131 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on identical host-supplied Z0.
+
+Tolerances (BASELINE.json north_star): ELBO 1e-5 relative, gradient 1e-4 relative (norm-wise) for
+Float32; Float64 runs are held to 1e-9 / 1e-7.
+"""
+import numpy as np
+import pytest
+import torch
+
+import nf_oracle as O
+from helpers import gpu_flow, gpu_target, oracle_flow, oracle_target, rel_err, z0
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: (1e-5, 1e-4), np.float64: (1e-9, 1e-7)}
+
+CASES = [
+    # kind, dim, target, N, kwargs
+    ("planar", 2, "banana", 10, dict(nlayers=20)),          # BASELINE config 1
+    ("planar", 2, "banana", 1000, dict(nlayers=20)),
+    ("planar", 5, "diag", 64, dict(nlayers=10)),            # reference test/flow.jl:137-144 shape
+    ("radial", 2, "warped", 1000, dict(nlayers=20)),        # BASELINE config 2 (small N)
+    ("radial", 5, "diag", 64, dict(nlayers=10)),
+    ("realnvp", 5, "diag", 64, dict(hdims=[32, 32], nlayers=2)),     # odd d: masks of 3 and 2 (test/flow.jl:4-11)
+    ("realnvp", 2, "banana", 16, dict(hdims=[16, 16], nlayers=3)),   # demo_RealNVP.jl shape
+    ("realnvp", 64, "funnel", 1000, dict(hdims=[256, 256], nlayers=4)),  # BASELINE config 3 (small N)
+    ("nsf", 5, "diag", 64, dict(hdims=[32, 32], K=10, B=5.0, nlayers=2)),
+    ("nsf", 16, "cross", 1000, dict(hdims=[32, 32], K=10, B=5.0, nlayers=4)),  # BASELINE config 4
+    ("nsf", 16, "cross", 500, dict(hdims=[32, 32], K=10, B=1.0, nlayers=2)),   # B=1: identity tails exercised
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("kind,dim,tname,N,kw", CASES, ids=[f"{c[0]}-d{c[1]}-{c[2]}-N{c[3]}" for c in CASES])
+def test_elbo_value_and_grad(gpu, kind, dim, tname, N, kw, dtype):
+    nf = gpu
+    of = oracle_flow(kind, dim, dtype, **kw)
+    ot = oracle_target(tname, dim)
+    xs = z0(N, dim, dtype)
+    v_ref, g_ref = O.elbo_value_and_grad(of, ot, of.theta(), torch.from_numpy(xs))
+    gf = gpu_flow(nf, of, dtype)
+    if kind in ("realnvp", "nsf") and dtype == np.float32:
+        gf.set_mma_mode(nf.NF_MMA_SIMT)
+    gt = gpu_target(nf, ot)
+    v, g = nf.api._elbo_impl(gf, gt, xs, want_grad=True)
+    tv, tg = TOL[dtype]
+    assert np.isfinite(v)
+    assert abs(v - v_ref) <= tv * max(abs(v_ref), 1.0), (v, v_ref)
+    assert rel_err(g, g_ref) <= tg, rel_err(g, g_ref)
+    # per-sample terms (elbo.jl:65-70) and value-only path agree with the value+grad path
+    terms = nf.batched_elbos(gf, gt, xs)
+    ref_terms = O.batched_elbos(of, ot, torch.from_numpy(xs)).detach().numpy()
+    assert rel_err(terms, ref_terms) <= 10 * tv
+    assert abs(nf.elbo_batch(gf, gt, xs) - v) <= 1e-6 * max(abs(v), 1.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("kind", ["realnvp", "nsf"])
+def test_forward_inverse_consistency(gpu, kind, dtype):
+    """reference test/flow.jl:25-39,92-106: x ≈ inv(fwd(x)), lj_fwd ≈ -lj_inv at d = 5, vector and d x 10 batch."""
+    nf = gpu
+    of = oracle_flow(kind, 5, dtype)
+    gf = gpu_flow(nf, of, dtype)
+    if dtype == np.float32:
+        gf.set_mma_mode(nf.NF_MMA_SIMT)
+    rtol = 1e-6 if (kind == "realnvp" and dtype == np.float64) else 1e-4
+    for n in (1, 10):
+        x = z0(n, 5, dtype, seed=5)
+        y, lj = gf.with_logabsdet_jacobian(x)
+        y_ref, lj_ref = of.forward(torch.from_numpy(x))
+        assert rel_err(y, y_ref.detach().numpy()) <= 1e-5
+        xr, lji = gf.inverse_with_logabsdet_jacobian(y)
+        np.testing.assert_allclose(xr, x, rtol=rtol, atol=rtol)
+        np.testing.assert_allclose(lj, -lji, rtol=rtol, atol=rtol)
+        lp = gf.logpdf(y)
+        lp_ref = of.logpdf(torch.from_numpy(y)).detach().numpy()
+        np.testing.assert_allclose(lp, lp_ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("kind,dim,kw", [("realnvp", 5, dict(hdims=[32, 32], nlayers=2)),
+                                         ("nsf", 16, dict(hdims=[32, 32], K=10, B=5.0, nlayers=2))])
+def test_loglikelihood_value_and_grad(gpu, kind, dim, kw, dtype):
+    """forward-KL objective (reference src/objectives/loglikelihood.jl:26-33) and its gradient."""
+    nf = gpu
+    of = oracle_flow(kind, dim, dtype, **kw)
+    gf = gpu_flow(nf, of, dtype)
+    if dtype == np.float32:
+        gf.set_mma_mode(nf.NF_MMA_SIMT)
+    rng = np.random.Generator(np.random.PCG64(11))
+    xs = (0.7 * rng.standard_normal((200, dim))).astype(dtype)
+    v_ref, g_ref = O.loglik_value_and_grad(of, of.theta(), torch.from_numpy(xs))
+    import ctypes as C
+    K = nf._capi
+    val = C.c_double()
+    g = np.empty(gf.theta.size, dtype=dtype)
+    K.check(K.lib().nf_loglik_value_and_grad(gf.handle(), K.ptr(gf.theta), xs.shape[0], K.ptr(xs), 1.0, C.byref(val), K.ptr(g)))
+    tv, tg = TOL[dtype]
+    assert abs(val.value - v_ref) <= tv * max(abs(v_ref), 1.0)
+    assert rel_err(g, g_ref) <= tg
+    assert abs(nf.loglikelihood(None, gf, xs) - val.value) <= 1e-6 * max(abs(v_ref), 1.0)
+
+
+def test_spline_bins_bit_exact(gpu):
+    """Bin search is exact integer work: identical knots + inputs -> identical bins (north_star)."""
+    nf = gpu
+    rng = np.random.Generator(np.random.PCG64(3))
+    for dtype in (np.float32, np.float64):
+        K = 10
+        w = rng.random((5000, K)).astype(dtype)
+        knots = np.concatenate([np.full((5000, 1), -5, dtype), (10 * np.cumsum(w / w.sum(1, keepdims=True), 1) - 5).astype(dtype)], 1)
+        v = rng.uniform(-6, 6, 5000).astype(dtype)
+        v[:500] = knots[np.arange(500), rng.integers(0, K + 1, 500)]        # exactly on a knot
+        ref = O.rqs_bin_index(torch.from_numpy(knots), torch.from_numpy(v)).numpy()
+        got = nf.rqs_bin_search(knots, v)
+        assert np.array_equal(got, ref.astype(np.int32))
+
+
+def test_spline_bins_end_to_end(gpu):
+    """Bins produced inside the flow match the oracle except for inputs within 1e-5 of a knot."""
+    nf = gpu
+    dtype = np.float32
+    of = oracle_flow("nsf", 16, dtype, hdims=[32, 32], K=10, B=5.0, nlayers=2)
+    gf = gpu_flow(nf, of, dtype).set_mma_mode(nf.NF_MMA_SIMT)
+    xs = z0(2000, 16, dtype)
+    got = nf.spline_bins(gf, xs)
+    of.forward(torch.from_numpy(xs))
+    ref = [l.last_bins.numpy() for l in reversed(of.layers)]
+    mism = sum(int((a != b).sum()) for a, b in zip(got, ref))
+    total = sum(a.size for a in got)
+    assert mism <= 1e-4 * total, (mism, total)

@@ -1,0 +1,77 @@
+"""The reference's own property tests, run against the CUDA path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64], ids=["f32", "f64"])
+def test_objectives_analytic_elbo(gpu, T):
+    """reference test/objectives.jl:1-37: the flow is the exact affine map of the target -> ELBO == 0."""
+    nf = gpu
+    rng = np.random.Generator(np.random.PCG64(1))
+    mu = rng.standard_normal(2).astype(T)
+    var = (rng.random(2) + 1e-3).astype(T)
+    target = nf.DiagNormal(mu, np.sqrt(var))
+    q0 = nf.MvNormal(np.zeros(2), np.ones(2))
+    flow = nf.transformed(q0, nf.Shift(mu) @ nf.Scale(np.sqrt(var)), T)
+    el = nf.elbo(rng, flow, target, 10)
+    assert abs(el) <= 1e-5
+    elb = nf.elbo_batch(rng, flow, target, 10)
+    assert abs(elb) <= 1e-5
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("kind", ["realnvp", "nsf", "planar", "radial"])
+def test_flow_elbo_finite(gpu, kind, T):
+    """reference test/flow.jl:42-61: elbo / elbo_batch finite at n = 64 and n = 1 (d = 5)."""
+    nf = gpu
+    dim = 5
+    q0 = nf.MvNormal(np.zeros(dim))
+    nf.seed(123)
+    flow = {"realnvp": lambda: nf.realnvp(q0, [32, 32], 2, T), "nsf": lambda: nf.nsf(q0, [32, 32], 10, 5.0, 2, T),
+            "planar": lambda: nf.planarflow(q0, 10, T), "radial": lambda: nf.radialflow(q0, 10, T)}[kind]()
+    if kind in ("realnvp", "nsf") and T == np.float32:
+        flow.set_mma_mode(nf.NF_MMA_SIMT)
+    rng = np.random.Generator(np.random.PCG64(2))
+    target = nf.DiagNormal(rng.standard_normal(dim), np.sqrt(rng.random(dim) + 1e-3))
+    assert np.isfinite(nf.elbo(rng, flow, target, 64))
+    assert np.isfinite(nf.elbo_batch(rng, flow, target, 64))
+    assert np.isfinite(nf.elbo(rng, flow, target, 1))
+    if kind in ("realnvp", "nsf"):
+        ys = flow.rand(100)
+        assert ys.shape == (100, dim) and ys.dtype == T
+        ls = flow.logpdf(ys)
+        assert ls.shape == (100,) and ls.dtype == T and np.all(np.isfinite(ls))
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64], ids=["f32", "f64"])
+def test_interface_train_flow_converges(gpu, T):
+    """reference test/interface.jl:1-53: train_flow(elbo, Shift∘Scale flow) -> theta ≈ (10,10,2,2)."""
+    nf = gpu
+    mu = 10 * np.ones(2)
+    target = nf.DiagNormal(mu, 2 * np.ones(2))
+    q0 = nf.MvNormal(np.zeros(2), np.ones(2))
+    flow = nf.transformed(q0, nf.Shift(np.zeros(2)) @ nf.Scale(np.ones(2)), T)
+    seen = {"cb": 0}
+
+    def cb(it, opt_stats, re, theta):
+        seen["cb"] += 1
+        return {"sample_per_iter": 10}
+
+    def checkconv(it, stat, re, theta, st):
+        return stat["gradient_norm"] < 1e-3
+
+    rng = np.random.Generator(np.random.PCG64(0))
+    flow_trained, stats, _ = nf.train_flow(rng, nf.elbo, flow, target, 10, max_iters=5000, optimiser=nf.Adam(0.01),
+                                           ADbackend=nf.AutoNFCUDA(), show_progress=False, callback=cb, hasconverged=checkconv)
+    theta, re = nf.destructure(flow_trained)
+    el_untrained = nf.elbo(rng, flow, target, 1000)
+    el_trained = nf.elbo(rng, flow_trained, target, 1000)
+    assert np.all(np.abs(theta[:2] - mu) < 0.2)
+    assert np.all(np.abs(theta[2:] - 2) < 0.2)
+    assert el_trained > el_untrained
+    assert el_trained > -1
+    assert seen["cb"] == len(stats) and "sample_per_iter" in stats[0]
+    with pytest.raises(TypeError):
+        nf.train_flow(nf.elbo, flow, target, 10)     # ADbackend is required, as in the reference
