@@ -84,6 +84,7 @@ struct Flow {
   // layered path: chunk size chosen by general_plan_workspace, opaque per-flow state
   int64_t chunk_N = 0;
   void* gen_state = nullptr;
+  void* tc_state = nullptr;            // tcgen05 path: prepared weight planes, tensor-map cache
 
   // state kept by nf_forward_stash for nf_backward
   int64_t stash_N = 0;

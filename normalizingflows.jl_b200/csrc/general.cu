@@ -28,7 +28,7 @@ struct Chunk {
   void* G = nullptr;
   void* gld = nullptr;                        // optional per-sample d/dlogdet (two-phase API)
   std::vector<LayerBufs> lb;                  // stash: one per layer; else a single shared set at [0]
-  void* ga[3] = {nullptr, nullptr, nullptr};  // backward temporaries (width = max MLP width)
+  void* ga[4] = {nullptr, nullptr, nullptr, nullptr};  // backward temporaries (width = max MLP width)
   int n_states = 0;
 };
 
@@ -70,7 +70,7 @@ size_t per_sample_bytes(const Flow& f, bool stash) {
     layer_max = std::max(layer_max, lbts);
   }
   b += (stash ? layer_sum : layer_max) / 1024 + 1;
-  b += 3 * act_bytes(f, 1024, max_width(f), false) / 1024 + 3 * (size_t)max_width(f) * es;
+  b += 4 * act_bytes(f, 1024, max_width(f), false) / 1024 + 4 * (size_t)max_width(f) * es;
   return b;
 }
 
@@ -140,7 +140,7 @@ int alloc_chunk(Flow& f, Chunk& c, int64_t n, bool stash, const void* x0_alias) 
 
 int alloc_backward_tmps(Flow& f, Chunk& c) {
   const int mw = max_width(f);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     size_t bytes = std::max(act_bytes(f, c.n, mw, false), (size_t)c.n * mw * f.esize());
     c.ga[i] = f.ws_alloc(bytes);
     if (!c.ga[i]) return NF_ERR_OOM;
@@ -251,8 +251,8 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
         G, INV ? Xout : Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, n, gA, gB);
     NF_LAUNCH_CHECK();
     if (tc) {
-      NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, c.ga[2], (float*)G, f.d_gsum));
-      NF_TRY(tc_mlp_backward(f, Ld, 1, n, b.act0, b.acts[1], (float*)gB, c.ga[2], (float*)G, f.d_gsum));
+      NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
+      NF_TRY(tc_mlp_backward(f, Ld, 1, n, b.act0, b.acts[1], (float*)gB, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
     } else {
       // s network: temporaries gC + (gA after it has been consumed is NOT safe) -> use a dedicated pair
       NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gA, G, d, Ld.d_idx2, f.d_gsum));
@@ -262,7 +262,7 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
     rqs_bwd_kernel<T, INV><<<(unsigned)ceil_div(n * cc, 128), 128, 0, f.stream>>>(
         G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA);
     NF_LAUNCH_CHECK();
-    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, c.ga[2], (float*)G, f.d_gsum));
+    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
     else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, G, d, Ld.d_idx2, f.d_gsum));
   }
   return NF_OK;

@@ -13,9 +13,9 @@ int tc_prepare_weights(Flow& f, const float* theta_dev);
 // x2 = X[:, idx2] -> split planes
 int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* act0);
 int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts);
-// g_last: fp32 [n, out] gradient w.r.t. the last Dense's pre-activation; scratch: one activation-sized buffer
+// g_last: fp32 [n, out] gradient w.r.t. the last Dense's pre-activation; scratch0/1: activation-sized buffers
 int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts, float* g_last,
-                    void* scratch, float* G, double* gsum);
+                    void* scratch0, void* scratch1, float* G, double* gsum);
 void tc_release(Flow& f);
 
 }  // namespace nf
