@@ -90,11 +90,12 @@ typedef enum nf_target_kind {
   NF_TARGET_DIAG_NORMAL  = 5   /* params: mu[dim], sigma[dim] (standard deviations; MvNormal(mu, Diagonal(sigma.^2))) */
 } nf_target_kind;
 
-/* MMA issue mode of the coupling-MLP contractions (fp32 flows).  BF16X3 is the parity mode. */
+/* MMA issue mode of the coupling-MLP contractions (fp32 flows).  F16X3 is the parity mode. */
 typedef enum nf_mma_mode {
   NF_MMA_SIMT    = 0,  /* CUDA-core FMA GEMMs in the flow dtype (the only mode for NF_F64)            */
-  NF_MMA_BF16X3  = 1,  /* tcgen05 kind::f16, operands split hi+lo bf16, 3 products, fp32 accumulate   */
-  NF_MMA_BF16X1  = 2   /* tcgen05 single bf16 pass: NOT parity-grade, offered for throughput studies  */
+  NF_MMA_F16X3   = 1,  /* tcgen05 kind::f16: operands split hi+lo fp16 under an exact per-tensor power-of-two
+                          scale (22 significant bits), 3 products, fp32 accumulate in TMEM                */
+  NF_MMA_F16X1   = 2   /* tcgen05 single fp16 pass (11-bit operands): NOT parity-grade, throughput studies   */
 } nf_mma_mode;
 
 /* ---- library / device ------------------------------------------------------------------------ */
@@ -114,7 +115,7 @@ NF_API int64_t nf_flow_num_params(nf_flow_t flow);
 NF_API int     nf_flow_dim(nf_flow_t flow);
 /* Base distribution q0 = MvNormal(mu, Diagonal(sigma.^2)); NULL -> zeros / ones.  double arrays of length dim. */
 NF_API int     nf_flow_set_base(nf_flow_t flow, const double* mu, const double* sigma);
-/* nf_mma_mode for the coupling MLPs; default NF_MMA_BF16X3 for NF_F32 flows, NF_MMA_SIMT for NF_F64. */
+/* nf_mma_mode for the coupling MLPs; default NF_MMA_F16X3 for NF_F32 flows, NF_MMA_SIMT for NF_F64. */
 NF_API int     nf_flow_set_mma_mode(nf_flow_t flow, int mode);
 /* Cap (bytes) on the activation workspace; batches larger than fits are processed in sample chunks. */
 NF_API int     nf_flow_set_workspace_limit(nf_flow_t flow, size_t bytes);
@@ -183,6 +184,8 @@ NF_API int nf_backward(nf_flow_t flow, const void* gy_host, const void* gld_host
 NF_API int nf_spline_bins(nf_flow_t flow, const void* theta_host, int64_t N, const void* x_host, int32_t* bins_out);
 /* Bin search alone on caller-supplied knots: knots [M][K+1], v [M] -> bins [M] (searchsortedfirst - 1). */
 NF_API int nf_rqs_bin_search(int dtype, const void* knots_host, const void* v_host, int64_t M, int K, int32_t* bins_out);
+/* One Dense layer Y[n,N] = X[n,K] Wt[K,N] + b through the tcgen05 forward GEMM (terms: 1 or 3 fp16 products). */
+NF_API int nf_tc_gemm_test(int64_t n, int K, int N, const float* X, const float* Wt, const float* b, int terms, float* Y);
 /* Number of kernels launched by this thread's library calls since the last reset (bench.py `gpu_launches`). */
 NF_API int64_t nf_launch_count(int reset);
 /* Duration (ms, CUDA events on the flow's stream) of the device work of the last value_and_grad call. */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libnfcuda.so")
 NF_F32, NF_F64 = 0, 1
 NF_PLANAR, NF_RADIAL, NF_AFFINE_COUPLING, NF_SPLINE_COUPLING, NF_SHIFT, NF_SCALE = 1, 2, 3, 4, 5, 6
 NF_TARGET_BANANA, NF_TARGET_FUNNEL, NF_TARGET_WARPED_GAUSS, NF_TARGET_CROSS, NF_TARGET_DIAG_NORMAL = 1, 2, 3, 4, 5
-NF_MMA_SIMT, NF_MMA_BF16X3, NF_MMA_BF16X1 = 0, 1, 2
+NF_MMA_SIMT, NF_MMA_F16X3, NF_MMA_F16X1 = 0, 1, 2
 
 
 class LayerDesc(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
     "nf_backward": (_i, [_vp, _vp, _vp, _vp]),
     "nf_spline_bins": (_i, [_vp, _vp, _i64, _vp, C.POINTER(C.c_int32)]),
     "nf_rqs_bin_search": (_i, [_i, _vp, _vp, _i64, _i, C.POINTER(C.c_int32)]),
+    "nf_tc_gemm_test": (_i, [_i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "nf_launch_count": (_i64, [_i]),
     "nf_last_device_ms": (_d, [_vp]),
 }

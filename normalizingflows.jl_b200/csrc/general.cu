@@ -357,6 +357,7 @@ int run_typed(Flow& f, const GeneralJob& job) {
   for (int64_t c0 = 0; c0 < N; c0 += Nc) {
     const int64_t n = std::min(Nc, N - c0);
     f.ws.off = ws_mark;
+    if (f.mma_mode != NF_MMA_SIMT && c0 > 0) NF_TRY(tc_begin_chunk(f));
     Chunk c;
     const T* in = job.in_dev ? (const T*)job.in_dev + c0 * d : nullptr;
     NF_TRY(alloc_chunk(f, c, n, stash, in));
@@ -430,7 +431,7 @@ int backward_from_stash_typed(Flow& f, const void* gy_host, const void* gld_host
   if (gld_host) NF_CUDA(cudaMemcpyAsync(c.gld, gld_host, (size_t)c.n * es, cudaMemcpyHostToDevice, f.stream));
   else NF_CUDA(cudaMemsetAsync(c.gld, 0, (size_t)c.n * es, f.stream));
   NF_TRY(alloc_backward_tmps(f, c));
-  if (f.mma_mode != NF_MMA_SIMT) NF_TRY(tc_prepare_weights(f, (const float*)f.d_theta));
+  // the weight planes and per-tensor scales prepared by nf_forward_stash are still current
   NF_TRY(sweep_backward_fwd<T>(f, c, (const T*)f.d_theta));
   gs->has_stash = false;
   return NF_OK;

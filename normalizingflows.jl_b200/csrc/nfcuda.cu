@@ -1,6 +1,7 @@
 // libnfcuda C ABI (include/nfcuda.h): handle management, host<->device staging, dispatch.
 #include "flow.hpp"
 #include "general.hpp"
+#include "tc_gemm.hpp"
 #include <cstring>
 #include <mutex>
 
@@ -147,11 +148,11 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
     f->layers.push_back(std::move(L));
   }
   f->P = off;
-  f->mma_mode = (dtype == NF_F32) ? NF_MMA_BF16X3 : NF_MMA_SIMT;
+  f->mma_mode = (dtype == NF_F32) ? NF_MMA_F16X3 : NF_MMA_SIMT;
   if (const char* e = getenv("NFCUDA_MMA")) {
     if (!strcmp(e, "simt")) f->mma_mode = NF_MMA_SIMT;
-    else if (!strcmp(e, "bf16x1") && dtype == NF_F32) f->mma_mode = NF_MMA_BF16X1;
-    else if (!strcmp(e, "bf16x3") && dtype == NF_F32) f->mma_mode = NF_MMA_BF16X3;
+    else if (!strcmp(e, "f16x1") && dtype == NF_F32) f->mma_mode = NF_MMA_F16X1;
+    else if (!strcmp(e, "f16x3") && dtype == NF_F32) f->mma_mode = NF_MMA_F16X3;
   }
   NF_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   NF_CUDA(cudaEventCreate(&f->ev0));
@@ -372,7 +373,7 @@ int nf_flow_set_base(nf_flow_t flow, const double* mu, const double* sigma) {
 int nf_flow_set_mma_mode(nf_flow_t flow, int mode) {
   NF_CHECK_HANDLE(flow);
   Flow& f = NF_FLOW(flow);
-  NF_REQUIRE(mode == NF_MMA_SIMT || mode == NF_MMA_BF16X3 || mode == NF_MMA_BF16X1, "unknown mma mode %d", mode);
+  NF_REQUIRE(mode == NF_MMA_SIMT || mode == NF_MMA_F16X3 || mode == NF_MMA_F16X1, "unknown mma mode %d", mode);
   NF_REQUIRE(f.dtype == NF_F32 || mode == NF_MMA_SIMT, "Float64 flows only support NF_MMA_SIMT");
   f.mma_mode = mode;
   return NF_OK;
@@ -599,6 +600,13 @@ int nf_rqs_bin_search(int dtype, const void* knots_host, const void* v_host, int
   NF_REQUIRE(knots_host && v_host && bins_out && M > 0 && K >= 1, "bad argument");
   NF_TRY(check_device());
   return rqs_bin_search_host(dtype, knots_host, v_host, M, K, bins_out);
+}
+
+int nf_tc_gemm_test(int64_t n, int K, int N, const float* X, const float* Wt, const float* b, int terms, float* Y) {
+  NF_REQUIRE(X && Wt && b && Y && n > 0 && K > 0 && N > 0, "bad argument");
+  NF_REQUIRE(terms == 1 || terms == 3, "terms must be 1 or 3");
+  NF_TRY(check_device());
+  return tc_gemm_selftest(n, K, N, X, Wt, b, terms, Y);
 }
 
 int64_t nf_launch_count(int reset) {

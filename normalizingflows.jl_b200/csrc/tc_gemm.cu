@@ -4,9 +4,13 @@
 //   forward : Y[n, out]  = act(X[n, in] W^T + b)            tc_gemm_kernel, K-major operands
 //   dgrad   : gX[n, in]  = gY[n, out] W   (* leakyrelu')     tc_gemm_kernel, K-major operands
 //   wgrad   : gW^T[in, out] = X^T[in, n] gY[n, out]          tc_wgrad_kernel, MN-major operands (contraction over samples)
-// Operands are bf16 "split planes": x = hi + lo with hi = bf16(x), lo = bf16(x - hi).  The parity
-// mode NF_MMA_BF16X3 issues three kind::f16 MMAs per K step (hi*hi + hi*lo + lo*hi) with fp32
-// accumulation in TMEM, which keeps the dropped term at 2^-16 relative; NF_MMA_BF16X1 issues hi*hi only.
+// Operands are fp16 "split planes": s*x = hi + lo with hi = fp16(s*x), lo = fp16(s*x - hi), where s is an
+// exact power of two chosen per tensor so that |s*x| <= 2^14 (no fp16 overflow; elements down to 2^-17 of
+// the tensor maximum keep 22 significant bits).  s comes from a rigorous bound known before the producing
+// kernel runs: bound(out) = amax(in) * max-row-L1(W) + max|b|, with amax(in) the EXACT maximum recorded
+// by the kernel that produced `in` (atomicMax), so slack never compounds across layers.  The parity mode
+// NF_MMA_F16X3 issues three kind::f16 MMAs per K step (hi*hi + hi*lo + lo*hi) with fp32 accumulation in
+// TMEM (dropped term 2^-22 relative); NF_MMA_F16X1 issues hi*hi only (11-bit operands, not parity grade).
 //
 // Kernel anatomy (one CTA per SM, persistent over M tiles of 128 samples):
 //   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) -> smem ring, mbarrier expect_tx
@@ -16,7 +20,7 @@
 #include "tc_gemm.hpp"
 #include "kernels_coupling.cuh"
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <map>
 #include <tuple>
 
@@ -81,7 +85,7 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -107,8 +111,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
-//   K-major : 128-byte rows (64 bf16 along K), 8-row atoms 1024 B apart (SBO); LBO unused.
-//   MN-major: 128-byte rows (64 bf16 along M/N), K rows; 8-row groups SBO apart, 64-wide MN blocks LBO apart.
+//   K-major : 128-byte rows (64 fp16 along K), 8-row atoms 1024 B apart (SBO); LBO unused.
+//   MN-major: 128-byte rows (64 fp16 along M/N), K rows; 8-row groups SBO apart, 64-wide MN blocks LBO apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
@@ -118,22 +122,36 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M x N, majors.
+// Instruction descriptor (cute::UMMA::InstrDescriptor): f16 x f16 -> f32, M x N, majors.
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+  return (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
+
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  const float ra = a - __bfloat162float(ha), rb = b - __bfloat162float(hb);
-  __nv_bfloat162 h; h.x = ha; h.y = hb;
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = pack_bf16(ra, rb);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// power-of-two scale s with bound * s <= 2^14 (1 for degenerate bounds); exact arithmetic
+__host__ __device__ __forceinline__ float pow2_scale(float bound) {
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  const int ex = ilogbf(bound) + 1;      // 2^ex > bound
+  int sh = 14 - ex;
+  sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+  return ldexpf(1.f, sh);
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// per-tensor metadata: meta[0] = scale s (stored = true * s), meta[1] = bits of the exact max |true|
+__device__ __forceinline__ void meta_amax(float* meta, float v) {
+  atomicMax(reinterpret_cast<unsigned int*>(meta + 1), __float_as_uint(v));   // v >= 0: uint order == float order
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,14 +165,19 @@ struct GemmParams {
   int terms;               // 1 or 3
   int epi;
   int n_store;             // number of output columns to store (planes: padded width; f32/scatter: valid width)
+  const float* a_meta;     // scale / amax of the A planes
+  const float* w_sc;       // per-Dense scalars: [0] weight scale, [1] max row L1, [2] max col L1, [3] max |b|
+  int bound_dgrad;         // 0: out bound = amax*w_sc[1] + w_sc[3] ; 1: amax*w_sc[2]
+  float rz_comp;           // expected relative shortfall of the RZ-accumulating tensor core for this chain length
+  float* out_meta;         // planes outputs: scale is written, amax accumulated
   const float* bias;       // [>= n tile] zero padded (EPI_*_ACT)
   int act;
-  __nv_bfloat16* out_hi;   // planes [M_pad, out_ld]
-  __nv_bfloat16* out_lo;
+  __half* out_hi;          // planes [M_pad, out_ld]
+  __half* out_lo;
   int64_t out_ld;
   float* out_f32;          // [M, out_f32_ld]
   int64_t out_f32_ld;
-  const __nv_bfloat16* mask_hi;   // EPI_PLANES_MASK: sign of the stashed activation
+  const __half* mask_hi;   // EPI_PLANES_MASK: sign of the stashed activation
   int64_t mask_ld;
   float* G;                // EPI_SCATTER_ADD
   int ldg;
@@ -168,13 +191,23 @@ template <int BN> struct GemmCfg {
   static constexpr int STAGES = (STAGE * 4 <= 200 * 1024) ? 4 : ((STAGE * 3 <= 200 * 1024) ? 3 : 2);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  // epilogue: 4 warps (one per TMEM lane quarter) per column half; wide tiles use two halves
+  static constexpr int HALVES = BN >= 128 ? 2 : 1;
+  static constexpr int CPT = BN / HALVES;                    // accumulator columns held per epilogue thread
+  static constexpr int THREADS = 64 + 128 * 2;
 };
 
+// The tensor core rounds its fp32 accumulator toward zero after every MMA, so a long accumulation chain
+// is biased low (tests/debug_gemm.py: -8e-7 relative for K = 256).  The chain is therefore cut at every
+// K slab of 64: each slab accumulates into a fresh TMEM buffer (correction products first, while the
+// accumulator is still tiny), the epilogue warps drain it and carry the running sum in registers with
+// round-to-nearest adds, the same split Ootomo & Yokota use for fp32 emulation on tensor cores.
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int S = Cfg::STAGES;
+  constexpr int CPT = Cfg::CPT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -196,12 +229,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * Cfg::HALVES); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   if (threadIdx.x >= 64 && p.bias) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = p.bias[n0 + i];
+    for (int i = threadIdx.x - 64; i < BN; i += Cfg::THREADS - 64) s_bias[i] = p.bias[n0 + i];
   }
   tc_fence_before();
   __syncthreads();
@@ -231,62 +264,95 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: one K slab (= one smem stage) per TMEM buffer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-      uint32_t it = 0, tl = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
-        mbar_wait(tempty_bar(acc), accph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+      uint32_t it = 0;   // slab counter == stage counter
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
+          const uint32_t acc = it & 1, accph = (it >> 1) & 1;
+          mbar_wait(tempty_bar(acc), accph ^ 1);
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
           const uint32_t st = base + s * Cfg::STAGE;
+          uint32_t first = 0;
+          // correction products (hi*lo, lo*hi) first, main products (hi*hi) last
+          for (int t = p.terms - 1; t >= 0; --t) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            for (int t = 0; t < p.terms; ++t) {
+            for (int kk = 0; kk < 4; ++kk) {
               const uint32_t a_addr = st + (t == 2 ? Cfg::A_PLANE : 0) + kk * 32;
               const uint32_t b_addr = st + 2 * Cfg::A_PLANE + (t == 1 ? Cfg::B_PLANE : 0) + kk * 32;
-              umma_bf16(d_tmem, make_smem_desc(a_addr, 16, 1024), make_smem_desc(b_addr, 16, 1024), idesc,
-                        (kc | kk | t) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, make_smem_desc(a_addr, 16, 1024), make_smem_desc(b_addr, 16, 1024), idesc, first);
+              first = 1;
             }
           }
           umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(acc));
         }
-        umma_commit(tfull_bar(acc));
       }
     }
-  } else {
-    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+  } else if (warp < 2 + 4 * Cfg::HALVES) {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     const int quarter = warp & 3;
-    uint32_t tl = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
-      mbar_wait(tfull_bar(acc), accph);
-      tc_fence_after();
+    const int half = (warp - 2) >> 2;
+    const int cbase = half * CPT;            // first accumulator column of this thread within the tile
+    const float s_a = p.a_meta[0];
+    const float amax_a = __uint_as_float(reinterpret_cast<const unsigned int*>(p.a_meta)[1]);
+    const float descale0 = 1.f / (s_a * p.w_sc[0]);
+    const float descale = fmaf(descale0, p.rz_comp, descale0);
+    float s_out = 1.f;
+    if (p.out_meta) {
+      const float bound = p.bound_dgrad ? amax_a * p.w_sc[2] : amax_a * p.w_sc[1] + p.w_sc[3];
+      s_out = pow2_scale(bound * 1.001f);
+      if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) p.out_meta[0] = s_out;
+    }
+    float run_max = 0.f;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      float racc[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) racc[j] = 0.f;
       const int64_t row = tile * 128 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.n_store) break;   // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        if (!row_ok) continue;
+      const int ncols_here = p.n_store - (n0 + cbase);   // columns of this thread's range that matter (warp-uniform)
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const uint32_t acc = it & 1, accph = (it >> 1) & 1;
+        mbar_wait(tfull_bar(acc), accph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cbase;
+#pragma unroll
+        for (int c = 0; c < CPT / 32; ++c) {
+          if (c * 32 < ncols_here) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+      if (!row_ok) continue;
+#pragma unroll
+      for (int c = 0; c < CPT / 32; ++c) {
+        const int col0 = n0 + cbase + c * 32;
+        if (col0 >= p.n_store) break;
+        const float* v = racc + c * 32;
+        const int bo = cbase + c * 32;     // offset into s_bias
         if (p.epi == EPI_PLANES_ACT || p.epi == EPI_PLANES_MASK) {
           uint32_t hi[16], lo[16];
           if (p.epi == EPI_PLANES_ACT) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              float a = __uint_as_float(v[j]) + s_bias[c * 32 + j];
-              float b = __uint_as_float(v[j + 1]) + s_bias[c * 32 + j + 1];
+              float a = v[j] * descale + s_bias[bo + j];
+              float b = v[j + 1] * descale + s_bias[bo + j + 1];
               if (p.act == ACT_LRELU) { a = a > 0.f ? a : 0.01f * a; b = b > 0.f ? b : 0.01f * b; }
-              split_pair(a, b, hi[j >> 1], lo[j >> 1]);
+              run_max = fmaxf(run_max, fmaxf(fabsf(a), fabsf(b)));
+              split_pair(a * s_out, b * s_out, hi[j >> 1], lo[j >> 1]);
             }
           } else {
             const uint4* mrow = reinterpret_cast<const uint4*>(p.mask_hi + row * p.mask_ld + col0);
@@ -296,12 +362,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const uint32_t m2 = mk[j >> 1];
-              // bf16 sign bits: low half bit 15, high half bit 31; activation > 0  <=> not negative and not zero
+              // fp16 sign bits: low half bit 15, high half bit 31; activation > 0  <=> not negative and not zero
               const bool pa = ((m2 & 0x8000u) == 0) && ((m2 & 0x7FFFu) != 0);
               const bool pb = ((m2 & 0x80000000u) == 0) && ((m2 & 0x7FFF0000u) != 0);
-              const float a = __uint_as_float(v[j]) * (pa ? 1.f : 0.01f);
-              const float b = __uint_as_float(v[j + 1]) * (pb ? 1.f : 0.01f);
-              split_pair(a, b, hi[j >> 1], lo[j >> 1]);
+              const float a = v[j] * descale * (pa ? 1.f : 0.01f);
+              const float b = v[j + 1] * descale * (pb ? 1.f : 0.01f);
+              run_max = fmaxf(run_max, fmaxf(fabsf(a), fabsf(b)));
+              split_pair(a * s_out, b * s_out, hi[j >> 1], lo[j >> 1]);
             }
           }
           uint4* oh = reinterpret_cast<uint4*>(p.out_hi + row * p.out_ld + col0);
@@ -317,7 +384,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (col0 + j < p.n_store) {
-              float a = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+              float a = v[j] * descale + s_bias[bo + j];
               if (p.act == ACT_TANH) a = tanhf(a);
               else if (p.act == ACT_LRELU) a = a > 0.f ? a : 0.01f * a;
               o[j] = a;
@@ -327,12 +394,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           float* g = p.G + row * p.ldg;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.n_store) g[p.idx[col0 + j]] += __uint_as_float(v[j]);
+            if (col0 + j < p.n_store) g[p.idx[col0 + j]] += v[j] * descale;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (p.out_meta) {
+      run_max = warp_max(run_max);
+      if (lane == 0) meta_amax(p.out_meta, run_max);
     }
   }
   tc_fence_before();
@@ -353,6 +421,8 @@ struct WgradParams {
   int kin, nout;      // valid sizes
   int mt;             // M tiles of 128 in-features
   int terms;
+  const float* x_meta;
+  const float* g_meta;
   double* gW;         // gsum + w_off, row-major [kin][nout]
 };
 
@@ -435,8 +505,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
             for (int t = 0; t < p.terms; ++t) {
               const uint32_t a_addr = st + (t == 2 ? Cfg::A_PLANE : 0) + mt * 2 * Cfg::BLK + ks * 16 * 128;
               const uint32_t b_addr = st + 2 * Cfg::A_PLANE + (t == 1 ? Cfg::B_PLANE : 0) + ks * 16 * 128;
-              umma_bf16(tmem_base + mt * BN, make_smem_desc(a_addr, Cfg::BLK, 1024), make_smem_desc(b_addr, Cfg::BLK, 1024),
-                        idesc, (it | ks | t) != 0 ? 1u : 0u);
+              umma_f16(tmem_base + mt * BN, make_smem_desc(a_addr, Cfg::BLK, 1024), make_smem_desc(b_addr, Cfg::BLK, 1024),
+                       idesc, (it | ks | t) != 0 ? 1u : 0u);
             }
           }
         }
@@ -448,6 +518,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
     const bool any = (int64_t)blockIdx.x < num_chunks;
     if (any) {
       const int quarter = warp & 3;
+      const float descale = 1.f / (p.x_meta[0] * p.g_meta[0]);
       mbar_wait(done_bar, 0);
       tc_fence_after();
       for (int mt = 0; mt < p.mt; ++mt) {
@@ -462,7 +533,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
             double* g = p.gW + (int64_t)krow * p.nout + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < p.nout) atomicAdd(&g[j], (double)__uint_as_float(v[j]));
+              if (c * 32 + j < p.nout) atomicAdd(&g[j], (double)(__uint_as_float(v[j]) * descale));
           }
         }
       }
@@ -477,34 +548,51 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// small helper kernels: split / gather into planes, plane column sums, weight preparation
+// helper kernels: absmax, split / gather into planes, plane column sums, weight preparation
 // ---------------------------------------------------------------------------------------------
-// planes [rows_pad, ld] hi then lo (lo plane at +plane_elems)
+// max |X[r, idx[k]]| (or X[r, k]) over r < n, k < n_idx -> meta amax
+__global__ void absmax_kernel(const float* __restrict__ X, int d, const int* __restrict__ idx, int n_idx, int64_t n,
+                              float* __restrict__ meta) {
+  float m = 0.f;
+  const int64_t total = n * n_idx;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / n_idx;
+    const int k = (int)(e - r * n_idx);
+    m = fmaxf(m, fabsf(idx ? X[r * d + idx[k]] : X[r * d + k]));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) meta_amax(meta, m);
+}
+
+// planes [rows_pad, ld]: hi plane then lo plane (+plane_elems); scale from the exact amax
 __global__ void gather_split_kernel(const float* __restrict__ X, int d, const int* __restrict__ idx, int n_idx, int64_t n,
-                                    __nv_bfloat16* __restrict__ out, int ld, int64_t plane_elems) {
+                                    __half* __restrict__ out, int ld, int64_t plane_elems, float* __restrict__ meta) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float s = pow2_scale(__uint_as_float(reinterpret_cast<const unsigned int*>(meta)[1]));
+  if (e == 0) meta[0] = s;
   if (e >= n * ld) return;
   const int64_t r = e / ld;
   const int k = (int)(e - r * ld);
   float v = 0.f;
-  if (k < n_idx) v = idx ? X[r * d + idx[k]] : X[r * d + k];
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  if (k < n_idx) v = (idx ? X[r * d + idx[k]] : X[r * d + k]) * s;
+  const __half h = __float2half_rn(v);
   out[e] = h;
-  out[plane_elems + e] = __float2bfloat16_rn(v - __bfloat162float(h));
+  out[plane_elems + e] = __float2half_rn(v - __half2float(h));
 }
 
-__global__ void plane_colsum_kernel(const __nv_bfloat16* __restrict__ P, int ld, int64_t plane_elems, int64_t n, int ncols,
-                                    int64_t rows_per_block, int use_lo, double* __restrict__ out) {
+__global__ void plane_colsum_kernel(const __half* __restrict__ P, int ld, int64_t plane_elems, int64_t n, int ncols,
+                                    int64_t rows_per_block, int use_lo, const float* __restrict__ meta, double* __restrict__ out) {
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+  const float inv = 1.f / meta[0];
   for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
     float s = 0.f;
     for (int64_t r = r0; r < r1; ++r) {
-      float v = __bfloat162float(P[r * ld + c]);
-      if (use_lo) v += __bfloat162float(P[plane_elems + r * ld + c]);
+      float v = __half2float(P[r * ld + c]);
+      if (use_lo) v += __half2float(P[plane_elems + r * ld + c]);
       s += v;
     }
-    atomicAdd(&out[c], (double)s);
+    atomicAdd(&out[c], (double)(s * inv));
   }
 }
 
@@ -513,29 +601,60 @@ struct DensePrep {
   int kin, nout;
   int kin_p, nf_rows;       // forward planes  Wf [nf_rows][kin_p]   : Wf[o][k] = Wt[k][o]
   int nout_p, nd_rows;      // dgrad planes    Wd [nd_rows][nout_p]  : Wd[k][o] = Wt[k][o]
-  int64_t wf_off, wd_off, bias_off;   // element offsets into the bf16 pool / float bias pool
+  int64_t wf_off, wd_off, bias_off;   // element offsets into the fp16 pool / float bias pool
 };
 
+// one block per Dense: [0] weight scale, [1] max_o sum_k |W[o,k]|, [2] max_k sum_o |W[o,k]|, [3] max |b|
+__global__ void prep_scalars_kernel(const float* __restrict__ theta, const DensePrep* __restrict__ preps, float* __restrict__ sc) {
+  const DensePrep d = preps[blockIdx.x];
+  const float* Wt = theta + d.w_off;   // [kin][nout]
+  float wmax = 0.f, rowl1 = 0.f, coll1 = 0.f, bmax = 0.f;
+  for (int o = threadIdx.x; o < d.nout; o += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < d.kin; ++k) { const float a = fabsf(Wt[(int64_t)k * d.nout + o]); s += a; wmax = fmaxf(wmax, a); }
+    rowl1 = fmaxf(rowl1, s);
+    bmax = fmaxf(bmax, fabsf(theta[d.b_off + o]));
+  }
+  for (int k = threadIdx.x; k < d.kin; k += blockDim.x) {
+    float s = 0.f;
+    for (int o = 0; o < d.nout; ++o) s += fabsf(Wt[(int64_t)k * d.nout + o]);
+    coll1 = fmaxf(coll1, s);
+  }
+  __shared__ float red[4][32];
+  wmax = warp_max(wmax); rowl1 = warp_max(rowl1); coll1 = warp_max(coll1); bmax = warp_max(bmax);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = wmax; red[1][w] = rowl1; red[2][w] = coll1; red[3][w] = bmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int i = 1; i < nw; ++i) { red[0][0] = fmaxf(red[0][0], red[0][i]); red[1][0] = fmaxf(red[1][0], red[1][i]);
+                                   red[2][0] = fmaxf(red[2][0], red[2][i]); red[3][0] = fmaxf(red[3][0], red[3][i]); }
+    float* o = sc + 4 * blockIdx.x;
+    o[0] = pow2_scale(red[0][0]); o[1] = red[1][0]; o[2] = red[2][0]; o[3] = red[3][0];
+  }
+}
+
 __global__ void prep_weights_kernel(const float* __restrict__ theta, const DensePrep* __restrict__ preps, int n_preps,
-                                    __nv_bfloat16* __restrict__ pool, float* __restrict__ bias_pool) {
+                                    const float* __restrict__ sc, __half* __restrict__ pool, float* __restrict__ bias_pool) {
   const int pi = blockIdx.y;
   if (pi >= n_preps) return;
   const DensePrep d = preps[pi];
+  const float ws = sc[4 * pi];
   const int64_t nf = (int64_t)d.nf_rows * d.kin_p, nd = (int64_t)d.nd_rows * d.nout_p;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nf + nd + d.nf_rows; e += (int64_t)gridDim.x * blockDim.x) {
     if (e < nf) {
       const int o = (int)(e / d.kin_p), k = (int)(e % d.kin_p);
-      const float v = (o < d.nout && k < d.kin) ? theta[d.w_off + (int64_t)k * d.nout + o] : 0.f;
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const float v = (o < d.nout && k < d.kin) ? theta[d.w_off + (int64_t)k * d.nout + o] * ws : 0.f;
+      const __half h = __float2half_rn(v);
       pool[d.wf_off + e] = h;
-      pool[d.wf_off + nf + e] = __float2bfloat16_rn(v - __bfloat162float(h));
+      pool[d.wf_off + nf + e] = __float2half_rn(v - __half2float(h));
     } else if (e < nf + nd) {
       const int64_t q = e - nf;
       const int k = (int)(q / d.nout_p), o = (int)(q % d.nout_p);
-      const float v = (o < d.nout && k < d.kin) ? theta[d.w_off + (int64_t)k * d.nout + o] : 0.f;
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const float v = (o < d.nout && k < d.kin) ? theta[d.w_off + (int64_t)k * d.nout + o] * ws : 0.f;
+      const __half h = __float2half_rn(v);
       pool[d.wd_off + q] = h;
-      pool[d.wd_off + nd + q] = __float2bfloat16_rn(v - __bfloat162float(h));
+      pool[d.wd_off + nd + q] = __float2half_rn(v - __half2float(h));
     } else {
       const int o = (int)(e - nf - nd);
       bias_pool[d.bias_off + o] = o < d.nout ? theta[d.b_off + o] : 0.f;
@@ -561,12 +680,33 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+constexpr int kMetaSlots = 8192;
+
+// Expected relative shortfall of one K slab accumulated by the RZ-rounding tensor core: n_main = average
+// number of hi*hi MMAs per slab that carry data.  Calibrated on B200 with tests/debug_gemm.py
+// (4 main MMAs: -9.0e-8, 2 main MMAs: -5.3e-8); about one fp32 ulp, applied to the de-scaling factor.
+float rz_compensation(int k_valid, int n_slabs) {
+  static float c0 = -1.f, c1 = -1.f;
+  if (c0 < 0.f) {
+    const char* e0 = getenv("NFCUDA_RZ_C0");
+    const char* e1 = getenv("NFCUDA_RZ_C1");
+    c0 = e0 ? (float)atof(e0) : 2.0e-8f;
+    c1 = e1 ? (float)atof(e1) : 1.75e-8f;
+  }
+  const float n_main = (float)((k_valid + 15) / 16) / (float)(n_slabs > 0 ? n_slabs : 1);
+  return c0 + c1 * n_main;
+}
+
 struct TcState {
   std::vector<DensePrep> preps;             // flattened [layer][mlp][dense]
   std::vector<std::vector<std::vector<int>>> index;   // index[layer][mlp][dense] -> preps slot
   DensePrep* d_preps = nullptr;
-  __nv_bfloat16* pool = nullptr;
+  float* d_scalars = nullptr;               // [n_preps][4]
+  __half* pool = nullptr;
   float* bias_pool = nullptr;
+  float* meta_pool = nullptr;               // [kMetaSlots][2]
+  int next_slot = 0;
+  std::map<const void*, int> slot_of;
   int64_t pool_elems = 0, bias_elems = 0;
   std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int, int>, CUtensorMap> maps;
 };
@@ -575,6 +715,18 @@ inline int pick_bn(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 12
 inline int pad64(int v) { return (int)round_up(v, 64); }
 
 TcState* get_state(Flow& f) { return (TcState*)f.tc_state; }
+
+// a tensor is (re)produced into `buf`: give it a fresh zeroed meta slot
+float* new_meta(TcState* st, const void* buf) {
+  if (st->next_slot >= kMetaSlots) return nullptr;
+  const int s = st->next_slot++;
+  st->slot_of[buf] = s;
+  return st->meta_pool + 2 * s;
+}
+float* meta_of(TcState* st, const void* buf) {
+  auto it = st->slot_of.find(buf);
+  return it == st->slot_of.end() ? nullptr : st->meta_pool + 2 * it->second;
+}
 
 int ensure_state(Flow& f) {
   if (f.tc_state) return NF_OK;
@@ -605,9 +757,11 @@ int ensure_state(Flow& f) {
     }
   }
   st->pool_elems = pool; st->bias_elems = bias;
-  NF_CUDA(cudaMalloc((void**)&st->pool, pool * sizeof(__nv_bfloat16)));
-  NF_CUDA(cudaMalloc((void**)&st->bias_pool, bias * sizeof(float)));
-  NF_CUDA(cudaMalloc((void**)&st->d_preps, st->preps.size() * sizeof(DensePrep)));
+  NF_CUDA(cudaMalloc((void**)&st->pool, std::max<int64_t>(pool, 1) * sizeof(__half)));
+  NF_CUDA(cudaMalloc((void**)&st->bias_pool, std::max<int64_t>(bias, 1) * sizeof(float)));
+  NF_CUDA(cudaMalloc((void**)&st->d_preps, std::max<size_t>(st->preps.size(), 1) * sizeof(DensePrep)));
+  NF_CUDA(cudaMalloc((void**)&st->d_scalars, std::max<size_t>(st->preps.size(), 1) * 4 * sizeof(float)));
+  NF_CUDA(cudaMalloc((void**)&st->meta_pool, kMetaSlots * 2 * sizeof(float)));
   NF_CUDA(cudaMemcpy(st->d_preps, st->preps.data(), st->preps.size() * sizeof(DensePrep), cudaMemcpyHostToDevice));
   return NF_OK;
 }
@@ -623,10 +777,11 @@ int make_map_kmajor(TcState* st, const void* basep, int64_t rows, int64_t cols, 
   cuuint64_t gstr[2] = {(cuuint64_t)cols * 2, (cuuint64_t)plane_elems * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(basep), gdim, gstr, box, estr,
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(basep), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (K-major) failed: %d (rows %lld cols %lld)", (int)r, (long long)rows, (long long)cols); return NF_ERR_CUDA; }
+  if (st->maps.size() > 4096) st->maps.clear();
   st->maps[key] = *out;
   return NF_OK;
 }
@@ -642,10 +797,11 @@ int make_map_mnmajor(TcState* st, const void* basep, int64_t rows, int64_t cols,
   cuuint64_t gstr[3] = {(cuuint64_t)cols * 2, 128, (cuuint64_t)plane_elems * 2};
   cuuint32_t box[4] = {64, 32, (cuuint32_t)nblocks, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(basep), gdim, gstr, box, estr,
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(basep), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (MN-major) failed: %d (rows %lld cols %lld)", (int)r, (long long)rows, (long long)cols); return NF_ERR_CUDA; }
+  if (st->maps.size() > 4096) st->maps.clear();
   st->maps[key] = *out;
   return NF_OK;
 }
@@ -661,7 +817,7 @@ int launch_gemm_bn(Flow& f, const CUtensorMap& ma, const CUtensorMap& mb, const 
   }
   const int64_t tiles = ceil_div(p.M, 128);
   dim3 grid((unsigned)std::min<int64_t>(tiles, std::max(1, kNumSMs / n_tiles_n)), (unsigned)n_tiles_n);
-  kern<<<grid, 192, Cfg::SMEM, f.stream>>>(ma, mb, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, f.stream>>>(ma, mb, p);
   NF_LAUNCH_CHECK();
   return NF_OK;
 }
@@ -693,12 +849,25 @@ int launch_wgrad_bn(Flow& f, const CUtensorMap& mx, const CUtensorMap& mg, const
 }
 
 struct Planes {
-  __nv_bfloat16* p;
+  __half* p;
   int64_t rows_pad;
   int ld;
   int64_t plane_elems() const { return rows_pad * ld; }
 };
-inline Planes planes_of(void* buf, int64_t n, int width) { return Planes{(__nv_bfloat16*)buf, round_up(n, 128), pad64(width)}; }
+inline Planes planes_of(void* buf, int64_t n, int width) { return Planes{(__half*)buf, round_up(n, 128), pad64(width)}; }
+
+// fp32 [n, ld_src] (optionally gathered columns) -> split planes with an exact-amax scale
+int split_into_planes(Flow& f, TcState* st, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* buf) {
+  Planes P = planes_of(buf, n, n_idx);
+  float* meta = new_meta(st, buf);
+  NF_REQUIRE(meta, "tcgen05 path: out of tensor metadata slots");
+  const int64_t total = n * n_idx;
+  absmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256 * 8), 4 * kNumSMs), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, meta);
+  NF_LAUNCH_CHECK();
+  gather_split_kernel<<<(unsigned)ceil_div(n * P.ld, 256), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, P.p, P.ld, P.plane_elems(), meta);
+  NF_LAUNCH_CHECK();
+  return NF_OK;
+}
 
 }  // namespace
 
@@ -708,38 +877,49 @@ size_t tc_weight_bytes(const Flow&) { return 0; }
 void tc_release(Flow& f) {
   TcState* st = get_state(f);
   if (!st) return;
-  cudaFree(st->pool); cudaFree(st->bias_pool); cudaFree(st->d_preps);
+  cudaFree(st->pool); cudaFree(st->bias_pool); cudaFree(st->d_preps); cudaFree(st->d_scalars); cudaFree(st->meta_pool);
   delete st;
   f.tc_state = nullptr;
+}
+
+int tc_begin_chunk(Flow& f) {
+  NF_TRY(ensure_state(f));
+  TcState* st = get_state(f);
+  st->next_slot = 0;
+  st->slot_of.clear();
+  NF_CUDA(cudaMemsetAsync(st->meta_pool, 0, kMetaSlots * 2 * sizeof(float), f.stream));
+  return NF_OK;
 }
 
 int tc_prepare_weights(Flow& f, const float* theta_dev) {
   NF_TRY(ensure_state(f));
   TcState* st = get_state(f);
+  NF_TRY(tc_begin_chunk(f));
   if (st->preps.empty()) return NF_OK;
+  prep_scalars_kernel<<<(unsigned)st->preps.size(), 256, 0, f.stream>>>(theta_dev, st->d_preps, st->d_scalars);
+  NF_LAUNCH_CHECK();
   dim3 grid(64, (unsigned)st->preps.size());
-  prep_weights_kernel<<<grid, 256, 0, f.stream>>>(theta_dev, st->d_preps, (int)st->preps.size(), st->pool, st->bias_pool);
+  prep_weights_kernel<<<grid, 256, 0, f.stream>>>(theta_dev, st->d_preps, (int)st->preps.size(), st->d_scalars, st->pool, st->bias_pool);
   NF_LAUNCH_CHECK();
   return NF_OK;
 }
 
 int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* act0) {
-  Planes P = planes_of(act0, n, n_idx);
-  gather_split_kernel<<<(unsigned)ceil_div(n * P.ld, 256), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, P.p, P.ld, P.plane_elems());
-  NF_LAUNCH_CHECK();
-  return NF_OK;
+  return split_into_planes(f, get_state(f), X, d, d_idx, n_idx, n, act0);
 }
 
 int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts) {
   TcState* st = get_state(f);
   const int li = (int)(&Ld - f.layers.data());
   const MLPDesc& md = Ld.mlps[m];
-  const int terms = f.mma_mode == NF_MMA_BF16X1 ? 1 : 3;
+  const int terms = f.mma_mode == NF_MMA_F16X1 ? 1 : 3;
   const int nd = md.n_dense();
   for (int i = 0; i < nd; ++i) {
-    const DensePrep& dp = st->preps[st->index[li][m][i]];
+    const int pi = st->index[li][m][i];
+    const DensePrep& dp = st->preps[pi];
     const bool last = (i + 1 == nd);
-    Planes A = planes_of(i == 0 ? act0 : acts[i - 1], n, dp.kin);
+    void* abuf = i == 0 ? act0 : acts[i - 1];
+    Planes A = planes_of(abuf, n, dp.kin);
     const int bn = std::min(dp.nf_rows, 256);
     const int n_tiles_n = dp.nf_rows / bn;
     CUtensorMap ma, mb;
@@ -747,9 +927,16 @@ int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, s
     NF_TRY(make_map_kmajor(st, st->pool + dp.wf_off, dp.nf_rows, dp.kin_p, (int64_t)dp.nf_rows * dp.kin_p, bn, &mb));
     GemmParams p{};
     p.M = n; p.num_k_chunks = dp.kin_p / 64; p.terms = terms;
+    p.a_meta = meta_of(st, abuf);
+    NF_REQUIRE(p.a_meta, "tcgen05 path: missing tensor metadata (forward input)");
+    p.w_sc = st->d_scalars + 4 * pi;
+    p.bound_dgrad = 0;
+    p.rz_comp = rz_compensation(dp.kin, p.num_k_chunks);
     p.bias = st->bias_pool + dp.bias_off;
     if (!last) {
       Planes O = planes_of(acts[i], n, dp.nout);
+      p.out_meta = new_meta(st, acts[i]);
+      NF_REQUIRE(p.out_meta, "tcgen05 path: out of tensor metadata slots");
       p.epi = EPI_PLANES_ACT; p.act = ACT_LRELU; p.n_store = O.ld;
       p.out_hi = O.p; p.out_lo = O.p + O.plane_elems(); p.out_ld = O.ld;
     } else {
@@ -766,25 +953,25 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
   TcState* st = get_state(f);
   const int li = (int)(&Ld - f.layers.data());
   const MLPDesc& md = Ld.mlps[m];
-  const int terms = f.mma_mode == NF_MMA_BF16X1 ? 1 : 3;
+  const int terms = f.mma_mode == NF_MMA_F16X1 ? 1 : 3;
   const int nd = md.n_dense();
-  // gradient w.r.t. the last pre-activation -> split planes
   void* gbuf = scratch0;
   void* gnext = scratch1;
-  {
-    Planes Gp = planes_of(gbuf, n, md.dims[nd]);
-    gather_split_kernel<<<(unsigned)ceil_div(n * Gp.ld, 256), 256, 0, f.stream>>>(g_last, md.dims[nd], nullptr, md.dims[nd], n, Gp.p,
-                                                                                  Gp.ld, Gp.plane_elems());
-    NF_LAUNCH_CHECK();
-  }
+  // gradient w.r.t. the last pre-activation -> split planes
+  NF_TRY(split_into_planes(f, st, g_last, md.dims[nd], nullptr, md.dims[nd], n, gbuf));
   for (int i = nd - 1; i >= 0; --i) {
-    const DensePrep& dp = st->preps[st->index[li][m][i]];
+    const int pi = st->index[li][m][i];
+    const DensePrep& dp = st->preps[pi];
     Planes Gp = planes_of(gbuf, n, dp.nout);
-    Planes X = planes_of(i == 0 ? act0 : acts[i - 1], n, dp.kin);
+    void* xbuf = i == 0 ? act0 : acts[i - 1];
+    Planes X = planes_of(xbuf, n, dp.kin);
+    const float* g_meta = meta_of(st, gbuf);
+    const float* x_meta = meta_of(st, xbuf);
+    NF_REQUIRE(g_meta && x_meta, "tcgen05 path: missing tensor metadata (backward)");
     {  // bias gradient
       const int64_t rpb = 1024;
       plane_colsum_kernel<<<(unsigned)ceil_div(n, rpb), 256, 0, f.stream>>>(Gp.p, Gp.ld, Gp.plane_elems(), n, dp.nout, rpb,
-                                                                          terms > 1 ? 1 : 0, gsum + dp.b_off);
+                                                                          terms > 1 ? 1 : 0, g_meta, gsum + dp.b_off);
       NF_LAUNCH_CHECK();
     }
     {  // weight gradient
@@ -795,6 +982,7 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
       NF_TRY(make_map_mnmajor(st, Gp.p, n, Gp.ld, Gp.plane_elems(), Gp.ld / 64, &mg));
       WgradParams wp{};
       wp.n = n; wp.kin = dp.kin; wp.nout = dp.nout; wp.mt = mt; wp.terms = terms; wp.gW = gsum + dp.w_off;
+      wp.x_meta = x_meta; wp.g_meta = g_meta;
       switch (Gp.ld) {
         case 64: NF_TRY(launch_wgrad_bn<64>(f, mx, mg, wp)); break;
         case 128: NF_TRY(launch_wgrad_bn<128>(f, mx, mg, wp)); break;
@@ -810,8 +998,12 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
       NF_TRY(make_map_kmajor(st, st->pool + dp.wd_off, dp.nd_rows, dp.nout_p, (int64_t)dp.nd_rows * dp.nout_p, bn, &mb));
       GemmParams p{};
       p.M = n; p.num_k_chunks = dp.nout_p / 64; p.terms = terms;
+      p.a_meta = g_meta; p.w_sc = st->d_scalars + 4 * pi; p.bound_dgrad = 1;
+      p.rz_comp = rz_compensation(dp.nout, p.num_k_chunks);
       if (i > 0) {
         Planes O = planes_of(gnext, n, dp.kin);
+        p.out_meta = new_meta(st, gnext);
+        NF_REQUIRE(p.out_meta, "tcgen05 path: out of tensor metadata slots");
         p.epi = EPI_PLANES_MASK; p.n_store = O.ld;
         p.out_hi = O.p; p.out_lo = O.p + O.plane_elems(); p.out_ld = O.ld;
         p.mask_hi = X.p; p.mask_ld = X.ld;
@@ -823,6 +1015,50 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
     }
   }
   return NF_OK;
+}
+
+
+// Test hook: Y[n, N] = X[n, K] * Wt[K, N] + b through the tcgen05 forward GEMM (one Dense, no activation).
+int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* Wt_host, const float* b_host, int terms,
+                     float* Y_host) {
+  Flow f;
+  f.dim = K + N; f.dtype = NF_F32;
+  f.mma_mode = terms == 1 ? NF_MMA_F16X1 : NF_MMA_F16X3;
+  NF_CUDA(cudaGetDevice(&f.device));
+  NF_CUDA(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+  LayerDesc L;
+  L.kind = NF_AFFINE_COUPLING;
+  MLPDesc md;
+  md.dims = {K, N};
+  md.w_off = {0}; md.b_off = {(int64_t)K * N};
+  md.out_act = 0;
+  L.mlps.push_back(md);
+  f.layers.push_back(L);
+  f.P = (int64_t)K * N + N;
+  float *theta = nullptr, *X = nullptr, *Y = nullptr;
+  void* act0 = nullptr;
+  int status = NF_OK;
+  auto body = [&]() -> int {
+    NF_CUDA(cudaMalloc((void**)&theta, f.P * sizeof(float)));
+    NF_CUDA(cudaMalloc((void**)&X, (size_t)n * K * sizeof(float)));
+    NF_CUDA(cudaMalloc((void**)&Y, (size_t)n * N * sizeof(float)));
+    NF_CUDA(cudaMalloc(&act0, tc_act_bytes(n, K)));
+    NF_CUDA(cudaMemcpy(theta, Wt_host, (size_t)K * N * sizeof(float), cudaMemcpyHostToDevice));
+    NF_CUDA(cudaMemcpy(theta + (size_t)K * N, b_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
+    NF_CUDA(cudaMemcpy(X, X_host, (size_t)n * K * sizeof(float), cudaMemcpyHostToDevice));
+    NF_TRY(tc_prepare_weights(f, theta));
+    NF_TRY(tc_gather_split(f, X, K, nullptr, K, n, act0));
+    std::vector<void*> acts{(void*)Y};
+    NF_TRY(tc_mlp_forward(f, f.layers[0], 0, n, act0, acts));
+    NF_CUDA(cudaStreamSynchronize(f.stream));
+    NF_CUDA(cudaMemcpy(Y_host, Y, (size_t)n * N * sizeof(float), cudaMemcpyDeviceToHost));
+    return NF_OK;
+  };
+  status = body();
+  cudaFree(theta); cudaFree(X); cudaFree(Y); cudaFree(act0);
+  tc_release(f);
+  cudaStreamDestroy(f.stream);
+  return status;
 }
 
 }  // namespace nf

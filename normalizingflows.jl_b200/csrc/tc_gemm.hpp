@@ -10,6 +10,8 @@ size_t tc_act_bytes(int64_t n, int width);
 size_t tc_weight_bytes(const Flow& f);
 // theta -> transposed / split bf16 weight planes (once per call, before any tc_mlp_*)
 int tc_prepare_weights(Flow& f, const float* theta_dev);
+// forget the per-tensor scale slots of the previous sample chunk (buffers are about to be reused)
+int tc_begin_chunk(Flow& f);
 // x2 = X[:, idx2] -> split planes
 int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* act0);
 int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts);
@@ -17,5 +19,7 @@ int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, s
 int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts, float* g_last,
                     void* scratch0, void* scratch1, float* G, double* gsum);
 void tc_release(Flow& f);
+int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* Wt_host, const float* b_host, int terms,
+                     float* Y_host);
 
 }  // namespace nf

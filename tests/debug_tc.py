@@ -8,7 +8,7 @@ from helpers import *
 
 nf = nfload.load()
 nf._capi.check(nf._capi.lib().nf_init(0))
-mode = {"simt": nf.NF_MMA_SIMT, "x3": nf.NF_MMA_BF16X3, "x1": nf.NF_MMA_BF16X1}[sys.argv[1] if len(sys.argv) > 1 else "x3"]
+mode = {"simt": nf.NF_MMA_SIMT, "x3": nf.NF_MMA_F16X3, "x1": nf.NF_MMA_F16X1}[sys.argv[1] if len(sys.argv) > 1 else "x3"]
 
 def run(kind, dim, tn, N, kw):
     of = oracle_flow(kind, dim, np.float64, **kw)
