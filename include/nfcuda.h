@@ -191,6 +191,12 @@ NF_API int64_t nf_launch_count(int reset);
 /* Duration (ms, CUDA events on the flow's stream) of the device work of the last value_and_grad call. */
 NF_API double  nf_last_device_ms(nf_flow_t flow);
 
+/* Per-kernel-class device timing (CUDA events on the flow's stream), used by bench.py for the roofline:
+ * enable, run, then list the recorded classes (comma separated) and collect {launches, total ms} per class. */
+NF_API int nf_profile_enable(nf_flow_t flow, int on);
+NF_API int nf_profile_keys(nf_flow_t flow, char* buf, int buflen);
+NF_API int nf_profile_collect(nf_flow_t flow, const char* key, int64_t* launches, double* total_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,9 @@ SIGNATURES = {
     "nf_tc_gemm_test": (_i, [_i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "nf_launch_count": (_i64, [_i]),
     "nf_last_device_ms": (_d, [_vp]),
+    "nf_profile_enable": (_i, [_vp, _i]),
+    "nf_profile_keys": (_i, [_vp, C.c_char_p, _i]),
+    "nf_profile_collect": (_i, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_d)]),
 }
 
 _lib = None

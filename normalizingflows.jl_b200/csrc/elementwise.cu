@@ -427,7 +427,9 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
   a.gpart = gpart; a.epart = epart; a.N = N; a.L = L; a.d = d;
   a.flags = flags | (z0_dev ? 0 : EW_GEN_Z0);
   a.seed = seed;
+  f.prof.begin("ew_flow", f.stream);
   kern<<<grid, threads, smem, f.stream>>>(a);
+  f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
   if (gsum_dev) {
     ew_finalize_kernel<T, DP><<<(L + 63) / 64, 64, 0, f.stream>>>(theta_dev, f.d_ew_meta, L, d, gpart, epart, grid, N,

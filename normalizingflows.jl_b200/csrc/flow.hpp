@@ -8,6 +8,8 @@
 #include "targets.cuh"
 #include <algorithm>
 #include <memory>
+#include <map>
+#include <string>
 
 namespace nf {
 
@@ -41,6 +43,44 @@ struct LayerDesc {
   std::vector<MLPDesc> mlps;           // affine: {s, t}; spline: {nn}
   int K = 0;
   double B = 0;
+};
+
+// Optional per-kernel-class timing with CUDA events on the flow's stream (bench.py roofline numbers).
+struct Profiler {
+  bool on = false;
+  struct Rec { cudaEvent_t a, b; };
+  std::map<std::string, std::vector<Rec>> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(const std::string& key, cudaStream_t st) {
+    if (!on) return;
+    Rec r{get(), get()};
+    cudaEventRecord(r.a, st);
+    recs[key].push_back(r);
+    cur = key;
+  }
+  void end(cudaStream_t st) {
+    if (!on || cur.empty()) return;
+    cudaEventRecord(recs[cur].back().b, st);
+    cur.clear();
+  }
+  // call after the stream has been synchronised; returns launches and total ms, recycles the events
+  void collect(const std::string& key, int64_t* count, double* ms) {
+    *count = 0; *ms = 0;
+    auto it = recs.find(key);
+    if (it == recs.end()) return;
+    for (auto& r : it->second) {
+      float t = 0; cudaEventElapsedTime(&t, r.a, r.b);
+      *ms += t; ++*count;
+      pool.push_back(r.a); pool.push_back(r.b);
+    }
+    recs.erase(it);
+  }
+  std::string keys() const { std::string k; for (auto& kv : recs) { if (!k.empty()) k += ","; k += kv.first; } return k; }
+  std::string cur;
 };
 
 struct Workspace {
@@ -77,6 +117,7 @@ struct Flow {
   size_t h_pinned_bytes = 0;
 
   Workspace ws;
+  Profiler prof;
   void ws_reset() { ws.off = 0; }
   void* ws_alloc(size_t bytes);        // bump allocation, 256 B aligned; nullptr (+error) when exhausted
   int ws_reserve(size_t bytes);        // make sure capacity >= bytes (reallocates; invalidates pointers)

@@ -617,4 +617,28 @@ int64_t nf_launch_count(int reset) {
 
 double nf_last_device_ms(nf_flow_t flow) { return flow ? NF_FLOW(flow).last_ms : -1.0; }
 
+int nf_profile_enable(nf_flow_t flow, int on) {
+  NF_CHECK_HANDLE(flow);
+  NF_FLOW(flow).prof.on = on != 0;
+  return NF_OK;
+}
+
+int nf_profile_keys(nf_flow_t flow, char* buf, int buflen) {
+  NF_CHECK_HANDLE(flow);
+  NF_REQUIRE(buf && buflen > 0, "bad argument");
+  const std::string k = NF_FLOW(flow).prof.keys();
+  snprintf(buf, buflen, "%s", k.c_str());
+  return NF_OK;
+}
+
+int nf_profile_collect(nf_flow_t flow, const char* key, int64_t* launches, double* total_ms) {
+  NF_CHECK_HANDLE(flow);
+  NF_REQUIRE(key && launches && total_ms, "null argument");
+  Flow& f = NF_FLOW(flow);
+  NF_CUDA(cudaSetDevice(f.device));
+  NF_CUDA(cudaStreamSynchronize(f.stream));
+  f.prof.collect(key, launches, total_ms);
+  return NF_OK;
+}
+
 }  // extern "C"

@@ -817,7 +817,13 @@ int launch_gemm_bn(Flow& f, const CUtensorMap& ma, const CUtensorMap& mb, const 
   }
   const int64_t tiles = ceil_div(p.M, 128);
   dim3 grid((unsigned)std::min<int64_t>(tiles, std::max(1, kNumSMs / n_tiles_n)), (unsigned)n_tiles_n);
+  if (f.prof.on) {
+    char key[64];
+    snprintf(key, sizeof(key), "tc_gemm_n%d_k%d", BN, p.num_k_chunks * 64);
+    f.prof.begin(key, f.stream);
+  }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, f.stream>>>(ma, mb, p);
+  f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
   return NF_OK;
 }
@@ -843,7 +849,13 @@ int launch_wgrad_bn(Flow& f, const CUtensorMap& mx, const CUtensorMap& mg, const
   const int64_t chunks = ceil_div(p.n, Cfg::KS);
   // at least 8 chunks (256 samples) per CTA so the atomic flush is amortised
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(kNumSMs, chunks / 8));
+  if (f.prof.on) {
+    char key[64];
+    snprintf(key, sizeof(key), "tc_wgrad_m%d_n%d", p.mt * 128, BN);
+    f.prof.begin(key, f.stream);
+  }
   kern<<<grid, 192, Cfg::SMEM, f.stream>>>(mx, mg, p);
+  f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
   return NF_OK;
 }

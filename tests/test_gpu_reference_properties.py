@@ -31,8 +31,6 @@ def test_flow_elbo_finite(gpu, kind, T):
     nf.seed(123)
     flow = {"realnvp": lambda: nf.realnvp(q0, [32, 32], 2, T), "nsf": lambda: nf.nsf(q0, [32, 32], 10, 5.0, 2, T),
             "planar": lambda: nf.planarflow(q0, 10, T), "radial": lambda: nf.radialflow(q0, 10, T)}[kind]()
-    if kind in ("realnvp", "nsf") and T == np.float32:
-        flow.set_mma_mode(nf.NF_MMA_SIMT)
     rng = np.random.Generator(np.random.PCG64(2))
     target = nf.DiagNormal(rng.standard_normal(dim), np.sqrt(rng.random(dim) + 1e-3))
     assert np.isfinite(nf.elbo(rng, flow, target, 64))
