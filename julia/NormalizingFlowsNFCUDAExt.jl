@@ -1,0 +1,166 @@
+# NormalizingFlowsNFCUDAExt -- the Julia side of the drop-in (UNEXECUTED in the build image: no Julia there).
+#
+# What a maintainer adds to NormalizingFlows.jl to run the ELBO / log-likelihood value+gradient on
+# libnfcuda behind the package's own seam:
+#     _prepare_gradient / _value_and_gradient         (src/optimize.jl:8-14)
+# selected by `train_flow(...; ADbackend = AutoNFCUDA(...))` (src/NormalizingFlows.jl:54-86).
+# `optimize`, Optimisers.jl, callbacks, convergence checks and the destructure'd theta stay untouched.
+# It supersedes ext/NormalizingFlowsCUDAExt.jl (which only sampled on the GPU, column by column).
+#
+# Packaging: list `libnfcuda_jll` (or a path in ENV["NFCUDA_LIB"]) as a weak dependency in Project.toml
+#   [weakdeps]  NFCUDA = "..."        [extensions]  NormalizingFlowsNFCUDAExt = "NFCUDA"
+module NormalizingFlowsNFCUDAExt
+
+using NormalizingFlows
+using NormalizingFlows: Bijectors, Distributions, Optimisers, ADTypes, Random
+import NormalizingFlows: _prepare_gradient, _value_and_gradient, _device_specific_rand
+
+const libnfcuda = get(ENV, "NFCUDA_LIB", "libnfcuda")
+
+# ---- C structs of include/nfcuda.h -----------------------------------------------------------------
+struct NFLayerDesc
+    kind::Cint
+    mask_idx::Ptr{Cint}
+    n_mask::Cint
+    hdims::Ptr{Cint}
+    n_hidden::Cint
+    K::Cint
+    B::Cdouble
+end
+const NF_F32, NF_F64 = Cint(0), Cint(1)
+const NF_PLANAR, NF_RADIAL, NF_AFFINE, NF_SPLINE, NF_SHIFT, NF_SCALE = Cint.(1:6)
+
+function check(status::Cint)
+    status == 0 && return nothing
+    error("libnfcuda error $status: " * unsafe_string(ccall((:nf_last_error, libnfcuda), Cstring, ())))
+end
+
+# ---- the ADTypes backend tag -------------------------------------------------------------------------
+"""
+    AutoNFCUDA(; device = 0, target)
+
+`target` names a device-side log-density: `(:banana, b, var)`, `(:funnel, μ, σ)`, `(:warped_gauss, σ1, σ2)`,
+`(:cross, μ, σ)`, `(:diag_normal, μ, σ)`.  The Julia `logp` closure handed to `train_flow` is used only
+to recognise the example targets; an arbitrary closure cannot cross the C ABI (use `nf_forward_stash` /
+`nf_backward` with CUDA.jl evaluating logp and its score on the device buffer).
+"""
+struct AutoNFCUDA <: ADTypes.AbstractADType
+    device::Int
+    target::Tuple
+end
+AutoNFCUDA(; device=0, target) = AutoNFCUDA(device, target)
+export AutoNFCUDA
+
+# ---- flow structure -> nf_layer_desc[] in theta (= Ls) order ------------------------------------------
+flatten_layers(f::ComposedFunction) = vcat(flatten_layers(f.outer), flatten_layers(f.inner))
+flatten_layers(f) = Any[f]
+
+hidden_dims(c) = Cint[size(l.weight, 1) for l in c.layers[1:(end - 1)]]
+
+function describe(layer, keep::Vector{Any})
+    z = Ptr{Cint}(C_NULL)
+    if layer isa Bijectors.PlanarLayer
+        return NFLayerDesc(NF_PLANAR, z, 0, z, 0, 0, 0.0)
+    elseif layer isa Bijectors.RadialLayer
+        return NFLayerDesc(NF_RADIAL, z, 0, z, 0, 0, 0.0)
+    elseif layer isa Bijectors.Shift
+        return NFLayerDesc(NF_SHIFT, z, 0, z, 0, 0, 0.0)
+    elseif layer isa Bijectors.Scale
+        return NFLayerDesc(NF_SCALE, z, 0, z, 0, 0, 0.0)
+    elseif layer isa NormalizingFlows.AffineCoupling
+        idx = Cint.(findall(!iszero, vec(sum(layer.mask.A_1; dims=2))) .- 1)   # PartitionMask transformed rows, 0-based
+        hd = hidden_dims(layer.s)
+        push!(keep, idx, hd)
+        return NFLayerDesc(NF_AFFINE, pointer(idx), length(idx), pointer(hd), length(hd), 0, 0.0)
+    elseif layer isa NormalizingFlows.NeuralSplineCoupling
+        idx = Cint.(findall(!iszero, vec(sum(layer.mask.A_1; dims=2))) .- 1)
+        hd = hidden_dims(layer.nn)
+        push!(keep, idx, hd)
+        return NFLayerDesc(NF_SPLINE, pointer(idx), length(idx), pointer(hd), length(hd), layer.K, Float64(layer.B))
+    end
+    error("NFCUDA: unsupported bijector $(typeof(layer))")
+end
+
+mutable struct Prep
+    flow::Ptr{Cvoid}
+    target::Ptr{Cvoid}
+    P::Int
+    T::DataType
+end
+
+target_kind(s::Symbol) = Dict(:banana => 1, :funnel => 2, :warped_gauss => 3, :cross => 4, :diag_normal => 5)[s]
+
+function make_prep(flow::Bijectors.TransformedDistribution, ad::AutoNFCUDA, ::Type{T}) where {T}
+    check(ccall((:nf_init, libnfcuda), Cint, (Cint,), ad.device))
+    keep = Any[]
+    descs = [describe(l, keep) for l in flatten_layers(flow.transform)]
+    d = length(flow.dist)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep descs check(ccall((:nf_flow_create, libnfcuda), Cint,
+        (Ref{Ptr{Cvoid}}, Ptr{NFLayerDesc}, Cint, Cint, Cint), h, descs, length(descs), d, T === Float32 ? NF_F32 : NF_F64))
+    μ = Float64.(Distributions.mean(flow.dist)); σ = Float64.(sqrt.(Distributions.var(flow.dist)))   # diagonal q₀
+    check(ccall((:nf_flow_set_base, libnfcuda), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h[], μ, σ))
+    tp = Float64[x for p in ad.target[2:end] for x in p]
+    t = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:nf_target_create, libnfcuda), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cdouble}, Cint),
+        t, target_kind(ad.target[1]), d, tp, length(tp)))
+    P = ccall((:nf_flow_num_params, libnfcuda), Int64, (Ptr{Cvoid},), h[])
+    prep = Prep(h[], t[], P, T)
+    finalizer(prep) do p
+        ccall((:nf_flow_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), p.flow)
+        ccall((:nf_target_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), p.target)
+    end
+    return prep
+end
+
+# `loss` is the closure of src/NormalizingFlows.jl:69: loss(θ, rng, args...) = -vo(rng, re(θ), args...)
+# its captured fields give the objective and the Restructure.
+function _prepare_gradient(loss, ad::AutoNFCUDA, θ::AbstractVector{T}, rng, args...) where {T}
+    flow = loss.re(θ)
+    prep = make_prep(flow, ad, T)
+    prep.P == length(θ) || error("NFCUDA: parameter count mismatch ($(prep.P) vs $(length(θ)))")
+    return prep
+end
+
+function _value_and_gradient(loss, prep::Prep, ad::AutoNFCUDA, θ::AbstractVector{T}, rng, args...) where {T}
+    g = similar(θ)
+    val = Ref{Cdouble}(0)
+    vo = loss.vo
+    if vo === NormalizingFlows.elbo || vo === NormalizingFlows.elbo_batch
+        logp, n_or_xs = args
+        if n_or_xs isa Integer                  # elbo([rng,] flow, logp, n): draws on the device (Philox)
+            seed = rand(rng, UInt64)
+            check(ccall((:nf_elbo_value_and_grad, libnfcuda), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{T}, Int64, Ptr{T}, UInt64, Cdouble, Ref{Cdouble}, Ptr{T}),
+                prep.flow, prep.target, θ, n_or_xs, C_NULL, seed, -1.0, val, g))
+        else                                    # elbo(flow, logp, xs::AbstractMatrix): host-supplied d×N draws
+            xs = Matrix{T}(n_or_xs)
+            check(ccall((:nf_elbo_value_and_grad, libnfcuda), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{T}, Int64, Ptr{T}, UInt64, Cdouble, Ref{Cdouble}, Ptr{T}),
+                prep.flow, prep.target, θ, size(xs, 2), xs, 0, -1.0, val, g))
+        end
+    elseif vo === NormalizingFlows.loglikelihood
+        xs = Matrix{T}(args[1])
+        check(ccall((:nf_loglik_value_and_grad, libnfcuda), Cint,
+            (Ptr{Cvoid}, Ptr{T}, Int64, Ptr{T}, Cdouble, Ref{Cdouble}, Ptr{T}),
+            prep.flow, θ, size(xs, 2), xs, -1.0, val, g))
+    else
+        error("NFCUDA: objective must be elbo, elbo_batch or loglikelihood")
+    end
+    return T(val[]), g                           # (loss, gradient) exactly as DI.value_and_gradient returns them
+end
+
+# Batched replacements for the per-column loop of ext/NormalizingFlowsCUDAExt.jl:65-74 ---------------------
+struct NFCUDARNG <: Random.AbstractRNG
+    seed::UInt64
+end
+function _device_specific_rand(rng::NFCUDARNG, td::Bijectors.TransformedDistribution, n::Int)
+    θ, _ = Optimisers.destructure(td)
+    T = eltype(θ)
+    prep = make_prep(td, AutoNFCUDA(0, (:diag_normal, zeros(length(td.dist)), ones(length(td.dist)))), T)
+    ys = Matrix{T}(undef, length(td.dist), n)
+    check(ccall((:nf_sample, libnfcuda), Cint, (Ptr{Cvoid}, Ptr{T}, Int64, UInt64, Ptr{T}), prep.flow, θ, n, rng.seed, ys))
+    return ys
+end
+
+end # module

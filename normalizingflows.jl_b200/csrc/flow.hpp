@@ -40,6 +40,7 @@ struct LayerDesc {
   std::vector<int> idx1, idx2;
   int* d_idx1 = nullptr;
   int* d_idx2 = nullptr;
+  int* d_pos = nullptr;                // [dim]: position of a column inside idx1, or -1
   std::vector<MLPDesc> mlps;           // affine: {s, t}; spline: {nn}
   int K = 0;
   double B = 0;

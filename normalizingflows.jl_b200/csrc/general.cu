@@ -29,6 +29,7 @@ struct Chunk {
   void* gld = nullptr;                        // optional per-sample d/dlogdet (two-phase API)
   std::vector<LayerBufs> lb;                  // stash: one per layer; else a single shared set at [0]
   void* ga[4] = {nullptr, nullptr, nullptr, nullptr};  // backward temporaries (width = max MLP width)
+  std::vector<float*> xmeta;                  // tcgen05 mode: {scale, max|X|} slot per state (bound for the fp16 operand scale)
   int n_states = 0;
 };
 
@@ -187,7 +188,7 @@ int simt_mlp_backward(Flow& f, const MLPDesc& md, const T* theta, int64_t n, con
     const T* in = (i == 0) ? act0 : (const T*)acts[i - 1];
     const int kin = md.dims[i], kout = md.dims[i + 1];
     {
-      const int64_t rpb = 512;
+      const int64_t rpb = 4096;
       colsum_atomic_kernel<T><<<(unsigned)ceil_div(n, rpb), 256, 0, f.stream>>>(g, n, kout, rpb, gsum + md.b_off[i]);
       NF_LAUNCH_CHECK();
     }
@@ -213,11 +214,11 @@ int simt_mlp_backward(Flow& f, const MLPDesc& md, const T* theta, int64_t n, con
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool INV>
 int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, int64_t n, const T* Xin, T* Xout, T* ld,
-                   int32_t* bins) {
+                   int32_t* bins, const float* amax_in, float* amax_out) {
   const int d = f.dim, c = (int)Ld.idx1.size(), cbar = (int)Ld.idx2.size();
   const bool tc = f.mma_mode != NF_MMA_SIMT;
   if (tc) {
-    NF_TRY(tc_gather_split(f, (const float*)Xin, d, Ld.d_idx2, cbar, n, b.act0));
+    NF_TRY(tc_gather_split(f, (const float*)Xin, d, Ld.d_idx2, cbar, n, b.act0, amax_in));
     for (size_t m = 0; m < Ld.mlps.size(); ++m) NF_TRY(tc_mlp_forward(f, Ld, (int)m, n, b.act0, b.acts[m]));
   } else {
     gather_cols_kernel<T><<<(unsigned)ceil_div(n * cbar, 256), 256, 0, f.stream>>>(Xin, d, Ld.d_idx2, cbar, n, (T*)b.act0);
@@ -225,8 +226,8 @@ int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, i
     for (size_t m = 0; m < Ld.mlps.size(); ++m) NF_TRY(simt_mlp_forward<T>(f, Ld.mlps[m], theta, n, (const T*)b.act0, b.acts[m]));
   }
   if (Ld.kind == NF_AFFINE_COUPLING) {
-    affine_apply_kernel<T, INV><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
-        Xin, (const T*)b.acts[0].back(), (const T*)b.acts[1].back(), Ld.d_idx1, c, d, n, Xout, ld);
+    affine_apply_kernel<T, INV><<<(unsigned)std::min<int64_t>(ceil_div(n * d, 256), 16 * kNumSMs), 256, 0, f.stream>>>(
+        Xin, (const T*)b.acts[0].back(), (const T*)b.acts[1].back(), Ld.d_pos, c, d, n, Xout, ld, amax_out);
   } else {
     rqs_apply_kernel<T, INV><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
         Xin, (const T*)b.acts[0].back(), Ld.d_idx1, c, d, Ld.K, (T)Ld.B, n, Xout, ld, bins);
@@ -247,12 +248,15 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
   T* gC = (T*)c.ga[2];
   if (Ld.kind == NF_AFFINE_COUPLING) {
     // gA <- d/d(pre-tanh s), gB <- d/dt
-    affine_bwd_kernel<T, INV><<<(unsigned)ceil_div(n * cc, 256), 256, 0, f.stream>>>(
-        G, INV ? Xout : Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, n, gA, gB);
+    float* mS = tc ? tc_alloc_meta(f) : nullptr;
+    float* mT = tc ? tc_alloc_meta(f) : nullptr;
+    if (tc) NF_REQUIRE(mS && mT, "tcgen05 path: out of tensor metadata slots");
+    affine_bwd_kernel<T, INV><<<(unsigned)std::min<int64_t>(ceil_div(n * cc, 256), 16 * kNumSMs), 256, 0, f.stream>>>(
+        G, INV ? Xout : Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, n, gA, gB, mS, mT);
     NF_LAUNCH_CHECK();
     if (tc) {
-      NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
-      NF_TRY(tc_mlp_backward(f, Ld, 1, n, b.act0, b.acts[1], (float*)gB, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
+      NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, mS, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
+      NF_TRY(tc_mlp_backward(f, Ld, 1, n, b.act0, b.acts[1], (float*)gB, mT, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
     } else {
       // s network: temporaries gC + (gA after it has been consumed is NOT safe) -> use a dedicated pair
       NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gA, G, d, Ld.d_idx2, f.d_gsum));
@@ -262,7 +266,7 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
     rqs_bwd_kernel<T, INV><<<(unsigned)ceil_div(n * cc, 128), 128, 0, f.stream>>>(
         G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA);
     NF_LAUNCH_CHECK();
-    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
+    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, nullptr, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
     else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, G, d, Ld.d_idx2, f.d_gsum));
   }
   return NF_OK;
@@ -295,7 +299,10 @@ int sweep_forward(Flow& f, Chunk& c, const T* theta, int32_t* bins, int64_t bins
       bl = bins + bins_layer_off + bins_chunk_off * (int64_t)Ld.idx1.size();
       bins_layer_off += N_total * (int64_t)Ld.idx1.size();
     }
-    NF_TRY((coupling_apply<T, false>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, bl)));
+    const bool track = !c.xmeta.empty() && Ld.kind == NF_AFFINE_COUPLING;
+    NF_TRY((coupling_apply<T, false>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, bl, c.xmeta.empty() ? nullptr : c.xmeta[state],
+                                     track ? c.xmeta[state + 1] : nullptr)));
+    if (!c.xmeta.empty() && !track) c.xmeta[state + 1] = nullptr;   // unknown bound: the next split measures it
     ++state;
   }
   return NF_OK;
@@ -312,7 +319,10 @@ int sweep_inverse(Flow& f, Chunk& c, const T* theta) {
     LayerBufs& b = c.stash ? c.lb[li] : c.lb[0];
     const T* Xin = (const T*)c.xin(state);
     T* Xout = (T*)c.xout(state);
-    NF_TRY((coupling_apply<T, true>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, nullptr)));
+    const bool track = !c.xmeta.empty() && Ld.kind == NF_AFFINE_COUPLING;
+    NF_TRY((coupling_apply<T, true>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, nullptr, c.xmeta.empty() ? nullptr : c.xmeta[state],
+                                    track ? c.xmeta[state + 1] : nullptr)));
+    if (!c.xmeta.empty() && !track) c.xmeta[state + 1] = nullptr;
     ++state;
   }
   return NF_OK;
@@ -366,6 +376,15 @@ int run_typed(Flow& f, const GeneralJob& job) {
       NF_LAUNCH_CHECK();
     }
     const int last = stash ? L : 1 + ((L - 1) & 1);
+    if (f.mma_mode != NF_MMA_SIMT) {
+      // exact max |x0| once per chunk; every later state gets its bound from the kernel that writes it
+      c.xmeta.assign(L + 1, nullptr);
+      for (int i = 0; i <= L; ++i) {
+        c.xmeta[i] = tc_alloc_meta(f);
+        NF_REQUIRE(c.xmeta[i], "tcgen05 path: out of tensor metadata slots");
+      }
+      NF_TRY(tc_absmax(f, (const float*)c.X[0], n * d, c.xmeta[0]));
+    }
     switch (job.op) {
       case OP_ELBO: {
         NF_REQUIRE(job.tgt, "ELBO needs a target");

@@ -103,15 +103,27 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const T* __restrict__ A,
     }
 }
 
-// column sums of g [N x n] -> double atomics (bias gradients)
+// column sums of g [N x n] -> double atomics (bias gradients).  blockDim = 256 = 32 column lanes x 8 row lanes.
 template <typename T>
 __global__ void colsum_atomic_kernel(const T* __restrict__ g, int64_t N, int n, int64_t rows_per_block, double* __restrict__ out) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = r0 + rows_per_block < N ? r0 + rows_per_block : N;
-  for (int c = threadIdx.x; c < n; c += blockDim.x) {
-    T s = 0;
-    for (int64_t r = r0; r < r1; ++r) s += g[r * n + c];
-    atomicAdd(&out[c], (double)s);
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int c = c0 + cx;
+    double s = 0;
+    if (c < n)
+      for (int64_t r = r0 + ry; r < r1; r += 8) s += (double)g[r * n + c];
+    red[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && c < n) {
+      double t = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += red[q][cx];
+      atomicAdd(&out[c], t);
+    }
+    __syncthreads();
   }
 }
 
@@ -130,24 +142,67 @@ __global__ void gather_cols_kernel(const T* __restrict__ X, int d, const int* __
 //   inverse : x1 = (y1 .- t) .* exp.(-s), logjac = -sum(s)        (:99-110)
 // S holds s AFTER the tanh output activation (|s| < 1), Tt holds t.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// amax_meta[1] holds the bits of a running max |x| (non-negative floats order like unsigned ints).
+// Block-level reduction first: ONE atomic per CTA (same-address atomics serialise in L2).
+__device__ __forceinline__ void amax_update(float* amax_meta, float v) {
+  __shared__ float s_amax[32];
+  v = warp_max_f(v);
+  if ((threadIdx.x & 31) == 0) s_amax[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m = threadIdx.x < (blockDim.x >> 5) ? s_amax[threadIdx.x] : 0.f;
+    m = warp_max_f(m);
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(amax_meta + 1), __float_as_uint(m));
+  }
+  __syncthreads();
+}
+
+// One thread per element of the state (coalesced); pos[j] = position of column j in the transformed block or -1.
+// Optionally records max |Xout| (exact) for the fp16 operand scaling of the next coupling's conditioner input.
 template <typename T, bool INV>
 __global__ void affine_apply_kernel(const T* __restrict__ Xin, const T* __restrict__ S, const T* __restrict__ Tt,
-                                    const int* __restrict__ idx1, int c, int d, int64_t N, T* __restrict__ Xout,
-                                    T* __restrict__ ld) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= N) return;
-  const T* xi = Xin + r * d;
-  T* xo = Xout + r * d;
-  for (int j = 0; j < d; ++j) xo[j] = xi[j];
-  T sum = 0;
-  for (int k = 0; k < c; ++k) {
-    const T s = S[r * c + k], t = Tt[r * c + k];
-    const int j = idx1[k];
-    if (!INV) xo[j] = Num<T>::exp(s) * xi[j] + t;
-    else xo[j] = (xi[j] - t) * Num<T>::exp(-s);
-    sum += s;
+                                    const int* __restrict__ pos, int c, int d, int64_t N, T* __restrict__ Xout,
+                                    T* __restrict__ ld, float* __restrict__ amax_meta) {
+  const int64_t total = N * d;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t iters = (total + stride - 1) / stride;      // same trip count for every thread (warp collectives inside)
+  float run_max = 0.f;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t e = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < total;
+    T y = 0, contrib = 0;
+    int64_t r = 0;
+    int k = -1;
+    if (valid) {
+      r = e / d;
+      const int j = (int)(e - r * d);
+      const T x = Xin[e];
+      k = pos[j];
+      if (k >= 0) {
+        const T s = S[r * c + k], t = Tt[r * c + k];
+        y = INV ? (x - t) * Num<T>::exp(-s) : Num<T>::exp(s) * x + t;
+        contrib = INV ? -s : s;
+      } else {
+        y = x;
+      }
+      Xout[e] = y;
+      run_max = fmaxf(run_max, fabsf((float)y));
+    }
+    if (ld) {
+      if ((d & 31) == 0) {            // a warp covers 32 consecutive columns of ONE row
+        const T sum = warp_sum(contrib);
+        if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&ld[r], sum);
+      } else if (valid && k >= 0) {
+        atomicAdd(&ld[r], contrib);
+      }
+    }
   }
-  if (ld) ld[r] += INV ? -sum : sum;
+  if (amax_meta) amax_update(amax_meta, run_max);
 }
 
 // Backward of the coupling arithmetic.  In: G = d/dXout (in place -> d/dXin on idx1 columns; the idx2
@@ -157,27 +212,36 @@ __global__ void affine_apply_kernel(const T* __restrict__ Xin, const T* __restri
 template <typename T, bool INV>
 __global__ void affine_bwd_kernel(T* __restrict__ G, const T* __restrict__ X1src, const T* __restrict__ S,
                                   const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int64_t N,
-                                  T* __restrict__ gS, T* __restrict__ gT) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= N * c) return;
-  const int64_t r = e / c;
-  const int k = (int)(e - r * c);
-  const int j = idx1[k];
-  const T s = S[e];
-  const T go = G[r * d + j];
-  const T x1 = X1src[r * d + j];
-  const T gl = gld ? gld[r] : T(1);
-  T gs, gt, gi;
-  if (!INV) {
-    const T es = Num<T>::exp(s);
-    gi = go * es; gs = go * x1 * es + gl; gt = go;
-  } else {
-    const T ems = Num<T>::exp(-s);
-    gi = go * ems; gt = -gi; gs = -go * x1 - gl;
+                                  T* __restrict__ gS, T* __restrict__ gT, float* __restrict__ amaxS, float* __restrict__ amaxT) {
+  const int64_t total = N * c;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float maxS = 0.f, maxT = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    T gs_out = 0, gt = 0;
+    const int64_t r = e / c;
+    const int k = (int)(e - r * c);
+    const int j = idx1[k];
+    const T s = S[e];
+    const T go = G[r * d + j];
+    const T x1 = X1src[r * d + j];
+    const T gl = gld ? gld[r] : T(1);
+    T gs, gi;
+    if (!INV) {
+      const T es = Num<T>::exp(s);
+      gi = go * es; gs = go * x1 * es + gl; gt = go;
+    } else {
+      const T ems = Num<T>::exp(-s);
+      gi = go * ems; gt = -gi; gs = -go * x1 - gl;
+    }
+    G[r * d + j] = gi;
+    gs_out = gs * (1 - s * s);   // through tanh
+    gS[e] = gs_out;
+    gT[e] = gt;
+    maxS = fmaxf(maxS, fabsf((float)gs_out));
+    maxT = fmaxf(maxT, fabsf((float)gt));
   }
-  G[r * d + j] = gi;
-  gS[e] = gs * (1 - s * s);   // through tanh
-  gT[e] = gt;
+  if (amaxS) amax_update(amaxS, maxS);
+  if (amaxT) amax_update(amaxT, maxT);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -138,6 +138,12 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
         NF_CUDA(cudaMalloc((void**)&L.d_idx2, cbar * sizeof(int)));
         NF_CUDA(cudaMemcpy(L.d_idx1, L.idx1.data(), c * sizeof(int), cudaMemcpyHostToDevice));
         NF_CUDA(cudaMemcpy(L.d_idx2, L.idx2.data(), cbar * sizeof(int), cudaMemcpyHostToDevice));
+        {
+          std::vector<int> pos(dim, -1);
+          for (int k = 0; k < c; ++k) pos[L.idx1[k]] = k;
+          NF_CUDA(cudaMalloc((void**)&L.d_pos, dim * sizeof(int)));
+          NF_CUDA(cudaMemcpy(L.d_pos, pos.data(), dim * sizeof(int), cudaMemcpyHostToDevice));
+        }
         break;
       }
       default:
@@ -185,7 +191,7 @@ static void flow_destroy(Flow* f) {
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
   general_release(*f);
-  for (auto& L : f->layers) { cudaFree(L.d_idx1); cudaFree(L.d_idx2); }
+  for (auto& L : f->layers) { cudaFree(L.d_idx1); cudaFree(L.d_idx2); cudaFree(L.d_pos); }
   cudaFree(f->d_base); cudaFree(f->d_ew_meta); cudaFree(f->d_ew_kinds);
   cudaFree(f->d_theta); cudaFree(f->d_gsum); cudaFree(f->d_out); cudaFreeHost(f->h_pinned);
   cudaFree(f->ws.base);

@@ -21,6 +21,7 @@
 #include "kernels_coupling.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstring>
 #include <map>
 #include <tuple>
 
@@ -74,6 +75,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -177,12 +186,19 @@ struct GemmParams {
   int64_t out_ld;
   float* out_f32;          // [M, out_f32_ld]
   int64_t out_f32_ld;
-  const __half* mask_hi;   // EPI_PLANES_MASK: sign of the stashed activation
-  int64_t mask_ld;
+  const uint32_t* mask_bits;   // EPI_PLANES_MASK: packed (activation > 0) bits of the stashed activation, [M_pad, mask_ld]
+  int64_t mask_ld;             // words per row
+  uint32_t* out_bits;          // EPI_PLANES_ACT: packed sign bits written next to the planes
+  int64_t out_bits_ld;
   float* G;                // EPI_SCATTER_ADD
   int ldg;
   const int* idx;
+  double* colsum_out;      // EPI_PLANES_MASK: column sums of the written values (= bias gradient of the layer below)
+  int colsum_n;
+  long long* dbg;          // optional timeline of CTA 0 (clock64): [role 0..2][event idx]
+  int dbg_flags;           // experiments: 1 skip plane stores, 2 skip sign-bit stores, 4 skip split/activation math
 };
+#define NF_DBG(role, idx, cond) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (cond) && (idx) < 512) p.dbg[(role) * 512 + (idx)] = clock64(); } while (0)
 
 template <int BN> struct GemmCfg {
   static constexpr int A_PLANE = 128 * 128;                  // 128 rows x 128 B
@@ -190,11 +206,16 @@ template <int BN> struct GemmCfg {
   static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
   static constexpr int STAGES = (STAGE * 4 <= 200 * 1024) ? 4 : ((STAGE * 3 <= 200 * 1024) ? 3 : 2);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
-  // epilogue: 4 warps (one per TMEM lane quarter) per column half; wide tiles use two halves
-  static constexpr int HALVES = BN >= 128 ? 2 : 1;
-  static constexpr int CPT = BN / HALVES;                    // accumulator columns held per epilogue thread
-  static constexpr int THREADS = 64 + 128 * 2;
+  // epilogue: 4 warps (one per TMEM lane quarter) per column group; wide tiles use four groups = 16 warps so that
+  // the per-element epilogue math has 4 warps per scheduler to hide its latencies
+  static constexpr int GROUPS = BN >= 128 ? 4 : BN / 32;
+  static constexpr int CPT = BN / GROUPS;                    // accumulator columns held per epilogue thread (32 or 64)
+  static constexpr int THREADS = 64 + 128 * GROUPS;
+  // per-warp epilogue staging tile: 32 rows x 64 B, XOR-swizzled 16-byte chunks (the SWIZZLE_64B pattern): fp16 plane
+  // chunks leave by TMA store, fp32 outputs use the same bytes as 32 rows x 16 floats
+  static constexpr int STG_WARP = 2048;
+  static constexpr int STG_OFF = ((256 + 2 * BN * 4 + 511) / 512) * 512;   // after barriers, bias, column sums; 512 B aligned
+  static constexpr int SMEM = STAGES * STAGE + STG_OFF + 4 * GROUPS * STG_WARP;   // base must be 1024 B aligned (checked)
 };
 
 // The tensor core rounds its fp32 accumulator toward zero after every MMA, so a long accumulation chain
@@ -204,13 +225,15 @@ template <int BN> struct GemmCfg {
 // round-to-nearest adds, the same split Ootomo & Yokota use for fp32 emulation on tensor cores.
 template <int BN>
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, GemmParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+               const __grid_constant__ CUtensorMap tmapO, GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int S = Cfg::STAGES;
   constexpr int CPT = Cfg::CPT;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();                               // SWIZZLE_128B tiles need a 1024 B aligned window
+  uint8_t* gen_base = smem_raw;
   const uint32_t bars = base + S * Cfg::STAGE;              // full[S], empty[S], tfull[2], tempty[2], tmem ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
@@ -219,6 +242,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + S * Cfg::STAGE + 8 * (2 * S + 4));
   float* s_bias = reinterpret_cast<float*>(gen_base + S * Cfg::STAGE + 256);
+  float* s_colsum = s_bias + BN;
+  uint8_t* s_stage = gen_base + S * Cfg::STAGE + Cfg::STG_OFF;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t num_tiles = (p.M + 127) / 128;
@@ -229,12 +254,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * Cfg::HALVES); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * Cfg::GROUPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  if (threadIdx.x >= 64 && p.bias) {
-    for (int i = threadIdx.x - 64; i < BN; i += Cfg::THREADS - 64) s_bias[i] = p.bias[n0 + i];
+  if (threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < BN; i += Cfg::THREADS - 64) {
+      s_bias[i] = p.bias ? p.bias[n0 + i] : 0.f;
+      s_colsum[i] = 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -252,6 +280,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
+          NF_DBG(0, 2 * it, true);
           mbar_expect_tx(full_bar(s), bytes);
           const uint32_t st = base + s * Cfg::STAGE;
           tma_load_3d(st, &tmapA, full_bar(s), kc * 64, m0, 0);
@@ -274,31 +303,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           const uint32_t ph = (it / S) & 1;
           const uint32_t acc = it & 1, accph = (it >> 1) & 1;
           mbar_wait(tempty_bar(acc), accph ^ 1);
+          NF_DBG(1, 3 * it, true);
           mbar_wait(full_bar(s), ph);
+          NF_DBG(1, 3 * it + 1, true);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
           const uint32_t st = base + s * Cfg::STAGE;
-          uint32_t first = 0;
+          // one descriptor per operand per stage; every MMA below only adds a compile-time constant to its
+          // 14-bit start-address field (a single thread issues these, so dependent address math is the cost)
+          const uint64_t adesc0 = make_smem_desc(st, 16, 1024);
+          const uint64_t bdesc0 = make_smem_desc(st + 2 * Cfg::A_PLANE, 16, 1024);
           // correction products (hi*lo, lo*hi) first, main products (hi*hi) last
-          for (int t = p.terms - 1; t >= 0; --t) {
+          if (p.terms > 1) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t a_addr = st + (t == 2 ? Cfg::A_PLANE : 0) + kk * 32;
-              const uint32_t b_addr = st + 2 * Cfg::A_PLANE + (t == 1 ? Cfg::B_PLANE : 0) + kk * 32;
-              umma_f16(d_tmem, make_smem_desc(a_addr, 16, 1024), make_smem_desc(b_addr, 16, 1024), idesc, first);
-              first = 1;
-            }
+            for (int kk = 0; kk < 4; ++kk)   // lo * hi
+              umma_f16(d_tmem, adesc0 + ((Cfg::A_PLANE + kk * 32) >> 4), bdesc0 + ((kk * 32) >> 4), idesc, kk > 0 ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)   // hi * lo
+              umma_f16(d_tmem, adesc0 + ((kk * 32) >> 4), bdesc0 + ((Cfg::B_PLANE + kk * 32) >> 4), idesc, 1u);
           }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)     // hi * hi
+            umma_f16(d_tmem, adesc0 + ((kk * 32) >> 4), bdesc0 + ((kk * 32) >> 4), idesc, (p.terms > 1 || kk > 0) ? 1u : 0u);
           umma_commit(empty_bar(s));
           umma_commit(tfull_bar(acc));
+          NF_DBG(1, 3 * it + 2, true);
         }
       }
     }
-  } else if (warp < 2 + 4 * Cfg::HALVES) {
-    // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+  } else {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4 =====
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int cbase = half * CPT;            // first accumulator column of this thread within the tile
+    const int group = (warp - 2) >> 2;
+    const int cbase = group * CPT;           // first accumulator column of this thread within the tile
     const float s_a = p.a_meta[0];
     const float amax_a = __uint_as_float(reinterpret_cast<const unsigned int*>(p.a_meta)[1]);
     const float descale0 = 1.f / (s_a * p.w_sc[0]);
@@ -309,6 +346,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       s_out = pow2_scale(bound * 1.001f);
       if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) p.out_meta[0] = s_out;
     }
+    const float ds_out = descale * s_out;    // accumulator -> stored (scaled) value in one FFMA
     float run_max = 0.f;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -321,6 +359,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       for (int kc = 0; kc < nk; ++kc, ++it) {
         const uint32_t acc = it & 1, accph = (it >> 1) & 1;
         mbar_wait(tfull_bar(acc), accph);
+        NF_DBG(2, 3 * it, threadIdx.x == 64);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cbase;
 #pragma unroll
@@ -335,79 +374,150 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
+        NF_DBG(2, 3 * it + 1, threadIdx.x == 64);
       }
-      if (!row_ok) continue;
 #pragma unroll
       for (int c = 0; c < CPT / 32; ++c) {
         const int col0 = n0 + cbase + c * 32;
-        if (col0 >= p.n_store) break;
+        if (col0 >= p.n_store) break;   // warp-uniform
         const float* v = racc + c * 32;
         const int bo = cbase + c * 32;     // offset into s_bias
         if (p.epi == EPI_PLANES_ACT || p.epi == EPI_PLANES_MASK) {
           uint32_t hi[16], lo[16];
           if (p.epi == EPI_PLANES_ACT) {
+            uint32_t bits = 0;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              float a = v[j] * descale + s_bias[bo + j];
-              float b = v[j + 1] * descale + s_bias[bo + j + 1];
-              if (p.act == ACT_LRELU) { a = a > 0.f ? a : 0.01f * a; b = b > 0.f ? b : 0.01f * b; }
+              // scaled pre-activation (positive power-of-two scale commutes with leakyrelu and with the sign test)
+              float a = fmaf(v[j], ds_out, s_bias[bo + j] * s_out);
+              float b = fmaf(v[j + 1], ds_out, s_bias[bo + j + 1] * s_out);
+              bits |= (a > 0.f ? 1u : 0u) << j;
+              bits |= (b > 0.f ? 1u : 0u) << (j + 1);
+              if (p.act == ACT_LRELU) { a = fmaxf(a, 0.01f * a); b = fmaxf(b, 0.01f * b); }
               run_max = fmaxf(run_max, fmaxf(fabsf(a), fabsf(b)));
-              split_pair(a * s_out, b * s_out, hi[j >> 1], lo[j >> 1]);
+              split_pair(a, b, hi[j >> 1], lo[j >> 1]);
             }
+            if (row_ok && p.out_bits && !(p.dbg_flags & 2)) p.out_bits[row * p.out_bits_ld + (col0 >> 5)] = bits;
           } else {
-            const uint4* mrow = reinterpret_cast<const uint4*>(p.mask_hi + row * p.mask_ld + col0);
-            uint32_t mk[16];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { const uint4 t4 = mrow[q]; mk[4 * q] = t4.x; mk[4 * q + 1] = t4.y; mk[4 * q + 2] = t4.z; mk[4 * q + 3] = t4.w; }
+            const uint32_t mbits = row_ok ? p.mask_bits[row * p.mask_ld + (col0 >> 5)] : 0u;
+            float cs[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const uint32_t m2 = mk[j >> 1];
-              // fp16 sign bits: low half bit 15, high half bit 31; activation > 0  <=> not negative and not zero
-              const bool pa = ((m2 & 0x8000u) == 0) && ((m2 & 0x7FFFu) != 0);
-              const bool pb = ((m2 & 0x80000000u) == 0) && ((m2 & 0x7FFF0000u) != 0);
-              const float a = v[j] * descale * (pa ? 1.f : 0.01f);
-              const float b = v[j + 1] * descale * (pb ? 1.f : 0.01f);
+              const bool pa = (mbits >> j) & 1u;          // leakyrelu'(h): 1 where the stashed activation was > 0, else 0.01
+              const bool pb = (mbits >> (j + 1)) & 1u;
+              const float a = row_ok ? v[j] * (pa ? ds_out : 0.01f * ds_out) : 0.f;      // scaled values
+              const float b = row_ok ? v[j + 1] * (pb ? ds_out : 0.01f * ds_out) : 0.f;
               run_max = fmaxf(run_max, fmaxf(fabsf(a), fabsf(b)));
-              split_pair(a * s_out, b * s_out, hi[j >> 1], lo[j >> 1]);
+              split_pair(a, b, hi[j >> 1], lo[j >> 1]);
+              cs[j] = a; cs[j + 1] = b;
+            }
+            if (p.colsum_out) {
+              // column sums over the 32 rows of this warp: recursive halving, 31 shuffles; lane l ends with column l
+#pragma unroll
+              for (int sft = 16; sft > 0; sft >>= 1) {
+                const bool up = (lane & sft) != 0;
+#pragma unroll
+                for (int i = 0; i < sft; ++i) {
+                  const float send = up ? cs[i] : cs[i + sft];
+                  const float keep = up ? cs[i + sft] : cs[i];
+                  cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                }
+              }
+              atomicAdd(&s_colsum[cbase + c * 32 + lane], cs[0] / s_out);
             }
           }
-          uint4* oh = reinterpret_cast<uint4*>(p.out_hi + row * p.out_ld + col0);
+          {
+            // fp16 chunk (32 rows x 64 B) -> per-warp smem tile in the SWIZZLE_64B pattern -> one TMA store per plane;
+            // rows past the end of the batch are clipped by the tensor map
+            uint8_t* stg = s_stage + (warp - 2) * Cfg::STG_WARP;
+            const uint32_t stg_u32 = smem_u32(stg);
+            const int row_base = (int)(tile * 128) + quarter * 32;
+            const int sw = (lane >> 1) & 3;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) oh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-          if (p.terms > 1) {
-            uint4* ol = reinterpret_cast<uint4*>(p.out_lo + row * p.out_ld + col0);
+            for (int pl = 0; pl < 2; ++pl) {
+              if (pl == 1 && p.terms == 1) break;
+              const uint32_t* src = pl == 0 ? hi : lo;
+              if (lane == 0) tma_store_wait_read();      // the previous store has finished reading the tile
+              __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ol[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-          }
-        } else if (p.epi == EPI_F32_ACT) {
-          float* o = p.out_f32 + row * p.out_f32_ld + col0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.n_store) {
-              float a = v[j] * descale + s_bias[bo + j];
-              if (p.act == ACT_TANH) a = tanhf(a);
-              else if (p.act == ACT_LRELU) a = a > 0.f ? a : 0.01f * a;
-              o[j] = a;
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw) << 4)) = make_uint4(src[4 * q], src[4 * q + 1], src[4 * q + 2], src[4 * q + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && !(p.dbg_flags & 1)) tma_store_3d(&tmapO, stg_u32, col0, row_base, pl);
             }
           }
-        } else {  // EPI_SCATTER_ADD
-          float* g = p.G + row * p.ldg;
+        } else {
+          // fp32 outputs: two 16-column halves through the staging tile (64 B pitch, XOR-swizzled 16 B chunks),
+          // then 4 lanes cover 64 contiguous bytes of one row
+          uint8_t* stg = s_stage + (warp - 2) * Cfg::STG_WARP;
+          const int64_t row_base = tile * 128 + quarter * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.n_store) g[p.idx[col0 + j]] += v[j] * descale;
+          for (int hf = 0; hf < 2; ++hf) {
+            const int cc0 = col0 + hf * 16;
+            if (cc0 >= p.n_store) break;     // warp-uniform
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float o4[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = hf * 16 + q * 4 + u;
+                float a = v[j] * descale;
+                if (p.epi == EPI_F32_ACT) {
+                  a += s_bias[bo + j];
+                  if (p.act == ACT_TANH) a = tanhf(a);
+                  else if (p.act == ACT_LRELU) a = a > 0.f ? a : 0.01f * a;
+                }
+                o4[u] = a;
+              }
+              *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const int rr = ps * 8 + (lane >> 2);
+              const int cq = cc0 + (lane & 3) * 4;
+              const float4 val = *reinterpret_cast<const float4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+              const int64_t grow = row_base + rr;
+              if (grow < p.M) {
+                const float vv[4] = {val.x, val.y, val.z, val.w};
+                if (p.epi == EPI_F32_ACT) {
+                  float* o = p.out_f32 + grow * p.out_f32_ld + cq;
+                  if (cq + 3 < p.n_store && (p.out_f32_ld & 3) == 0) *reinterpret_cast<float4*>(o) = val;
+                  else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (cq + u < p.n_store) o[u] = vv[u];
+                  }
+                } else {  // EPI_SCATTER_ADD: G[row, idx[col]] += v
+                  float* g = p.G + grow * p.ldg;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) if (cq + u < p.n_store) g[p.idx[cq + u]] += vv[u];
+                }
+              }
+            }
+            __syncwarp();
+          }
         }
       }
+      NF_DBG(2, 3 * (it - 1) + 2, threadIdx.x == 64);
     }
     if (p.out_meta) {
-      run_max = warp_max(run_max);
+      run_max = warp_max(run_max) / s_out;     // tracked on the scaled values
       if (lane == 0) meta_amax(p.out_meta, run_max);
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+  if (p.colsum_out && threadIdx.x >= 64) {
+    for (int i = threadIdx.x - 64; i < BN; i += Cfg::THREADS - 64)
+      if (n0 + i < p.colsum_n) atomicAdd(&p.colsum_out[n0 + i], (double)s_colsum[i]);
   }
 }
 
@@ -564,20 +674,29 @@ __global__ void absmax_kernel(const float* __restrict__ X, int d, const int* __r
   if ((threadIdx.x & 31) == 0) meta_amax(meta, m);
 }
 
-// planes [rows_pad, ld]: hi plane then lo plane (+plane_elems); scale from the exact amax
+// planes [rows_pad, ld]: hi plane then lo plane (+plane_elems); one thread per pair of adjacent columns.
+// amax_src[1] bounds max |X|; meta receives the scale and the same bound for downstream layers.
+template <typename I>
 __global__ void gather_split_kernel(const float* __restrict__ X, int d, const int* __restrict__ idx, int n_idx, int64_t n,
-                                    __half* __restrict__ out, int ld, int64_t plane_elems, float* __restrict__ meta) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const float s = pow2_scale(__uint_as_float(reinterpret_cast<const unsigned int*>(meta)[1]));
-  if (e == 0) meta[0] = s;
-  if (e >= n * ld) return;
-  const int64_t r = e / ld;
-  const int k = (int)(e - r * ld);
-  float v = 0.f;
-  if (k < n_idx) v = (idx ? X[r * d + idx[k]] : X[r * d + k]) * s;
-  const __half h = __float2half_rn(v);
-  out[e] = h;
-  out[plane_elems + e] = __float2half_rn(v - __half2float(h));
+                                    __half* __restrict__ out, int ld, int64_t plane_elems, const float* __restrict__ amax_src,
+                                    float* __restrict__ meta) {
+  const I e = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x;
+  const unsigned int abits = reinterpret_cast<const unsigned int*>(amax_src)[1];
+  const float s = pow2_scale(__uint_as_float(abits));
+  if (e == 0) { meta[0] = s; reinterpret_cast<unsigned int*>(meta)[1] = abits; }
+  const I half_ld = (I)(ld >> 1);
+  if (e >= (I)n * half_ld) return;
+  const I r = e / half_ld;
+  const int k = (int)(e - r * half_ld) * 2;
+  float v0 = 0.f, v1 = 0.f;
+  const float* xr = X + (int64_t)r * d;
+  if (k < n_idx) v0 = (idx ? xr[idx[k]] : xr[k]) * s;
+  if (k + 1 < n_idx) v1 = (idx ? xr[idx[k + 1]] : xr[k + 1]) * s;
+  uint32_t hi, lo;
+  split_pair(v0, v1, hi, lo);
+  const int64_t o = (int64_t)r * ld + k;
+  *reinterpret_cast<uint32_t*>(out + o) = hi;
+  *reinterpret_cast<uint32_t*>(out + plane_elems + o) = lo;
 }
 
 __global__ void plane_colsum_kernel(const __half* __restrict__ P, int ld, int64_t plane_elems, int64_t n, int ncols,
@@ -786,6 +905,26 @@ int make_map_kmajor(TcState* st, const void* basep, int64_t rows, int64_t cols, 
   return NF_OK;
 }
 
+// Store view of split planes: dims {cols, rows, 2}, box {32, 32, 1}, SWIZZLE_64B (matches the epilogue staging tile)
+int make_map_store(TcState* st, const void* basep, int64_t rows, int64_t cols, int64_t plane_elems, CUtensorMap* out) {
+  auto key = std::make_tuple(basep, rows, cols, plane_elems, 32, 2);
+  auto itf = st->maps.find(key);
+  if (itf != st->maps.end()) { *out = itf->second; return NF_OK; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return NF_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  cuuint64_t gstr[2] = {(cuuint64_t)cols * 2, (cuuint64_t)plane_elems * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(basep), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (store) failed: %d (rows %lld cols %lld)", (int)r, (long long)rows, (long long)cols); return NF_ERR_CUDA; }
+  if (st->maps.size() > 4096) st->maps.clear();
+  st->maps[key] = *out;
+  return NF_OK;
+}
+
 // MN-major view for wgrad: dims {64, rows, cols/64, 2}, box {64, 32, nblocks, 1} -> smem [block][row][64]
 int make_map_mnmajor(TcState* st, const void* basep, int64_t rows, int64_t cols, int64_t plane_elems, int nblocks, CUtensorMap* out) {
   auto key = std::make_tuple(basep, rows, cols, plane_elems, nblocks, 1);
@@ -807,7 +946,7 @@ int make_map_mnmajor(TcState* st, const void* basep, int64_t rows, int64_t cols,
 }
 
 template <int BN>
-int launch_gemm_bn(Flow& f, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int n_tiles_n) {
+int launch_gemm_bn(Flow& f, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmParams& p, int n_tiles_n) {
   using Cfg = GemmCfg<BN>;
   auto kern = tc_gemm_kernel<BN>;
   static bool attr_set = false;
@@ -817,23 +956,54 @@ int launch_gemm_bn(Flow& f, const CUtensorMap& ma, const CUtensorMap& mb, const 
   }
   const int64_t tiles = ceil_div(p.M, 128);
   dim3 grid((unsigned)std::min<int64_t>(tiles, std::max(1, kNumSMs / n_tiles_n)), (unsigned)n_tiles_n);
+  char key[64];
+  snprintf(key, sizeof(key), "tc_gemm_n%d_k%d_e%d", BN, p.num_k_chunks * 64, p.epi);
+  // NFCUDA_DBG=<class>: dump the clock64 timeline of CTA 0 for the n-th (NFCUDA_DBG_SKIP) launch of that class
+  static int dbg_seen = 0;
+  const char* dbg_cls = getenv("NFCUDA_DBG");
+  long long* d_dbg = nullptr;
+  GemmParams pp = p;
+  pp.dbg_flags = getenv("NFCUDA_DBG_FLAGS") ? atoi(getenv("NFCUDA_DBG_FLAGS")) : 0;
+  if (dbg_cls && !strcmp(dbg_cls, key)) {
+    const int skip = getenv("NFCUDA_DBG_SKIP") ? atoi(getenv("NFCUDA_DBG_SKIP")) : 0;
+    if (dbg_seen++ == skip) {
+      NF_CUDA(cudaMalloc((void**)&d_dbg, 3 * 512 * sizeof(long long)));
+      NF_CUDA(cudaMemset(d_dbg, 0, 3 * 512 * sizeof(long long)));
+      pp.dbg = d_dbg;
+    }
+  }
   if (f.prof.on) {
-    char key[64];
-    snprintf(key, sizeof(key), "tc_gemm_n%d_k%d", BN, p.num_k_chunks * 64);
+    key[strlen(key) - 3] = 0;      // profile classes ignore the epilogue kind
     f.prof.begin(key, f.stream);
   }
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM, f.stream>>>(ma, mb, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, f.stream>>>(ma, mb, mo, pp);
   f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
+  if (d_dbg) {
+    std::vector<long long> h(3 * 512);
+    NF_CUDA(cudaStreamSynchronize(f.stream));
+    NF_CUDA(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_dbg);
+    long long t0 = 0;
+    for (auto v : h) if (v && (!t0 || v < t0)) t0 = v;
+    fprintf(stderr, "[nfcuda dbg] %s grid %u tiles %lld nk %d : clock64 relative to first event (CTA 0)\n", dbg_cls, grid.x, (long long)tiles, p.num_k_chunks);
+    const char* names[3] = {"producer (2*it: slot free, issue)", "mma (3*it: tmem free, smem full, issued)", "epilogue w2 (3*it: tmem full, drained, [tile finalised])"};
+    for (int r = 0; r < 3; ++r) {
+      fprintf(stderr, "  %s\n   ", names[r]);
+      for (int i = 0; i < 96; ++i) fprintf(stderr, " %lld", h[r * 512 + i] ? h[r * 512 + i] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return NF_OK;
 }
 
-int launch_gemm(Flow& f, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int n_tiles_n) {
+// mo: store map of the output planes (EPI_PLANES_*); any valid map otherwise (unused)
+int launch_gemm(Flow& f, int bn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmParams& p, int n_tiles_n) {
   switch (bn) {
-    case 32: return launch_gemm_bn<32>(f, ma, mb, p, n_tiles_n);
-    case 64: return launch_gemm_bn<64>(f, ma, mb, p, n_tiles_n);
-    case 128: return launch_gemm_bn<128>(f, ma, mb, p, n_tiles_n);
-    default: return launch_gemm_bn<256>(f, ma, mb, p, n_tiles_n);
+    case 32: return launch_gemm_bn<32>(f, ma, mb, mo, p, n_tiles_n);
+    case 64: return launch_gemm_bn<64>(f, ma, mb, mo, p, n_tiles_n);
+    case 128: return launch_gemm_bn<128>(f, ma, mb, mo, p, n_tiles_n);
+    default: return launch_gemm_bn<256>(f, ma, mb, mo, p, n_tiles_n);
   }
 }
 
@@ -865,25 +1035,39 @@ struct Planes {
   int64_t rows_pad;
   int ld;
   int64_t plane_elems() const { return rows_pad * ld; }
+  uint32_t* bits() const { return reinterpret_cast<uint32_t*>(p + 2 * plane_elems()); }   // [rows_pad, ld/32] sign bits
+  int bits_ld() const { return ld / 32; }
 };
 inline Planes planes_of(void* buf, int64_t n, int width) { return Planes{(__half*)buf, round_up(n, 128), pad64(width)}; }
 
-// fp32 [n, ld_src] (optionally gathered columns) -> split planes with an exact-amax scale
-int split_into_planes(Flow& f, TcState* st, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* buf) {
+// fp32 [n, ld_src] (optionally gathered columns) -> split planes.  The scale comes from `amax_src` (a bound on
+// max |X| recorded by the producer of X) when given, else from an exact absmax pass.
+int split_into_planes(Flow& f, TcState* st, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* buf,
+                      const float* amax_src) {
   Planes P = planes_of(buf, n, n_idx);
   float* meta = new_meta(st, buf);
   NF_REQUIRE(meta, "tcgen05 path: out of tensor metadata slots");
-  const int64_t total = n * n_idx;
-  absmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256 * 8), 4 * kNumSMs), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, meta);
-  NF_LAUNCH_CHECK();
-  gather_split_kernel<<<(unsigned)ceil_div(n * P.ld, 256), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, P.p, P.ld, P.plane_elems(), meta);
+  if (!amax_src) {
+    const int64_t total = n * n_idx;
+    absmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256 * 8), 4 * kNumSMs), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, meta);
+    NF_LAUNCH_CHECK();
+    amax_src = meta;
+  }
+  const int64_t pairs = n * (P.ld / 2);
+  if (pairs < (int64_t)1 << 31)
+    gather_split_kernel<int><<<(unsigned)ceil_div(pairs, 256), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, P.p, P.ld, P.plane_elems(), amax_src, meta);
+  else
+    gather_split_kernel<int64_t><<<(unsigned)ceil_div(pairs, 256), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, P.p, P.ld, P.plane_elems(), amax_src, meta);
   NF_LAUNCH_CHECK();
   return NF_OK;
 }
 
 }  // namespace
 
-size_t tc_act_bytes(int64_t n, int width) { return (size_t)round_up(n, 128) * pad64(width) * 4; }
+size_t tc_act_bytes(int64_t n, int width) {
+  const size_t rows = (size_t)round_up(n, 128), ld = (size_t)pad64(width);
+  return rows * ld * 4 /* hi + lo planes */ + rows * (ld / 32) * 4 /* packed sign bits */;
+}
 size_t tc_weight_bytes(const Flow&) { return 0; }
 
 void tc_release(Flow& f) {
@@ -916,8 +1100,20 @@ int tc_prepare_weights(Flow& f, const float* theta_dev) {
   return NF_OK;
 }
 
-int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* act0) {
-  return split_into_planes(f, get_state(f), X, d, d_idx, n_idx, n, act0);
+int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* act0, const float* amax_src) {
+  return split_into_planes(f, get_state(f), X, d, d_idx, n_idx, n, act0, amax_src);
+}
+
+float* tc_alloc_meta(Flow& f) {
+  TcState* st = get_state(f);
+  if (!st || st->next_slot >= kMetaSlots) return nullptr;
+  return st->meta_pool + 2 * (st->next_slot++);
+}
+
+int tc_absmax(Flow& f, const float* X, int64_t count, float* meta) {
+  absmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div(count, 256 * 8), 4 * kNumSMs), 256, 0, f.stream>>>(X, 1, nullptr, 1, count, meta);
+  NF_LAUNCH_CHECK();
+  return NF_OK;
 }
 
 int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts) {
@@ -945,23 +1141,26 @@ int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, s
     p.bound_dgrad = 0;
     p.rz_comp = rz_compensation(dp.kin, p.num_k_chunks);
     p.bias = st->bias_pool + dp.bias_off;
+    CUtensorMap mo = ma;
     if (!last) {
       Planes O = planes_of(acts[i], n, dp.nout);
+      NF_TRY(make_map_store(st, O.p, n, O.ld, O.plane_elems(), &mo));
       p.out_meta = new_meta(st, acts[i]);
       NF_REQUIRE(p.out_meta, "tcgen05 path: out of tensor metadata slots");
       p.epi = EPI_PLANES_ACT; p.act = ACT_LRELU; p.n_store = O.ld;
       p.out_hi = O.p; p.out_lo = O.p + O.plane_elems(); p.out_ld = O.ld;
+      p.out_bits = O.bits(); p.out_bits_ld = O.bits_ld();
     } else {
       p.epi = EPI_F32_ACT; p.act = md.out_act ? ACT_TANH : ACT_NONE; p.n_store = dp.nout;
       p.out_f32 = (float*)acts[i]; p.out_f32_ld = dp.nout;
     }
-    NF_TRY(launch_gemm(f, bn, ma, mb, p, n_tiles_n));
+    NF_TRY(launch_gemm(f, bn, ma, mb, mo, p, n_tiles_n));
   }
   return NF_OK;
 }
 
 int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts, float* g_last,
-                    void* scratch0, void* scratch1, float* G, double* gsum) {
+                    const float* g_last_amax, void* scratch0, void* scratch1, float* G, double* gsum) {
   TcState* st = get_state(f);
   const int li = (int)(&Ld - f.layers.data());
   const MLPDesc& md = Ld.mlps[m];
@@ -970,7 +1169,12 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
   void* gbuf = scratch0;
   void* gnext = scratch1;
   // gradient w.r.t. the last pre-activation -> split planes
-  NF_TRY(split_into_planes(f, st, g_last, md.dims[nd], nullptr, md.dims[nd], n, gbuf));
+  NF_TRY(split_into_planes(f, st, g_last, md.dims[nd], nullptr, md.dims[nd], n, gbuf, g_last_amax));
+  {  // bias gradient of the last Dense straight from the fp32 gradient
+    const int64_t rpb = 4096;
+    colsum_atomic_kernel<float><<<(unsigned)ceil_div(n, rpb), 256, 0, f.stream>>>(g_last, n, md.dims[nd], rpb, gsum + md.b_off[nd - 1]);
+    NF_LAUNCH_CHECK();
+  }
   for (int i = nd - 1; i >= 0; --i) {
     const int pi = st->index[li][m][i];
     const DensePrep& dp = st->preps[pi];
@@ -980,12 +1184,6 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
     const float* g_meta = meta_of(st, gbuf);
     const float* x_meta = meta_of(st, xbuf);
     NF_REQUIRE(g_meta && x_meta, "tcgen05 path: missing tensor metadata (backward)");
-    {  // bias gradient
-      const int64_t rpb = 1024;
-      plane_colsum_kernel<<<(unsigned)ceil_div(n, rpb), 256, 0, f.stream>>>(Gp.p, Gp.ld, Gp.plane_elems(), n, dp.nout, rpb,
-                                                                          terms > 1 ? 1 : 0, g_meta, gsum + dp.b_off);
-      NF_LAUNCH_CHECK();
-    }
     {  // weight gradient
       NF_REQUIRE(X.ld <= 256 && Gp.ld <= 256, "tcgen05 wgrad supports layer widths up to 256 (got %d x %d)", dp.kin, dp.nout);
       CUtensorMap mx, mg;
@@ -1012,17 +1210,21 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
       p.M = n; p.num_k_chunks = dp.nout_p / 64; p.terms = terms;
       p.a_meta = g_meta; p.w_sc = st->d_scalars + 4 * pi; p.bound_dgrad = 1;
       p.rz_comp = rz_compensation(dp.nout, p.num_k_chunks);
+      CUtensorMap mo = ma;
       if (i > 0) {
         Planes O = planes_of(gnext, n, dp.kin);
+        NF_TRY(make_map_store(st, O.p, n, O.ld, O.plane_elems(), &mo));
         p.out_meta = new_meta(st, gnext);
         NF_REQUIRE(p.out_meta, "tcgen05 path: out of tensor metadata slots");
         p.epi = EPI_PLANES_MASK; p.n_store = O.ld;
         p.out_hi = O.p; p.out_lo = O.p + O.plane_elems(); p.out_ld = O.ld;
-        p.mask_hi = X.p; p.mask_ld = X.ld;
+        p.mask_bits = X.bits(); p.mask_ld = X.bits_ld();
+        const DensePrep& below = st->preps[st->index[li][m][i - 1]];
+        p.colsum_out = gsum + below.b_off; p.colsum_n = below.nout;   // bias gradient of Dense i-1, fused
       } else {
         p.epi = EPI_SCATTER_ADD; p.n_store = dp.kin; p.G = G; p.ldg = f.dim; p.idx = Ld.d_idx2;
       }
-      NF_TRY(launch_gemm(f, bn, ma, mb, p, n_tiles_n));
+      NF_TRY(launch_gemm(f, bn, ma, mb, mo, p, n_tiles_n));
       std::swap(gbuf, gnext);
     }
   }
@@ -1059,7 +1261,7 @@ int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* 
     NF_CUDA(cudaMemcpy(theta + (size_t)K * N, b_host, (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
     NF_CUDA(cudaMemcpy(X, X_host, (size_t)n * K * sizeof(float), cudaMemcpyHostToDevice));
     NF_TRY(tc_prepare_weights(f, theta));
-    NF_TRY(tc_gather_split(f, X, K, nullptr, K, n, act0));
+    NF_TRY(tc_gather_split(f, X, K, nullptr, K, n, act0, nullptr));
     std::vector<void*> acts{(void*)Y};
     NF_TRY(tc_mlp_forward(f, f.layers[0], 0, n, act0, acts));
     NF_CUDA(cudaStreamSynchronize(f.stream));

@@ -13,11 +13,15 @@ int tc_prepare_weights(Flow& f, const float* theta_dev);
 // forget the per-tensor scale slots of the previous sample chunk (buffers are about to be reused)
 int tc_begin_chunk(Flow& f);
 // x2 = X[:, idx2] -> split planes
-int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* act0);
+// amax_src: optional metadata slot whose [1] bounds max |X| (skips the absmax pass)
+int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* act0, const float* amax_src);
+// fresh zeroed {scale, amax} slot; exact max |X| over `count` floats
+float* tc_alloc_meta(Flow& f);
+int tc_absmax(Flow& f, const float* X, int64_t count, float* meta);
 int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts);
 // g_last: fp32 [n, out] gradient w.r.t. the last Dense's pre-activation; scratch0/1: activation-sized buffers
 int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts, float* g_last,
-                    void* scratch0, void* scratch1, float* G, double* gsum);
+                    const float* g_last_amax, void* scratch0, void* scratch1, float* G, double* gsum);
 void tc_release(Flow& f);
 int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* Wt_host, const float* b_host, int terms,
                      float* Y_host);
