@@ -336,12 +336,279 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Inverse direction (SURVEY row a5 / kernel K5): x0 = T^{-1}(y), logdet of the inverse, and for the
+// forward-KL objective `loglikelihood` (reference src/objectives/loglikelihood.jl:26-33, Bijectors
+// logpdf(td, y) = logpdf(q0, x0) + logdet_inv) the gradient w.r.t. theta by implicit differentiation:
+//   z = f^{-1}(y; th):  dL/dy = J^{-T} g,  dL/dth = -(df/dth)^T J^{-T} g - dlogdet_fwd/dth,
+//   g = dL/dz - grad_z logdet_fwd(z),  J = df/dz  (rank-one updates of the identity -> Sherman-Morrison).
+// Planar inverse: scalar root find of  a + m tanh(a + b) = w.y  (monotone since m = w.u_hat > -1; App. A.1),
+// safeguarded Newton inside the bracket [w.y - |m|, w.y + |m|].  Radial inverse: closed form (App. A.2).
+// No stash is needed: the backward sweep walks the FORWARD maps from x0 back to y.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int DP, int S>
+__global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
+  using N_ = Num<T>;
+  constexpr int STR = ew_stride<DP>();
+  constexpr int NACC = ew_nacc<DP>();
+  const int L = a.L, d = a.d, tid = threadIdx.x, nthr = blockDim.x;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* s_tab = reinterpret_cast<T*>(smem_raw);
+  T* s_acc = s_tab + (size_t)L * STR;
+  int* s_kind = reinterpret_cast<int*>(s_acc + (size_t)L * NACC);
+  for (int i = tid; i < L * STR; i += nthr) s_tab[i] = a.table[i];
+  for (int i = tid; i < L * NACC; i += nthr) s_acc[i] = 0;
+  for (int i = tid; i < L; i += nthr) s_kind[i] = a.kinds[i];
+  __syncthreads();
+  const bool want_grad = a.flags & EW_GRAD;
+  const T tol = sizeof(T) == 4 ? T(1e-7) : T(1e-15);
+  T obj_local = 0;
+  const int lane = tid & 31;
+  const int64_t group = (int64_t)nthr * S;
+  const int64_t ngroups = (a.N + group - 1) / group;
+  for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
+    T z[S][DP], ld[S];
+    bool live[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int64_t j = gi * group + (int64_t)s * nthr + tid;
+      live[s] = j < a.N;
+      const int64_t jj = live[s] ? j : 0;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) z[s][k] = (k < d) ? a.z0[jj * d + k] : T(0);
+      ld[s] = 0;
+    }
+    // ---- inverse sweep: inverse(f1∘...∘fL) applies f1^{-1} first (theta order) ----
+    for (int l = 0; l < L; ++l) {
+      const T* e = s_tab + (size_t)l * STR;
+      const int kind = s_kind[l];
+      if (kind == NF_PLANAR) {
+        const T b = e[0], m = e[1];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          T c = 0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) c += e[4 + k] * z[s][k];
+          const T am = N_::abs(m);
+          T lo = c - am, hi = c + am, al = c, t = 0;
+          for (int it = 0; it < 60; ++it) {
+            t = N_::tanh(al + b);
+            const T f = al + m * t - c;
+            if (N_::abs(f) <= tol * (1 + N_::abs(c))) break;
+            if (f > 0) hi = al; else lo = al;
+            T an = al - f / (1 + m * (1 - t * t));
+            if (!(an > lo && an < hi)) an = (lo + hi) / 2;
+            al = an;
+          }
+          t = N_::tanh(al + b);
+#pragma unroll
+          for (int k = 0; k < DP; ++k) z[s][k] -= e[4 + DP + k] * t;
+          ld[s] -= N_::log1p(m * (1 - t * t));
+        }
+      } else if (kind == NF_RADIAL) {
+        const T alpha = e[0], bh = e[1];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          T rho2 = 0, df[DP];
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { df[k] = (k < d) ? z[s][k] - e[4 + k] : T(0); rho2 += df[k] * df[k]; }
+          const T rho = N_::sqrt(rho2);
+          const T q = (alpha + bh) - rho;
+          const T r = (N_::sqrt(q * q + 4 * alpha * rho) - q) / 2;
+          const T fac = (alpha + r) / (alpha + bh + r);
+#pragma unroll
+          for (int k = 0; k < DP; ++k) z[s][k] = (k < d) ? e[4 + k] + fac * df[k] : T(0);
+          const T h = 1 / (alpha + r), g = bh * h;
+          ld[s] -= T(d - 1) * N_::log1p(g) + N_::log1p(g - g * h * r);
+        }
+      } else if (kind == NF_SHIFT) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int k = 0; k < DP; ++k) z[s][k] -= e[4 + k];
+      } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+          for (int k = 0; k < DP; ++k) z[s][k] *= e[4 + DP + k];
+          ld[s] -= e[0];
+        }
+      }
+    }
+    if (a.flags & (EW_WRITE_Y | EW_WRITE_LD)) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int64_t j = gi * group + (int64_t)s * nthr + tid;
+        if (!live[s]) continue;
+        if (a.flags & EW_WRITE_Y)
+#pragma unroll
+          for (int k = 0; k < DP; ++k)
+            if (k < d) a.y_out[j * d + k] = z[s][k];
+        if (a.flags & EW_WRITE_LD) a.ld_out[j] = ld[s];
+      }
+    }
+    if (!(a.flags & EW_TARGET)) continue;     // EW_TARGET here means "log-likelihood head"
+    // ---- head: logpdf(q0, x0) + logdet_inv ;  g = d logq0 / d x0 ----
+    T gz[S][DP];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      T q = 0;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) {
+        T u = 0, is = 1;
+        if (k < d) {
+          if (a.base) { is = 1 / a.base[d + k]; u = (z[s][k] - a.base[k]) * is; } else u = z[s][k];
+        }
+        q += u * u;
+        gz[s][k] = live[s] ? -u * is : T(0);
+      }
+      const T term = a.base_c0 - q / 2 + ld[s];
+      if (live[s]) {
+        obj_local += term;
+        if (a.flags & EW_WRITE_TERMS) a.terms_out[gi * group + (int64_t)s * nthr + tid] = term;
+      }
+    }
+    if (!want_grad) continue;
+    // ---- backward sweep: layers L-1 .. 0, walking the forward maps from x0 back to y ----
+    for (int l = L - 1; l >= 0; --l) {
+      const T* e = s_tab + (size_t)l * STR;
+      T* acc = s_acc + (size_t)l * NACC;
+      const int kind = s_kind[l];
+      if (kind == NF_PLANAR) {
+        const T b = e[0], m = e[1];
+        T ga[S], tt[S], gyn[S][DP];
+        T g_m = 0, g_b = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const T w8 = live[s] ? T(1) : T(0);
+          T dot = b;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) dot += e[4 + k] * z[s][k];
+          const T t = N_::tanh(dot);
+          const T psi = 1 - t * t, den = 1 + m * psi;
+          // g_hat = gz - grad_z logdet_fwd = gz + (2 t m psi / den) w ;  gy = g_hat - psi w (u_hat . g_hat) / den
+          const T cw = w8 * 2 * t * m * psi / den;
+          T ug = 0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { gyn[s][k] = gz[s][k] + cw * e[4 + k]; ug += e[4 + DP + k] * gyn[s][k]; }
+          const T sc = psi * ug / den;
+          T ugy = 0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { gyn[s][k] -= sc * e[4 + k]; ugy += e[4 + DP + k] * gyn[s][k]; }
+          // parameter gradients = forward-layer backward at z with upstream (-gy, -1)
+          const T gt = -ugy + w8 * 2 * t * m / den;
+          ga[s] = psi * gt; tt[s] = t;
+          g_m += -w8 * psi / den; g_b += ga[s];
+        }
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          T gu = 0, gw = 0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            gu += -tt[s] * gyn[s][k];
+            gw += z[s][k] * ga[s];
+          }
+          if (k < d) {
+            gu = warp_sum(gu); gw = warp_sum(gw);
+            if (lane == 0) { atomicAdd(&acc[k], gu); atomicAdd(&acc[DP + k], gw); }
+          }
+        }
+        g_m = warp_sum(g_m); g_b = warp_sum(g_b);
+        if (lane == 0) { atomicAdd(&acc[2 * DP], g_m); atomicAdd(&acc[2 * DP + 1], g_b); }
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { z[s][k] += e[4 + DP + k] * tt[s]; gz[s][k] = gyn[s][k]; }
+      } else if (kind == NF_RADIAL) {
+        const T alpha = e[0], bh = e[1];
+        T g_al = 0, g_bh = 0, gz0[DP];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) gz0[k] = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const T w8 = live[s] ? T(1) : T(0);
+          T u[DP], r2 = 0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { u[k] = (k < d) ? z[s][k] - e[4 + k] : T(0); r2 += u[k] * u[k]; }
+          const T r = N_::sqrt(r2), ir = r > 0 ? 1 / r : T(0);
+          const T h = 1 / (alpha + r), g = bh * h, gp = -bh * h * h;
+          const T A = 1 + g, Bq = 1 + alpha * bh * h * h;
+          const T dld_dh = T(d - 1) * bh / A + 2 * alpha * bh * h / Bq;
+          const T dld_dr = -h * h * dld_dh;
+          // g_hat = gz - (dld/dr) u / r ;  J = A I + (gp / r) u u^T  (symmetric) ;  gy = J^{-1} g_hat
+          T gh[DP], ugh = 0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { gh[k] = gz[s][k] - w8 * dld_dr * u[k] * ir; ugh += u[k] * gh[k]; }
+          const T cj = (gp * ir) / (A + gp * r);
+          T gy[DP], ugy = 0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) { gy[k] = (gh[k] - cj * u[k] * ugh) / A; ugy += u[k] * gy[k]; }
+          // parameter gradients = forward-layer backward at z with upstream (-gy, -1)
+          g_al += -ugy * gp - w8 * ((-h * h) * dld_dh + bh * h * h / Bq);
+          g_bh += -ugy * h - w8 * (T(d - 1) * h / A + alpha * h * h / Bq);
+          // d f / d z0 = -(J - I)  =>  contribution (J - I)^T gy  with upstream -gy, plus the logdet term
+          const T coef = -ugy * gp - w8 * dld_dr;       // same r-channel as the forward kernel, upstream (-gy, -1)
+#pragma unroll
+          for (int k = 0; k < DP; ++k) {
+            gz0[k] += g * gy[k] - coef * u[k] * ir;
+            z[s][k] = (k < d) ? z[s][k] + g * u[k] : T(0);
+            gz[s][k] = gy[k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DP; ++k)
+          if (k < d) {
+            const T v = warp_sum(gz0[k]);
+            if (lane == 0) atomicAdd(&acc[k], v);
+          }
+        g_al = warp_sum(g_al); g_bh = warp_sum(g_bh);
+        if (lane == 0) { atomicAdd(&acc[2 * DP], g_al); atomicAdd(&acc[2 * DP + 1], g_bh); }
+      } else if (kind == NF_SHIFT) {
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          T v = 0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) { v -= gz[s][k]; z[s][k] += e[4 + k]; }
+          if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+        }
+      } else {  // NF_SCALE: z = y / a
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          T v = 0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            v -= gz[s][k] * z[s][k] * e[4 + DP + k];
+            gz[s][k] *= e[4 + DP + k];
+            z[s][k] *= e[4 + k];
+          }
+          if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (a.gpart)
+    for (int i = tid; i < L * NACC; i += nthr) a.gpart[(size_t)blockIdx.x * L * NACC + i] = s_acc[i];
+  if (a.epart) {
+    double ev = warp_sum((double)obj_local);
+    __shared__ double s_e[32];
+    if ((tid & 31) == 0) s_e[tid >> 5] = ev;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int w = 0; w < (nthr + 31) / 32; ++w) t += s_e[w];
+      a.epart[blockIdx.x] = t;
+    }
+  }
+}
+
 // Deterministic cross-CTA reduction + chain rule from the reduced per-layer sums to theta order.
 // One thread per layer; gsum[P+1] receives UNSCALED sums (gradient sums then the ELBO sum at [P]).
 template <typename T, int DP>
 __global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
                                    const T* __restrict__ gpart, const double* __restrict__ epart, int nblocks,
-                                   int64_t N, int64_t P, int want_grad, double* __restrict__ gsum) {
+                                   int64_t N, int64_t P, int want_grad, int inverse, double* __restrict__ gsum) {
   constexpr int NACC = ew_nacc<DP>();
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l == 0) {
@@ -384,7 +651,7 @@ __global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMet
       for (int k = 0; k < d; ++k) g[k] = G[k];
       break;
     case NF_SCALE:
-      for (int k = 0; k < d; ++k) g[k] = G[k] + (double)N / (double)p[k];
+      for (int k = 0; k < d; ++k) g[k] = G[k] + (inverse ? -1.0 : 1.0) * (double)N / (double)p[k];
       break;
   }
 }
@@ -394,16 +661,16 @@ __global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMet
 // ---------------------------------------------------------------------------------------------
 template <typename T, int DP, int S>
 static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, const T* z0_dev, uint64_t seed,
-                     int flags, T* y_out, T* ld_out, T* terms_out, double* gsum_dev) {
+                     int flags, T* y_out, T* ld_out, T* terms_out, double* gsum_dev, bool inverse) {
   const int L = (int)f.layers.size(), d = f.dim;
   constexpr int STR = ew_stride<DP>(), NACC = ew_nacc<DP>();
   const int threads = 128;
-  const size_t smem = ((size_t)L * STR + (size_t)L * NACC + (size_t)L * S * threads) * sizeof(T) + (size_t)L * sizeof(int) + 16;
+  const size_t smem = ((size_t)L * STR + (size_t)L * NACC + (inverse ? 0 : (size_t)L * S * threads)) * sizeof(T) + (size_t)L * sizeof(int) + 16;
   if (smem > 200 * 1024) {
     set_error("elementwise flow with %d layers needs %zu B of shared memory (limit 200 KiB)", L, smem);
     return NF_ERR_UNSUPPORTED;
   }
-  auto kern = ew_flow_kernel<T, DP, S>;
+  auto kern = inverse ? ew_inv_flow_kernel<T, DP, S> : ew_flow_kernel<T, DP, S>;
   NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t group = (int64_t)threads * S;
   int max_blocks = 0;
@@ -433,7 +700,7 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
   NF_LAUNCH_CHECK();
   if (gsum_dev) {
     ew_finalize_kernel<T, DP><<<(L + 63) / 64, 64, 0, f.stream>>>(theta_dev, f.d_ew_meta, L, d, gpart, epart, grid, N,
-                                                                 f.P, (flags & EW_GRAD) ? 1 : 0, gsum_dev);
+                                                                 f.P, (flags & EW_GRAD) ? 1 : 0, inverse ? 1 : 0, gsum_dev);
     NF_LAUNCH_CHECK();
   }
   return NF_OK;
@@ -441,9 +708,9 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
 
 template <typename T>
 int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
-           bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev) {
+           bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev, bool inverse, bool head) {
   int flags = 0;
-  if (tgt) flags |= EW_TARGET;
+  if (tgt || (inverse && head)) flags |= EW_TARGET;
   if (want_grad) flags |= EW_GRAD;
   if (y_out) flags |= EW_WRITE_Y;
   if (ld_out) flags |= EW_WRITE_LD;
@@ -451,7 +718,7 @@ int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const v
   const int d = f.dim;
 #define NF_EW_CASE(DPV, SV)                                                                              \
   return ew_launch<T, DPV, SV>(f, tgt, (const T*)theta_dev, N, (const T*)z0_dev, seed, flags, (T*)y_out, \
-                               (T*)ld_out, (T*)terms_out, gsum_dev)
+                               (T*)ld_out, (T*)terms_out, gsum_dev, inverse)
   if (d <= 2) NF_EW_CASE(2, 4);
   if (d <= 4) NF_EW_CASE(4, 2);
   if (d <= 8) NF_EW_CASE(8, 1);
@@ -463,7 +730,7 @@ int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const v
   return NF_ERR_UNSUPPORTED;
 }
 
-template int ew_run<float>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*);
-template int ew_run<double>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*);
+template int ew_run<float>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool, bool);
+template int ew_run<double>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool, bool);
 
 }  // namespace nf

@@ -154,6 +154,7 @@ struct Target {
 // elementwise.cu
 template <typename T>
 int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
-           bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev);
+           bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev, bool inverse = false,
+           bool head = false);
 
 }  // namespace nf

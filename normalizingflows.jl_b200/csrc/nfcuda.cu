@@ -219,12 +219,14 @@ struct Job {
 // Runs the job; leaves un-normalised sums in f.d_gsum (gradient sums [0,P), objective sum at [P]).
 static int run_job(Flow& f, const Job& j) {
   NF_REQUIRE(j.N > 0, "N must be positive");
-  if (f.all_elementwise && (j.op == OP_ELBO || j.op == OP_FORWARD)) {
+  if (f.all_elementwise && (j.op == OP_ELBO || j.op == OP_FORWARD || j.op == OP_INVERSE || j.op == OP_LOGLIK)) {
+    const bool inv = j.op == OP_INVERSE || j.op == OP_LOGLIK;
+    const bool head = j.op == OP_LOGLIK;
+    double* gs = (j.op == OP_ELBO || j.op == OP_LOGLIK) ? f.d_gsum : nullptr;
+    NF_REQUIRE(!inv || j.in_dev, "inverse / log-likelihood need input samples");
     if (f.dtype == NF_F32)
-      return ew_run<float>(f, j.tgt, j.theta_dev, j.N, j.in_dev, j.seed, j.want_grad, j.y_out, j.ld_out, j.terms_out,
-                           j.op == OP_ELBO ? f.d_gsum : nullptr);
-    return ew_run<double>(f, j.tgt, j.theta_dev, j.N, j.in_dev, j.seed, j.want_grad, j.y_out, j.ld_out, j.terms_out,
-                          j.op == OP_ELBO ? f.d_gsum : nullptr);
+      return ew_run<float>(f, j.tgt, j.theta_dev, j.N, j.in_dev, j.seed, j.want_grad, j.y_out, j.ld_out, j.terms_out, gs, inv, head);
+    return ew_run<double>(f, j.tgt, j.theta_dev, j.N, j.in_dev, j.seed, j.want_grad, j.y_out, j.ld_out, j.terms_out, gs, inv, head);
   }
   GeneralJob g;
   g.op = j.op; g.tgt = j.tgt; g.theta_dev = j.theta_dev; g.in_dev = j.in_dev; g.N = j.N; g.seed = j.seed;

@@ -82,7 +82,7 @@ def test_elbo_value_and_grad(gpu, kind, dim, tname, N, kw, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
-@pytest.mark.parametrize("kind", ["realnvp", "nsf"])
+@pytest.mark.parametrize("kind", ["realnvp", "nsf", "planar", "radial"])
 def test_forward_inverse_consistency(gpu, kind, dtype):
     """reference test/flow.jl:25-39,92-106: x ≈ inv(fwd(x)), lj_fwd ≈ -lj_inv at d = 5, vector and d x 10 batch."""
     nf = gpu
@@ -95,6 +95,8 @@ def test_forward_inverse_consistency(gpu, kind, dtype):
         y_ref, lj_ref = of.forward(torch.from_numpy(x))
         assert rel_err(y, y_ref.detach().numpy()) <= 1e-5
         xr, lji = gf.inverse_with_logabsdet_jacobian(y)
+        if kind == "planar" and dtype == np.float32:
+            rtol = 5e-4        # 10 chained scalar root finds in Float32 (the reference tests Float32 at 1e-4 with its own solver)
         np.testing.assert_allclose(xr, x, rtol=rtol, atol=rtol)
         np.testing.assert_allclose(lj, -lji, rtol=rtol, atol=rtol)
         lp = gf.logpdf(y)
@@ -104,7 +106,9 @@ def test_forward_inverse_consistency(gpu, kind, dtype):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
 @pytest.mark.parametrize("kind,dim,kw", [("realnvp", 5, dict(hdims=[32, 32], nlayers=2)),
-                                         ("nsf", 16, dict(hdims=[32, 32], K=10, B=5.0, nlayers=2))])
+                                         ("nsf", 16, dict(hdims=[32, 32], K=10, B=5.0, nlayers=2)),
+                                         ("planar", 2, dict(nlayers=10)), ("planar", 5, dict(nlayers=6)),
+                                         ("radial", 2, dict(nlayers=10)), ("radial", 5, dict(nlayers=6))])
 def test_loglikelihood_value_and_grad(gpu, kind, dim, kw, dtype):
     """forward-KL objective (reference src/objectives/loglikelihood.jl:26-33) and its gradient."""
     nf = gpu
@@ -119,6 +123,8 @@ def test_loglikelihood_value_and_grad(gpu, kind, dim, kw, dtype):
     g = np.empty(gf.theta.size, dtype=dtype)
     K.check(K.lib().nf_loglik_value_and_grad(gf.handle(), K.ptr(gf.theta), xs.shape[0], K.ptr(xs), 1.0, C.byref(val), K.ptr(g)))
     tv, tg = TOL[dtype]
+    if kind == "planar" and dtype == np.float32:
+        tv, tg = 2e-5, 5e-4   # chained Float32 root finds (oracle and kernel stop at different iterates)
     assert abs(val.value - v_ref) <= tv * max(abs(v_ref), 1.0)
     assert rel_err(g, g_ref) <= tg
     assert abs(nf.loglikelihood(None, gf, xs) - val.value) <= 1e-6 * max(abs(v_ref), 1.0)
