@@ -93,6 +93,63 @@ def make_theta(nf):
     return flow
 
 
+def run_side_config(args):
+    """--config c1|c2|c4|c4b|c3x1: the other BASELINE.json configs (parity-test cases, reported for context; single GPU,
+    device-resident inputs).  Not the driver's headline line."""
+    import torch
+    import nfload
+    nf = nfload.load()
+    K = nf._capi
+    lib = K.lib()
+    K.check(lib.nf_init(0))
+    nf.seed(123)
+    cfg = args.config
+    if cfg == "c1":
+        flow, tgt, n, name = nf.planarflow(nf.MvNormal(np.zeros(2)), 20, np.float32), nf.Banana(2, 1.0, 10.0), 10, "planar x20 d=2 Banana N=10"
+    elif cfg == "c2":
+        flow, tgt, n, name = nf.radialflow(nf.MvNormal(np.zeros(2)), 20, np.float32), nf.WarpedGauss(1.0, 0.12), 1 << 20, "radial x20 d=2 WarpedGauss N=2^20"
+    elif cfg == "c2p":
+        flow, tgt, n, name = nf.planarflow(nf.MvNormal(np.zeros(2)), 20, np.float32), nf.Banana(2, 1.0, 10.0), 1 << 20, "planar x20 d=2 Banana N=2^20"
+    elif cfg in ("c4", "c4b"):
+        nl = 4 if cfg == "c4" else 8
+        flow, tgt, n, name = nf.nsf(nf.MvNormal(np.zeros(16)), [32, 32], 10, 5.0, nl, np.float32), nf.Cross(2.0, 0.15, 16), 1 << 20, "NSF d=16 K=10 B=5 [32,32] %d couplings Cross x8 N=2^20" % (2 * nl)
+    elif cfg == "c3x1":
+        flow, tgt, n, name = make_theta(nf), nf.Funnel(DIM), 1 << 20, "RealNVP C3 in NF_MMA_F16X1 (single fp16 pass, NOT parity grade)"
+        flow.set_mma_mode(nf.NF_MMA_F16X1)
+    else:
+        raise SystemExit("unknown --config " + cfg)
+    n = args.batch if args.batch != BATCH_PER_GPU else n
+    dev = torch.device("cuda", 0)
+    d = flow.dim
+    theta_dev = torch.from_numpy(flow.theta).to(dev)
+    z0 = torch.randn((n, d), device=dev, dtype=torch.float32)
+    grad = torch.empty(flow.num_params, device=dev, dtype=torch.float32)
+    val = C.c_double()
+    torch.cuda.synchronize()
+    h, th = flow.handle(), tgt.handle()
+
+    def step():
+        K.check(lib.nf_elbo_value_and_grad_dev(h, th, theta_dev.data_ptr(), n, z0.data_ptr(), 0, -1.0, C.byref(val), grad.data_ptr()))
+    for _ in range(max(args.warmup, 3)):
+        step()
+    lib.nf_launch_count(1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        step()
+        dev_ms += lib.nf_last_device_ms(h)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sustained, burst, hbm, src = peaks()
+    v = n * args.steps / dt
+    print(json.dumps({"metric": "ELBO+grad samples/sec", "config": {"workload": name}, "value": v, "unit": "samples/s",
+                      "ms_per_step": 1e3 * dt / args.steps, "device_ms_per_step": dev_ms / args.steps, "steps": args.steps,
+                      "gpu_launches": int(lib.nf_launch_count(0)), "loss": val.value,
+                      "roofline": {"bound": "hbm", "achieved": v * 4 * d / 1e9, "peak": hbm, "unit": "GB/s", "frac": v * 4 * d / 1e9 / hbm,
+                                   "note": "algorithmic bytes = 4*d per sample (Z0 read); these kernels are SFU/FP32-issue bound, see DESIGN.md"}}))
+
+
 def run_reference(args):
     """--impl reference: the CPU restatement oracle (kind 'port') on all host cores, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -157,10 +214,13 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="base draws per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", help="c3 (headline) | c1 | c2 | c2p | c4 | c4b | c3x1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "c3":
+        return run_side_config(args)
 
     import torch
     import torch.distributed as dist

@@ -201,7 +201,7 @@ int simt_mlp_backward(Flow& f, const MLPDesc& md, const T* theta, int64_t n, con
       EpiMaskLrelu<T> epi{gin, kin, in, kin};
       NF_TRY((launch_simt_gemm<T, false, true>(f, g, kout, theta + md.w_off[i], kout, n, kin, kout, 0, epi)));
       g = gin;
-    } else {
+    } else if (G) {
       EpiScatterAdd<T> epi{G, d, d_idx2};
       NF_TRY((launch_simt_gemm<T, false, true>(f, g, kout, theta + md.w_off[i], kout, n, kin, kout, 0, epi)));
     }
@@ -236,8 +236,11 @@ int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, i
   return NF_OK;
 }
 
+// need_input_grad = false for the layer whose input is the batch itself (base draws / data): the gradient w.r.t. its
+// conditioner input is never used, so the first-Dense dgrad (GEMM + scatter) is skipped.
 template <typename T, bool INV>
-int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, Chunk& c, const T* Xin, const T* Xout) {
+int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, Chunk& c, const T* Xin, const T* Xout,
+                      bool need_input_grad) {
   const int d = f.dim, cc = (int)Ld.idx1.size();
   const int64_t n = c.n;
   const bool tc = f.mma_mode != NF_MMA_SIMT;
@@ -255,19 +258,19 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
         G, INV ? Xout : Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, n, gA, gB, mS, mT);
     NF_LAUNCH_CHECK();
     if (tc) {
-      NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, mS, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
-      NF_TRY(tc_mlp_backward(f, Ld, 1, n, b.act0, b.acts[1], (float*)gB, mT, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
+      NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, mS, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum));
+      NF_TRY(tc_mlp_backward(f, Ld, 1, n, b.act0, b.acts[1], (float*)gB, mT, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum));
     } else {
       // s network: temporaries gC + (gA after it has been consumed is NOT safe) -> use a dedicated pair
-      NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gA, G, d, Ld.d_idx2, f.d_gsum));
-      NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[1], theta, n, (const T*)b.act0, b.acts[1], gB, gC, gB, G, d, Ld.d_idx2, f.d_gsum));
+      NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gA, need_input_grad ? G : nullptr, d, Ld.d_idx2, f.d_gsum));
+      NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[1], theta, n, (const T*)b.act0, b.acts[1], gB, gC, gB, need_input_grad ? G : nullptr, d, Ld.d_idx2, f.d_gsum));
     }
   } else {
     rqs_bwd_kernel<T, INV><<<(unsigned)ceil_div(n * cc, 128), 128, 0, f.stream>>>(
         G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA);
     NF_LAUNCH_CHECK();
-    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, nullptr, c.ga[2], c.ga[3], (float*)G, f.d_gsum));
-    else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, G, d, Ld.d_idx2, f.d_gsum));
+    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, nullptr, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum));
+    else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, need_input_grad ? G : nullptr, d, Ld.d_idx2, f.d_gsum));
   }
   return NF_OK;
 }
@@ -333,7 +336,7 @@ int sweep_backward_fwd(Flow& f, Chunk& c, const T* theta) {   // backward of the
   const int L = (int)f.layers.size();
   int state = L;
   for (int li = 0; li < L; ++li) {   // layer 0 was applied last
-    NF_TRY((coupling_backward<T, false>(f, f.layers[li], c.lb[li], theta, c, (const T*)c.X[state - 1], (const T*)c.X[state])));
+    NF_TRY((coupling_backward<T, false>(f, f.layers[li], c.lb[li], theta, c, (const T*)c.X[state - 1], (const T*)c.X[state], state - 1 > 0)));
     --state;
   }
   return NF_OK;
@@ -344,7 +347,7 @@ int sweep_backward_inv(Flow& f, Chunk& c, const T* theta) {   // backward of the
   const int L = (int)f.layers.size();
   int state = L;
   for (int li = L - 1; li >= 0; --li) {   // layer L-1's inverse was applied last
-    NF_TRY((coupling_backward<T, true>(f, f.layers[li], c.lb[li], theta, c, (const T*)c.X[state - 1], (const T*)c.X[state])));
+    NF_TRY((coupling_backward<T, true>(f, f.layers[li], c.lb[li], theta, c, (const T*)c.X[state - 1], (const T*)c.X[state], state - 1 > 0)));
     --state;
   }
   return NF_OK;

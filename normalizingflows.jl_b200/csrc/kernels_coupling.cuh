@@ -171,6 +171,7 @@ __global__ void affine_apply_kernel(const T* __restrict__ Xin, const T* __restri
   const int64_t total = N * d;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t iters = (total + stride - 1) / stride;      // same trip count for every thread (warp collectives inside)
+  const bool small = total < ((int64_t)1 << 31);            // 32-bit index math (64-bit division is ~10x the cost)
   float run_max = 0.f;
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t e = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,8 +180,9 @@ __global__ void affine_apply_kernel(const T* __restrict__ Xin, const T* __restri
     int64_t r = 0;
     int k = -1;
     if (valid) {
-      r = e / d;
-      const int j = (int)(e - r * d);
+      int j;
+      if (small) { const unsigned int r32 = (unsigned int)e / (unsigned int)d; r = r32; j = (int)((unsigned int)e - r32 * (unsigned int)d); }
+      else { r = e / d; j = (int)(e - r * d); }
       const T x = Xin[e];
       k = pos[j];
       if (k >= 0) {
@@ -216,10 +218,12 @@ __global__ void affine_bwd_kernel(T* __restrict__ G, const T* __restrict__ X1src
   const int64_t total = N * c;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float maxS = 0.f, maxT = 0.f;
+  const bool small = total < ((int64_t)1 << 31);
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     T gs_out = 0, gt = 0;
-    const int64_t r = e / c;
-    const int k = (int)(e - r * c);
+    int64_t r; int k;
+    if (small) { const unsigned int r32 = (unsigned int)e / (unsigned int)c; r = r32; k = (int)((unsigned int)e - r32 * (unsigned int)c); }
+    else { r = e / c; k = (int)(e - r * c); }
     const int j = idx1[k];
     const T s = S[e];
     const T go = G[r * d + j];

@@ -58,6 +58,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 28)) __trap();   // a protocol bug must fail loudly instead of hanging the GPU
   }
 }
+// same, for warps that have nothing else to do: back off between polls so they do not steal issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+    if (++spins > (1u << 26)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -358,7 +375,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       const int ncols_here = p.n_store - (n0 + cbase);   // columns of this thread's range that matter (warp-uniform)
       for (int kc = 0; kc < nk; ++kc, ++it) {
         const uint32_t acc = it & 1, accph = (it >> 1) & 1;
-        mbar_wait(tfull_bar(acc), accph);
+        mbar_wait_relaxed(tfull_bar(acc), accph);
         NF_DBG(2, 3 * it, threadIdx.x == 64);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cbase;
@@ -1200,7 +1217,7 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
         default: NF_TRY(launch_wgrad_bn<256>(f, mx, mg, wp)); break;
       }
     }
-    {  // data gradient
+    if (i > 0 || G) {  // data gradient (skipped for the first Dense when nobody needs d/d(conditioner input))
       const int bn = std::min(dp.nd_rows, 256);
       const int n_tiles_n = dp.nd_rows / bn;
       CUtensorMap ma, mb;
