@@ -229,8 +229,22 @@ int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, i
     affine_apply_kernel<T, INV><<<(unsigned)std::min<int64_t>(ceil_div(n * d, 256), 16 * kNumSMs), 256, 0, f.stream>>>(
         Xin, (const T*)b.acts[0].back(), (const T*)b.acts[1].back(), Ld.d_pos, c, d, n, Xout, ld, amax_out);
   } else {
-    rqs_apply_kernel<T, INV><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
-        Xin, (const T*)b.acts[0].back(), Ld.d_idx1, c, d, Ld.K, (T)Ld.B, n, Xout, ld, bins);
+    const size_t sm = (size_t)128 * (3 * Ld.K - 1) * sizeof(T);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n * c, 128), 32 * kNumSMs);
+    if (Ld.K <= 8) {
+      rqs_apply_kernel<T, 8, INV><<<grid, 128, sm, f.stream>>>(Xin, (const T*)b.acts[0].back(), Ld.d_idx1, Ld.d_pos, c, d, Ld.K,
+                                                               (T)Ld.B, n, Xout, ld, bins, amax_out);
+    } else if (Ld.K <= 10) {
+      rqs_apply_kernel<T, 10, INV><<<grid, 128, sm, f.stream>>>(Xin, (const T*)b.acts[0].back(), Ld.d_idx1, Ld.d_pos, c, d, Ld.K,
+                                                                (T)Ld.B, n, Xout, ld, bins, amax_out);
+    } else if (Ld.K <= 16) {
+      rqs_apply_kernel<T, 16, INV><<<grid, 128, sm, f.stream>>>(Xin, (const T*)b.acts[0].back(), Ld.d_idx1, Ld.d_pos, c, d, Ld.K,
+                                                                (T)Ld.B, n, Xout, ld, bins, amax_out);
+    } else {
+      auto kern = rqs_apply_kernel<T, 64, INV>;
+      NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      kern<<<grid, 128, sm, f.stream>>>(Xin, (const T*)b.acts[0].back(), Ld.d_idx1, Ld.d_pos, c, d, Ld.K, (T)Ld.B, n, Xout, ld, bins, amax_out);
+    }
   }
   NF_LAUNCH_CHECK();
   return NF_OK;
@@ -266,10 +280,23 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
       NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[1], theta, n, (const T*)b.act0, b.acts[1], gB, gC, gB, need_input_grad ? G : nullptr, d, Ld.d_idx2, f.d_gsum));
     }
   } else {
-    rqs_bwd_kernel<T, INV><<<(unsigned)ceil_div(n * cc, 128), 128, 0, f.stream>>>(
-        G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA);
+    float* mR = tc ? tc_alloc_meta(f) : nullptr;
+    if (tc) NF_REQUIRE(mR, "tcgen05 path: out of tensor metadata slots");
+    const size_t sm = (size_t)128 * (3 * Ld.K - 1) * sizeof(T);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n * cc, 128), 32 * kNumSMs);
+    if (Ld.K <= 8) {
+      rqs_bwd_kernel<T, 8, INV><<<grid, 128, sm, f.stream>>>(G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR);
+    } else if (Ld.K <= 10) {
+      rqs_bwd_kernel<T, 10, INV><<<grid, 128, sm, f.stream>>>(G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR);
+    } else if (Ld.K <= 16) {
+      rqs_bwd_kernel<T, 16, INV><<<grid, 128, sm, f.stream>>>(G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR);
+    } else {
+      auto kern = rqs_bwd_kernel<T, 64, INV>;
+      NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      kern<<<grid, 128, sm, f.stream>>>(G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR);
+    }
     NF_LAUNCH_CHECK();
-    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, nullptr, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum));
+    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, mR, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum));
     else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, need_input_grad ? G : nullptr, d, Ld.d_idx2, f.d_gsum));
   }
   return NF_OK;
@@ -302,7 +329,7 @@ int sweep_forward(Flow& f, Chunk& c, const T* theta, int32_t* bins, int64_t bins
       bl = bins + bins_layer_off + bins_chunk_off * (int64_t)Ld.idx1.size();
       bins_layer_off += N_total * (int64_t)Ld.idx1.size();
     }
-    const bool track = !c.xmeta.empty() && Ld.kind == NF_AFFINE_COUPLING;
+    const bool track = !c.xmeta.empty();
     NF_TRY((coupling_apply<T, false>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, bl, c.xmeta.empty() ? nullptr : c.xmeta[state],
                                      track ? c.xmeta[state + 1] : nullptr)));
     if (!c.xmeta.empty() && !track) c.xmeta[state + 1] = nullptr;   // unknown bound: the next split measures it
@@ -322,7 +349,7 @@ int sweep_inverse(Flow& f, Chunk& c, const T* theta) {
     LayerBufs& b = c.stash ? c.lb[li] : c.lb[0];
     const T* Xin = (const T*)c.xin(state);
     T* Xout = (T*)c.xout(state);
-    const bool track = !c.xmeta.empty() && Ld.kind == NF_AFFINE_COUPLING;
+    const bool track = !c.xmeta.empty();
     NF_TRY((coupling_apply<T, true>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, nullptr, c.xmeta.empty() ? nullptr : c.xmeta[state],
                                     track ? c.xmeta[state + 1] : nullptr)));
     if (!c.xmeta.empty() && !track) c.xmeta[state + 1] = nullptr;

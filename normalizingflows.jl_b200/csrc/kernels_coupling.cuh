@@ -340,124 +340,232 @@ __device__ __forceinline__ void rqs_eval_inv(const RqsBin<T>& b, T y, T& x, T& l
   xi_out = xi;
 }
 
-// one thread per sample; loops over the c transformed coordinates
-template <typename T, bool INV>
-__global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict__ raw, const int* __restrict__ idx1,
-                                 int c, int d, int K, T B, int64_t N, T* __restrict__ Xout, T* __restrict__ ld,
-                                 int32_t* __restrict__ bins) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= N) return;
-  const int P3 = 3 * K - 1;
-  const T* xi = Xin + r * d;
-  T* xo = Xout + r * d;
-  for (int j = 0; j < d; ++j) xo[j] = xi[j];
-  T sum = 0;
-  for (int i = 0; i < c; ++i) {
-    const T* tw = raw + (r * c + i) * P3;
-    const T v = xi[idx1[i]];
-    RqsBin<T> b;
-    rqs_locate<T, INV>(tw, tw + K, tw + 2 * K, K, B, v, b);
-    if (bins) bins[r * c + i] = b.k;
-    if (b.k >= 1 && b.k <= K) {
-      T o, lj, tmp;
-      if (!INV) rqs_eval_fwd(b, v, o, lj); else rqs_eval_inv(b, v, o, lj, tmp);
-      xo[idx1[i]] = o;
-      sum += lj;
+// Shared evaluation of one (sample, coordinate) spline from its 3K-1 logits held in registers/local memory:
+// exp() of every width/height logit is computed once and reused by the bin search, the knots and the softmax backward.
+template <typename T, int KMAX> struct RqsLocal {
+  T ew[KMAX], eh[KMAX];
+  T Sw, Sh;
+};
+
+template <typename T, int KMAX, bool INV>
+__device__ __forceinline__ void rqs_locate_cached(const T* __restrict__ tl, int K, T B, T v, RqsLocal<T, KMAX>& L, RqsBin<T>& b) {
+  using N = Num<T>;
+  T Sw = 0, Sh = 0;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K) {
+      L.ew[k] = N::exp(tl[k]); L.eh[k] = N::exp(tl[K + k]);
+      Sw = add_rn(Sw, L.ew[k]); Sh = add_rn(Sh, L.eh[k]);
     }
   }
-  if (ld) ld[r] += sum;
+  L.Sw = Sw; L.Sh = Sh;
+  const T* es = INV ? L.eh : L.ew;
+  const T* eo = INV ? L.ew : L.eh;
+  const T rSs = 1 / (INV ? Sh : Sw), rSo = 1 / (INV ? Sw : Sh);   // softmax by reciprocal multiply (one division per family)
+  const T twoB = 2 * B;
+  // knots of the searched family: sequential cumsum, knot = (2B)*cs - B without FMA contraction
+  T cs = 0, prev = -B, prevc = 0, s0 = 0, s1 = 0, c0 = 0, c1 = 0;
+  int bin = K + 1;
+  bool found = !(prev < v);
+  if (found) bin = 0;
+#pragma unroll
+  for (int k = 1; k <= KMAX; ++k) {
+    if (k <= K && !found) {
+      cs = add_rn(cs, mul_rn(es[k - 1], rSs));
+      const T knot = add_rn(mul_rn(twoB, cs), -B);
+      if (!(knot < v)) { bin = k; s0 = prev; s1 = knot; c0 = prevc; c1 = cs; found = true; }
+      else { prev = knot; prevc = cs; }
+    }
+  }
+  b.k = bin;
+  if (bin < 1 || bin > K) return;
+  T co = 0, o0 = -B, o1 = 0, oc0 = 0, oc1 = 0;
+#pragma unroll
+  for (int k = 1; k <= KMAX; ++k) {
+    if (k <= bin) {
+      co = add_rn(co, mul_rn(eo[k - 1], rSo));
+      const T knot = add_rn(mul_rn(twoB, co), -B);
+      if (k == bin - 1) { o0 = knot; oc0 = co; }
+      if (k == bin) { o1 = knot; oc1 = co; }
+    }
+  }
+  if (!INV) { b.x0 = s0; b.x1 = s1; b.cx0 = c0; b.cx1 = c1; b.y0 = o0; b.y1 = o1; b.cy0 = oc0; b.cy1 = oc1; }
+  else      { b.y0 = s0; b.y1 = s1; b.cy0 = c0; b.cy1 = c1; b.x0 = o0; b.x1 = o1; b.cx0 = oc0; b.cx1 = oc1; }
+  b.Sw = Sw; b.Sh = Sh;
+  b.d0 = (bin - 1 == 0) ? T(1) : N::log(N::exp(tl[2 * K + bin - 2]) + 1);
+  b.d1 = (bin == K) ? T(1) : N::log(N::exp(tl[2 * K + bin - 1]) + 1);
+}
+
+// One thread per (sample, transformed coordinate).  The block's 3K-1 logits per thread are one contiguous chunk
+// of theta_raw: staged through shared memory so global traffic is coalesced (row stride 3K-1 is conflict-free).
+// Passthrough columns are copied by a separate coalesced loop.  Dynamic smem: blockDim * (3K-1) * sizeof(T).
+template <typename T, int KMAX, bool INV>
+__global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict__ raw, const int* __restrict__ idx1,
+                                 const int* __restrict__ pos, int c, int d, int K, T B, int64_t N, T* __restrict__ Xout,
+                                 T* __restrict__ ld, int32_t* __restrict__ bins, float* __restrict__ amax_meta) {
+  extern __shared__ __align__(16) unsigned char rqs_smem[];
+  T* sm = reinterpret_cast<T*>(rqs_smem);
+  const int P3 = 3 * K - 1;
+  const int64_t total = N * c;
+  float run_max = 0.f;
+  // passthrough columns
+  {
+    const int64_t nd = N * d;
+    const bool small = nd < ((int64_t)1 << 31);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nd; e += (int64_t)gridDim.x * blockDim.x) {
+      const int j = small ? (int)((unsigned int)e % (unsigned int)d) : (int)(e % d);
+      if (pos[j] < 0) { const T x = Xin[e]; Xout[e] = x; run_max = fmaxf(run_max, fabsf((float)x)); }
+    }
+  }
+  const int64_t nblk = (total + blockDim.x - 1) / blockDim.x;
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t e0 = blk * blockDim.x;
+    const int64_t cnt = (total - e0 < blockDim.x ? total - e0 : blockDim.x) * P3;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) sm[i] = raw[e0 * P3 + i];
+    __syncthreads();
+    const int64_t e = e0 + threadIdx.x;
+    T lj_out = 0; int64_t r_out = 0; int i_out = -1;
+    if (e < total) {
+      T tl[3 * KMAX];
+#pragma unroll
+      for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) tl[k] = sm[threadIdx.x * P3 + k];
+      const int64_t r = e / c;
+      const int i = (int)(e - r * c);
+      const int j = idx1[i];
+      const T v = Xin[r * d + j];
+      RqsLocal<T, KMAX> L;
+      RqsBin<T> b;
+      rqs_locate_cached<T, KMAX, INV>(tl, K, B, v, L, b);
+      if (bins) bins[e] = b.k;
+      T o = v, lj = 0, tmp;
+      if (b.k >= 1 && b.k <= K) { if (!INV) rqs_eval_fwd(b, v, o, lj); else rqs_eval_inv(b, v, o, lj, tmp); }
+      Xout[r * d + j] = o;
+      run_max = fmaxf(run_max, fabsf((float)o));
+      lj_out = lj; r_out = r; i_out = i;
+    }
+    if (ld) {
+      const bool pow2 = (c & (c - 1)) == 0 && c <= 32 && (blockDim.x % c) == 0;
+      if (pow2) {          // the c coordinates of a sample sit in c adjacent lanes: segmented butterfly, one add per sample
+        for (int o = c >> 1; o > 0; o >>= 1) lj_out += __shfl_xor_sync(0xffffffffu, lj_out, o);
+        if (e < total && i_out == 0) atomicAdd(&ld[r_out], lj_out);
+      } else if (e < total && lj_out != T(0)) {
+        atomicAdd(&ld[r_out], lj_out);
+      }
+    }
+  }
+  if (amax_meta) amax_update(amax_meta, run_max);
 }
 
 // Backward of the spline coupling arithmetic: G (in place on idx1 columns) and graw = d/dtheta_raw.
-// Vsrc = the spline input (Xin): x1 for forward, y1 for inverse.
-template <typename T, bool INV>
+// Vsrc = the spline input (Xin): x1 for forward, y1 for inverse.  Same staging as rqs_apply_kernel, both ways.
+template <typename T, int KMAX, bool INV>
 __global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restrict__ raw,
                                const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int K, T B,
-                               int64_t N, T* __restrict__ graw) {
+                               int64_t N, T* __restrict__ graw, float* __restrict__ amax_meta) {
   using Nm = Num<T>;
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= N * c) return;
-  const int64_t r = e / c;
-  const int i = (int)(e - r * c);
+  extern __shared__ __align__(16) unsigned char rqs_smem[];
+  T* sm = reinterpret_cast<T*>(rqs_smem);
   const int P3 = 3 * K - 1;
-  const T* tw = raw + e * P3;
-  const T* th = tw + K;
-  const T* td = tw + 2 * K;
-  T* gw = graw + e * P3;
-  T* gh = gw + K;
-  T* gd = gw + 2 * K;
-  for (int k = 0; k < P3; ++k) gw[k] = 0;
-  const int j = idx1[i];
-  const T v = Vsrc[r * d + j];
-  const T go = G[r * d + j];
-  const T gl = gld ? gld[r] : T(1);
-  RqsBin<T> b;
-  rqs_locate<T, INV>(tw, th, td, K, B, v, b);
-  if (b.k < 1 || b.k > K) return;   // identity tail: dy/dx = 1, no parameter gradient; G unchanged
-  const T dx = b.x1 - b.x0, dy = b.y1 - b.y0;
-  const T s = dy / dx;
-  T x, xi;
-  if (!INV) { x = v; xi = (x - b.x0) / dx; }
-  else { T lj_; rqs_eval_inv(b, v, x, lj_, xi); }
-  const T om = 1 - xi;
-  const T tt = b.d1 + b.d0 - 2 * s;
-  const T den = s + tt * xi * om;
-  const T num = s * xi * xi + b.d0 * xi * om;
-  const T q = b.d1 * xi * xi + 2 * s * xi * om + b.d0 * om * om;
-  // d(logJ)/d(xi) at fixed parameters
-  const T lj_xi = (2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om) / q - 2 * tt * (om - xi) / den;
-  T gy, glj;       // effective upstream gradients on the FORWARD map y = F(x), logJ(x)
-  T g_in = 0;      // gradient w.r.t. the spline input
-  if (!INV) {
-    gy = go; glj = gl;
-  } else {
-    // x = F^{-1}(y): dx/dy = 1/F_x, dx/dparams = -F_params/F_x, lj_inv = -lj(x(y, p), p)
-    // L = go*x - gl*lj(x,p):  dL/dy = (go - gl*lj_x)/F_x =: a,  dL/dp = -a*F_p - gl*lj_p
-    const T Fx = s * s * q / (den * den);
-    const T a = (go - gl * (lj_xi / dx)) / Fx;
-    gy = -a; glj = -gl; g_in = a;
-  }
-  // accumulate gradients of  gy*y + glj*lj  w.r.t. (x0,x1,y0,y1,d0,d1) and xi
-  T g_y0 = gy, g_dy = gy * num / den;
-  const T g_num = gy * dy / den;
-  T g_den = -gy * dy * num / (den * den) - 2 * glj / den;
-  T g_s = 2 * glj / s;
-  const T g_q = glj / q;
-  T g_d1 = g_q * xi * xi, g_d0 = g_q * om * om;
-  g_s += g_q * 2 * xi * om;
-  T g_xi = g_q * (2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om);
-  g_s += g_num * xi * xi; g_d0 += g_num * xi * om; g_xi += g_num * (2 * s * xi + b.d0 * (om - xi));
-  g_s += g_den * (1 - 2 * xi * om); g_d1 += g_den * xi * om; g_d0 += g_den * xi * om; g_xi += g_den * tt * (om - xi);
-  T g_x0 = -g_xi / dx, g_dx = -g_xi * xi / dx;
-  if (!INV) g_in = g_xi / dx;
-  g_dy += g_s / dx; g_dx += -g_s * s / dx;
-  const T g_y1 = g_dy; g_y0 -= g_dy;
-  const T g_x1 = g_dx; g_x0 -= g_dx;
-  G[r * d + j] = g_in;
-  // knots -> logits: X_j = 2B c_j - B, c_j = sum_{k<=j} p_k, p = softmax(t)
-  const T twoB = 2 * B;
-  {
-    const T a0 = (b.k - 1 >= 1) ? g_x0 : T(0);   // knot 0 is the constant -B
-    const T a1 = g_x1;
-    const T dotp = twoB * (a0 * b.cx0 + a1 * b.cx1);
-    for (int k = 1; k <= K; ++k) {
-      const T p = Nm::exp(tw[k - 1]) / b.Sw;
-      const T gp = twoB * ((k <= b.k - 1 ? a0 : T(0)) + (k <= b.k ? a1 : T(0)));
-      gw[k - 1] = p * (gp - dotp);
+  const int64_t total = N * c;
+  float run_max = 0.f;
+  const int64_t nblk = (total + blockDim.x - 1) / blockDim.x;
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t e0 = blk * blockDim.x;
+    const int64_t cnt = (total - e0 < blockDim.x ? total - e0 : blockDim.x) * P3;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) sm[i] = raw[e0 * P3 + i];
+    __syncthreads();
+    const int64_t e = e0 + threadIdx.x;
+    T tl[3 * KMAX];
+    if (e < total) {
+#pragma unroll
+      for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) tl[k] = sm[threadIdx.x * P3 + k];
+    }
+    __syncthreads();
+    if (e < total) {
+      T* gw = sm + threadIdx.x * P3;      // this thread's output row, written into the staging tile
+#pragma unroll
+      for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) gw[k] = 0;
+      const int64_t r = e / c;
+      const int i = (int)(e - r * c);
+      const int j = idx1[i];
+      const T v = Vsrc[r * d + j];
+      const T go = G[r * d + j];
+      const T gl = gld ? gld[r] : T(1);
+      RqsLocal<T, KMAX> L;
+      RqsBin<T> b;
+      rqs_locate_cached<T, KMAX, INV>(tl, K, B, v, L, b);
+      if (b.k >= 1 && b.k <= K) {   // identity tails: dy/dx = 1, no parameter gradient; G unchanged
+        const T dx = b.x1 - b.x0, dy = b.y1 - b.y0;
+        const T s = dy / dx;
+        T x, xi;
+        if (!INV) { x = v; xi = (x - b.x0) / dx; }
+        else { T lj_; rqs_eval_inv(b, v, x, lj_, xi); }
+        const T om = 1 - xi;
+        const T tt = b.d1 + b.d0 - 2 * s;
+        const T den = s + tt * xi * om;
+        const T num = s * xi * xi + b.d0 * xi * om;
+        const T q = b.d1 * xi * xi + 2 * s * xi * om + b.d0 * om * om;
+        const T lj_xi = (2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om) / q - 2 * tt * (om - xi) / den;
+        T gy, glj, g_in = 0;
+        if (!INV) { gy = go; glj = gl; }
+        else {
+          // L = go*x - gl*lj(x,p):  dL/dy = (go - gl*lj_x)/F_x =: a,  dL/dp = -a*F_p - gl*lj_p
+          const T Fx = s * s * q / (den * den);
+          const T a = (go - gl * (lj_xi / dx)) / Fx;
+          gy = -a; glj = -gl; g_in = a;
+        }
+        T g_y0 = gy, g_dy = gy * num / den;
+        const T g_num = gy * dy / den;
+        T g_den = -gy * dy * num / (den * den) - 2 * glj / den;
+        T g_s = 2 * glj / s;
+        const T g_q = glj / q;
+        T g_d1 = g_q * xi * xi, g_d0 = g_q * om * om;
+        g_s += g_q * 2 * xi * om;
+        T g_xi = g_q * (2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om);
+        g_s += g_num * xi * xi; g_d0 += g_num * xi * om; g_xi += g_num * (2 * s * xi + b.d0 * (om - xi));
+        g_s += g_den * (1 - 2 * xi * om); g_d1 += g_den * xi * om; g_d0 += g_den * xi * om; g_xi += g_den * tt * (om - xi);
+        T g_x0 = -g_xi / dx, g_dx = -g_xi * xi / dx;
+        if (!INV) g_in = g_xi / dx;
+        g_dy += g_s / dx; g_dx += -g_s * s / dx;
+        const T g_y1 = g_dy; g_y0 -= g_dy;
+        const T g_x1 = g_dx; g_x0 -= g_dx;
+        G[r * d + j] = g_in;
+        const T twoB = 2 * B;
+        const T rSw = 1 / L.Sw, rSh = 1 / L.Sh;
+        {   // knots -> width logits: X_j = 2B c_j - B, c_j = sum_{k<=j} p_k, p = softmax
+          const T a0 = (b.k - 1 >= 1) ? g_x0 : T(0), a1 = g_x1;
+          const T dotp = twoB * (a0 * b.cx0 + a1 * b.cx1);
+#pragma unroll
+          for (int k = 1; k <= KMAX; ++k) if (k <= K) {
+            const T p = L.ew[k - 1] * rSw;
+            const T gp = twoB * ((k <= b.k - 1 ? a0 : T(0)) + (k <= b.k ? a1 : T(0)));
+            gw[k - 1] = p * (gp - dotp);
+          }
+        }
+        {   // height logits
+          const T a0 = (b.k - 1 >= 1) ? g_y0 : T(0), a1 = g_y1;
+          const T dotp = twoB * (a0 * b.cy0 + a1 * b.cy1);
+#pragma unroll
+          for (int k = 1; k <= KMAX; ++k) if (k <= K) {
+            const T p = L.eh[k - 1] * rSh;
+            const T gp = twoB * ((k <= b.k - 1 ? a0 : T(0)) + (k <= b.k ? a1 : T(0)));
+            gw[K + k - 1] = p * (gp - dotp);
+          }
+        }
+        if (b.k - 1 >= 1) { const T ex = Nm::exp(tl[2 * K + b.k - 2]); gw[2 * K + b.k - 2] = g_d0 * ex / (ex + 1); }
+        if (b.k <= K - 1) { const T ex = Nm::exp(tl[2 * K + b.k - 1]); gw[2 * K + b.k - 1] = g_d1 * ex / (ex + 1); }
+      }
+    }
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const T gv = sm[i];
+      graw[e0 * P3 + i] = gv;
+      run_max = fmaxf(run_max, fabsf((float)gv));
     }
   }
-  {
-    const T a0 = (b.k - 1 >= 1) ? g_y0 : T(0);
-    const T a1 = g_y1;
-    const T dotp = twoB * (a0 * b.cy0 + a1 * b.cy1);
-    for (int k = 1; k <= K; ++k) {
-      const T p = Nm::exp(th[k - 1]) / b.Sh;
-      const T gp = twoB * ((k <= b.k - 1 ? a0 : T(0)) + (k <= b.k ? a1 : T(0)));
-      gh[k - 1] = p * (gp - dotp);
-    }
-  }
-  if (b.k - 1 >= 1) { const T ex = Nm::exp(td[b.k - 2]); gd[b.k - 2] = g_d0 * ex / (ex + 1); }
-  if (b.k <= K - 1) { const T ex = Nm::exp(td[b.k - 1]); gd[b.k - 1] = g_d1 * ex / (ex + 1); }
+  if (amax_meta) amax_update(amax_meta, run_max);
 }
 
 template <typename T>

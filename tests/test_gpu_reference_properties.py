@@ -73,3 +73,37 @@ def test_interface_train_flow_converges(gpu, T):
     assert seen["cb"] == len(stats) and "sample_per_iter" in stats[0]
     with pytest.raises(TypeError):
         nf.train_flow(nf.elbo, flow, target, 10)     # ADbackend is required, as in the reference
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64], ids=["f32", "f64"])
+def test_two_phase_api_matches_fused_elbo(gpu, T):
+    """nf_forward_stash + caller-side logp/score + nf_backward == the fused ELBO gradient (user-supplied log-density path)."""
+    nf = gpu
+    dim = 6
+    nf.seed(5)
+    flow = nf.realnvp(nf.MvNormal(np.zeros(dim)), [16, 16], 2, T)
+    rng = np.random.Generator(np.random.PCG64(4))
+    mu, sg = rng.standard_normal(dim), rng.uniform(0.5, 1.5, dim)
+    target = nf.DiagNormal(mu, sg)
+    xs = rng.standard_normal((200, dim)).astype(T)
+    v, g = nf.api._elbo_impl(flow, target, xs, want_grad=True)
+    ys, ld = nf.forward_stash(flow, xs)
+    score = (-(ys - mu) / sg ** 2).astype(T)                 # d logp / dy evaluated by the caller
+    g2 = nf.backward(flow, score / len(xs), np.full(len(xs), 1.0 / len(xs), dtype=T))
+    tol = 1e-4 if T == np.float32 else 1e-9
+    assert np.linalg.norm(g2 - g) <= tol * np.linalg.norm(g)
+
+
+def test_device_sampling_statistics(gpu):
+    """_device_specific_rand replacement: Philox base draws ~ N(mu, sigma^2), reproducible per seed."""
+    nf = gpu
+    q0 = nf.MvNormal([1.0, -2.0, 0.5], [0.5, 2.0, 1.0])
+    flow = nf.planarflow(q0, 2, np.float32)
+    z = flow.rand_base(200000, seed=7)
+    assert z.shape == (200000, 3) and z.dtype == np.float32
+    assert np.allclose(z.mean(0), q0.mu, atol=0.02) and np.allclose(z.std(0), q0.sigma, rtol=0.02)
+    assert np.array_equal(z, flow.rand_base(200000, seed=7)) and not np.array_equal(z, flow.rand_base(200000, seed=8))
+    kurt = (((z - z.mean(0)) / z.std(0)) ** 4).mean(0)
+    assert np.allclose(kurt, 3.0, atol=0.1)
+    ys = flow.rand(1000, seed=3)
+    assert ys.shape == (1000, 3) and np.all(np.isfinite(ys))
