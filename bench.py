@@ -65,14 +65,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples that arrived inside [t_begin, t_end] (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t_begin is not None and not (t_begin <= ts <= t_end + 0.25):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -269,18 +272,19 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # started before the warm-up so that nvidia-smi's own start-up is outside the timed region
     for _ in range(args.warmup):
         loss = step_resident()
     lib.nf_launch_count(1)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         loss = step_resident()
     sync_all()
-    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    dt = t1 - t0
     launches = lib.nf_launch_count(0)
     # second pass over the same K steps with a CUDA-event pair around every GEMM launch (per-kernel-class device time
     # for the roofline); kept out of the headline region because the extra event records perturb launch overlap
@@ -292,7 +296,7 @@ def main():
     sync_all()
     dt_prof = time.perf_counter() - t0p
     K.check(lib.nf_profile_enable(h, 0))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
     tmax = torch.tensor([dt], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

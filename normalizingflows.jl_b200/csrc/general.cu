@@ -420,9 +420,20 @@ int run_typed(Flow& f, const GeneralJob& job) {
         NF_REQUIRE(job.tgt, "ELBO needs a target");
         NF_TRY(sweep_forward<T>(f, c, theta, nullptr, 0, N));
         T* terms = job.terms_out ? (T*)job.terms_out + c0 : nullptr;
-        elbo_head_kernel<T><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
-            (const T*)c.X[last], (const T*)c.X[0], (const T*)c.ld, job.tgt->params<T>(), base, (T)f.base_c0, d, n,
-            (T*)c.G, terms, f.d_gsum + f.P);
+        {
+          const size_t sm = (size_t)128 * (d + 1) * sizeof(T);
+          if (sm <= 96 * 1024) {
+            auto kern = elbo_head_tiled_kernel<T>;
+            if (sm > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            kern<<<(unsigned)ceil_div(n, 128), 128, sm, f.stream>>>((const T*)c.X[last], (const T*)c.X[0], (const T*)c.ld,
+                                                                    job.tgt->params<T>(), base, (T)f.base_c0, d, n, (T*)c.G, terms,
+                                                                    f.d_gsum + f.P);
+          } else {
+            elbo_head_kernel<T><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
+                (const T*)c.X[last], (const T*)c.X[0], (const T*)c.ld, job.tgt->params<T>(), base, (T)f.base_c0, d, n,
+                (T*)c.G, terms, f.d_gsum + f.P);
+          }
+        }
         NF_LAUNCH_CHECK();
         if (grad) {
           NF_TRY(alloc_backward_tmps(f, c));

@@ -168,39 +168,53 @@ template <typename T, bool INV>
 __global__ void affine_apply_kernel(const T* __restrict__ Xin, const T* __restrict__ S, const T* __restrict__ Tt,
                                     const int* __restrict__ pos, int c, int d, int64_t N, T* __restrict__ Xout,
                                     T* __restrict__ ld, float* __restrict__ amax_meta) {
+  constexpr int U = 4;                                       // independent elements in flight per thread
   const int64_t total = N * d;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t iters = (total + stride - 1) / stride;      // same trip count for every thread (warp collectives inside)
+  const int64_t iters = (total + stride * U - 1) / (stride * U);   // same trip count for every thread (warp collectives inside)
   const bool small = total < ((int64_t)1 << 31);            // 32-bit index math (64-bit division is ~10x the cost)
   float run_max = 0.f;
   for (int64_t it = 0; it < iters; ++it) {
-    const int64_t e = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = e < total;
-    T y = 0, contrib = 0;
-    int64_t r = 0;
-    int k = -1;
-    if (valid) {
-      int j;
-      if (small) { const unsigned int r32 = (unsigned int)e / (unsigned int)d; r = r32; j = (int)((unsigned int)e - r32 * (unsigned int)d); }
-      else { r = e / d; j = (int)(e - r * d); }
-      const T x = Xin[e];
-      k = pos[j];
-      if (k >= 0) {
-        const T s = S[r * c + k], t = Tt[r * c + k];
-        y = INV ? (x - t) * Num<T>::exp(-s) : Num<T>::exp(s) * x + t;
-        contrib = INV ? -s : s;
-      } else {
-        y = x;
+    int64_t e[U], r[U];
+    int k[U];
+    bool valid[U];
+    T x[U], sv[U], tv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      e[u] = (it * U + u) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      valid[u] = e[u] < total;
+      r[u] = 0; k[u] = -1; x[u] = 0;
+      if (valid[u]) {
+        int j;
+        if (small) { const unsigned int r32 = (unsigned int)e[u] / (unsigned int)d; r[u] = r32; j = (int)((unsigned int)e[u] - r32 * (unsigned int)d); }
+        else { r[u] = e[u] / d; j = (int)(e[u] - r[u] * d); }
+        x[u] = Xin[e[u]];
+        k[u] = pos[j];
       }
-      Xout[e] = y;
-      run_max = fmaxf(run_max, fabsf((float)y));
     }
-    if (ld) {
-      if ((d & 31) == 0) {            // a warp covers 32 consecutive columns of ONE row
-        const T sum = warp_sum(contrib);
-        if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&ld[r], sum);
-      } else if (valid && k >= 0) {
-        atomicAdd(&ld[r], contrib);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      sv[u] = 0; tv[u] = 0;
+      if (k[u] >= 0) { sv[u] = S[r[u] * c + k[u]]; tv[u] = Tt[r[u] * c + k[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T y = x[u], contrib = 0;
+      if (k[u] >= 0) {
+        y = INV ? (x[u] - tv[u]) * Num<T>::exp(-sv[u]) : Num<T>::exp(sv[u]) * x[u] + tv[u];
+        contrib = INV ? -sv[u] : sv[u];
+      }
+      if (valid[u]) {
+        Xout[e[u]] = y;
+        run_max = fmaxf(run_max, fabsf((float)y));
+      }
+      if (ld) {
+        if ((d & 31) == 0) {            // a warp covers 32 consecutive columns of ONE row
+          const T sum = warp_sum(contrib);
+          if ((threadIdx.x & 31) == 0 && valid[u]) atomicAdd(&ld[r[u]], sum);
+        } else if (valid[u] && k[u] >= 0) {
+          atomicAdd(&ld[r[u]], contrib);
+        }
       }
     }
   }
@@ -581,6 +595,51 @@ __global__ void rqs_bin_search_kernel(const T* __restrict__ knots, const T* __re
 // ---------------------------------------------------------------------------------------------
 // objective heads
 // ---------------------------------------------------------------------------------------------
+// ELBO head, coalesced: a CTA stages 128 rows of X0 and then of Y through shared memory (pitch d+1: conflict-free
+// row-per-thread access), evaluates the target in place (z -> dlogp/dz) and streams G back out.
+// Dynamic smem: blockDim.x * (d + 1) * sizeof(T).
+template <typename T>
+__global__ void elbo_head_tiled_kernel(const T* __restrict__ Y, const T* __restrict__ X0, const T* __restrict__ ld,
+                                       TargetParams<T> tp, const T* __restrict__ base, T base_c0, int d, int64_t N,
+                                       T* __restrict__ G, T* __restrict__ terms, double* __restrict__ sum_out) {
+  extern __shared__ __align__(16) unsigned char head_smem[];
+  T* sm = reinterpret_cast<T*>(head_smem);
+  const int nthr = blockDim.x, tid = threadIdx.x, pitch = d + 1;
+  const int64_t r0 = (int64_t)blockIdx.x * nthr;
+  const int nrows = (int)((N - r0) < nthr ? (N - r0) : nthr);
+  const int cnt = nrows * d;
+  for (int i = tid; i < cnt; i += nthr) sm[(i / d) * pitch + (i % d)] = X0[r0 * d + i];
+  __syncthreads();
+  T q = 0;
+  if (tid < nrows)
+    for (int k = 0; k < d; ++k) {
+      const T x = sm[tid * pitch + k];
+      const T u = base ? (x - base[k]) / base[d + k] : x;
+      q += u * u;
+    }
+  __syncthreads();
+  for (int i = tid; i < cnt; i += nthr) sm[(i / d) * pitch + (i % d)] = Y[r0 * d + i];
+  __syncthreads();
+  double term = 0;
+  if (tid < nrows) {
+    const T lp = target_logp_score<T, 0>(tp, sm + tid * pitch, sm + tid * pitch);
+    const T t = lp - (base_c0 - q / 2) + ld[r0 + tid];
+    if (terms) terms[r0 + tid] = t;
+    term = (double)t;
+  }
+  __syncthreads();
+  for (int i = tid; i < cnt; i += nthr) G[r0 * d + i] = sm[(i / d) * pitch + (i % d)];
+  term = warp_sum(term);
+  __shared__ double sh[32];
+  if ((tid & 31) == 0) sh[tid >> 5] = term;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0;
+    for (int w = 0; w < (nthr + 31) / 32; ++w) s += sh[w];
+    atomicAdd(sum_out, s);
+  }
+}
+
 // ELBO head (reference src/objectives/elbo.jl:65-70): term = logp(y) - logq0(x0) + logdet; G = dlogp/dy.
 template <typename T>
 __global__ void elbo_head_kernel(const T* __restrict__ Y, const T* __restrict__ X0, const T* __restrict__ ld,

@@ -195,6 +195,7 @@ struct GemmParams {
   const float* w_sc;       // per-Dense scalars: [0] weight scale, [1] max row L1, [2] max col L1, [3] max |b|
   int bound_dgrad;         // 0: out bound = amax*w_sc[1] + w_sc[3] ; 1: amax*w_sc[2]
   float rz_comp;           // expected relative shortfall of the RZ-accumulating tensor core for this chain length
+  int slab_stages;         // K stages (of 64) accumulated in one TMEM buffer before the epilogue drains it (1 .. num_k_chunks)
   float* out_meta;         // planes outputs: scale is written, amax accumulated
   const float* bias;       // [>= n tile] zero padded (EPI_*_ACT)
   int act;
@@ -313,13 +314,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     // ===== MMA issuer: one K slab (= one smem stage) per TMEM buffer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-      uint32_t it = 0;   // slab counter == stage counter
+      uint32_t it = 0;   // stage counter
+      uint32_t sl = 0;   // slab counter: one TMEM buffer per slab of `slab_stages` K stages
+      const int ss = p.slab_stages;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
-          const uint32_t acc = it & 1, accph = (it >> 1) & 1;
-          mbar_wait(tempty_bar(acc), accph ^ 1);
+          const uint32_t acc = sl & 1, accph = (sl >> 1) & 1;
+          const bool slab_first = (kc % ss) == 0;
+          const bool slab_last = (kc % ss) == ss - 1 || kc == nk - 1;
+          if (slab_first) mbar_wait(tempty_bar(acc), accph ^ 1);
           NF_DBG(1, 3 * it, true);
           mbar_wait(full_bar(s), ph);
           NF_DBG(1, 3 * it + 1, true);
@@ -334,16 +339,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           if (p.terms > 1) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)   // lo * hi
-              umma_f16(d_tmem, adesc0 + ((Cfg::A_PLANE + kk * 32) >> 4), bdesc0 + ((kk * 32) >> 4), idesc, kk > 0 ? 1u : 0u);
+              umma_f16(d_tmem, adesc0 + ((Cfg::A_PLANE + kk * 32) >> 4), bdesc0 + ((kk * 32) >> 4), idesc, (kk > 0 || !slab_first) ? 1u : 0u);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)   // hi * lo
               umma_f16(d_tmem, adesc0 + ((kk * 32) >> 4), bdesc0 + ((Cfg::B_PLANE + kk * 32) >> 4), idesc, 1u);
           }
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)     // hi * hi
-            umma_f16(d_tmem, adesc0 + ((kk * 32) >> 4), bdesc0 + ((kk * 32) >> 4), idesc, (p.terms > 1 || kk > 0) ? 1u : 0u);
+            umma_f16(d_tmem, adesc0 + ((kk * 32) >> 4), bdesc0 + ((kk * 32) >> 4), idesc, (p.terms > 1 || kk > 0 || !slab_first) ? 1u : 0u);
           umma_commit(empty_bar(s));
-          umma_commit(tfull_bar(acc));
+          if (slab_last) { umma_commit(tfull_bar(acc)); ++sl; }
           NF_DBG(1, 3 * it + 2, true);
         }
       }
@@ -373,7 +378,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       const int64_t row = tile * 128 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const int ncols_here = p.n_store - (n0 + cbase);   // columns of this thread's range that matter (warp-uniform)
-      for (int kc = 0; kc < nk; ++kc, ++it) {
+      const int nslabs = (nk + p.slab_stages - 1) / p.slab_stages;
+      for (int kc = 0; kc < nslabs; ++kc, ++it) {
         const uint32_t acc = it & 1, accph = (it >> 1) & 1;
         mbar_wait_relaxed(tfull_bar(acc), accph);
         NF_DBG(2, 3 * it, threadIdx.x == 64);
@@ -821,16 +827,31 @@ constexpr int kMetaSlots = 8192;
 // Expected relative shortfall of one K slab accumulated by the RZ-rounding tensor core: n_main = average
 // number of hi*hi MMAs per slab that carry data.  Calibrated on B200 with tests/debug_gemm.py
 // (4 main MMAs: -9.0e-8, 2 main MMAs: -5.3e-8); about one fp32 ulp, applied to the de-scaling factor.
-float rz_compensation(int k_valid, int n_slabs) {
-  static float c0 = -1.f, c1 = -1.f;
+// slab_stages > 1: later stages of a slab add their correction products onto an already large accumulator, so all
+// 12 MMAs of those stages truncate (c2 per MMA).
+float rz_compensation(int k_valid, int n_stages, int slab_stages) {
+  static float c0 = -1.f, c1 = -1.f, c2 = -1.f;
   if (c0 < 0.f) {
     const char* e0 = getenv("NFCUDA_RZ_C0");
     const char* e1 = getenv("NFCUDA_RZ_C1");
+    const char* e2 = getenv("NFCUDA_RZ_C2");
     c0 = e0 ? (float)atof(e0) : 2.0e-8f;
     c1 = e1 ? (float)atof(e1) : 1.75e-8f;
+    c2 = e2 ? (float)atof(e2) : 1.6e-8f;
   }
-  const float n_main = (float)((k_valid + 15) / 16) / (float)(n_slabs > 0 ? n_slabs : 1);
-  return c0 + c1 * n_main;
+  const float n_main = (float)((k_valid + 15) / 16) / (float)(n_stages > 0 ? n_stages : 1);   // data-carrying hi*hi MMAs per stage
+  const int ss = slab_stages < n_stages ? slab_stages : n_stages;
+  return c0 + c1 * n_main + c2 * 3.f * n_main * (float)(ss - 1);
+}
+// K stages per TMEM accumulation chain.  Forward GEMMs feed the ELBO value (1e-5 budget): one stage per chain.
+// Backward (dgrad) GEMMs only feed the gradient (1e-4 budget): the whole K in one chain, which lets the next
+// tile's MMAs overlap this tile's epilogue (tile-level TMEM double buffering).
+int slab_stages_for(bool backward, int n_stages) {
+  const char* e = getenv(backward ? "NFCUDA_SLAB_BWD" : "NFCUDA_SLAB_FWD");
+  int ss = e ? atoi(e) : (backward ? n_stages : 1);
+  if (ss < 1) ss = 1;
+  if (ss > n_stages) ss = n_stages;
+  return ss;
 }
 
 struct TcState {
@@ -1156,7 +1177,8 @@ int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, s
     NF_REQUIRE(p.a_meta, "tcgen05 path: missing tensor metadata (forward input)");
     p.w_sc = st->d_scalars + 4 * pi;
     p.bound_dgrad = 0;
-    p.rz_comp = rz_compensation(dp.kin, p.num_k_chunks);
+    p.slab_stages = slab_stages_for(false, p.num_k_chunks);
+    p.rz_comp = rz_compensation(dp.kin, p.num_k_chunks, p.slab_stages);
     p.bias = st->bias_pool + dp.bias_off;
     CUtensorMap mo = ma;
     if (!last) {
@@ -1226,7 +1248,8 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
       GemmParams p{};
       p.M = n; p.num_k_chunks = dp.nout_p / 64; p.terms = terms;
       p.a_meta = g_meta; p.w_sc = st->d_scalars + 4 * pi; p.bound_dgrad = 1;
-      p.rz_comp = rz_compensation(dp.nout, p.num_k_chunks);
+      p.slab_stages = slab_stages_for(true, p.num_k_chunks);
+      p.rz_comp = rz_compensation(dp.nout, p.num_k_chunks, p.slab_stages);
       CUtensorMap mo = ma;
       if (i > 0) {
         Planes O = planes_of(gnext, n, dp.kin);
