@@ -155,6 +155,17 @@ NF_API int nf_loglik_value_and_grad(nf_flow_t flow, const void* theta_host, int6
 NF_API int nf_loglik_value_and_grad_dev(nf_flow_t flow, const void* theta_dev, int64_t N, const void* xs_dev,
                                  double scale, double* value_out, void* grad_dev_out);
 
+/* On-device optimiser loop: `n_iters` iterations of
+ *     ls, g = value_and_gradient(-elbo) ; theta <- Optimisers.Adam(eta, (beta1, beta2), eps) step
+ * i.e. the body of the reference's `while` loop (src/optimize.jl:85-105) without its per-iteration host round trip;
+ * valid when no callback / hasconverged needs theta on the host every iteration.  Base draws come from the device
+ * Philox stream with seed + i for iteration i.  theta (and optionally the Adam moments m, v, for continuing a run that
+ * already made t0 steps) are read from and written back to the host buffers once.  stats_out[i] = {loss_i, gradient_norm_i}
+ * (the reference's opt_stats fields, src/optimize.jl:89). */
+NF_API int nf_train_elbo_adam(nf_flow_t flow, nf_target_t target, void* theta_host_inout, int64_t N, uint64_t seed, int n_iters,
+                              int t0, double eta, double beta1, double beta2, double eps, void* m_host_inout, void* v_host_inout,
+                              double* stats_out);
+
 /* ---- transform / density API ------------------------------------------------------------------ */
 /* with_logabsdet_jacobian(flow.transform, xs): y_out N x dim, logdet_out N (either may be NULL).
  * (reference src/flows/realnvp.jl:77-83, src/flows/neuralspline.jl:102-108; Bijectors planar/radial) */

@@ -48,6 +48,7 @@ SIGNATURES = {
     "nf_elbo_terms": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "nf_loglik_value_and_grad": (_i, [_vp, _vp, _i64, _vp, _d, C.POINTER(_d), _vp]),
     "nf_loglik_value_and_grad_dev": (_i, [_vp, _vp, _i64, _vp, _d, C.POINTER(_d), _vp]),
+    "nf_train_elbo_adam": (_i, [_vp, _vp, _vp, _i64, _u64, _i, _i, _d, _d, _d, _d, _vp, _vp, C.POINTER(_d)]),
     "nf_forward": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "nf_inverse": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "nf_logpdf": (_i, [_vp, _vp, _i64, _vp, _vp]),

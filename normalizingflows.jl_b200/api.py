@@ -420,7 +420,7 @@ def destructure(flow: Flow):
 # ------------------------------------------------------------------------------------------------
 # objectives (reference src/objectives/elbo.jl, loglikelihood.jl)
 # ------------------------------------------------------------------------------------------------
-def _elbo_impl(flow: Flow, logp: _Target, xs_or_n, rng=None, want_grad=False, scale=1.0):
+def _elbo_impl(flow: Flow, logp: _Target, xs_or_n, rng=None, want_grad=False, scale=1.0, seed=None):
     if not isinstance(logp, _Target):
         raise TypeError("logp must be a device target (Banana, Funnel, WarpedGauss, Cross, DiagNormal); "
                         "use forward_stash/backward for a user-supplied density")
@@ -428,7 +428,7 @@ def _elbo_impl(flow: Flow, logp: _Target, xs_or_n, rng=None, want_grad=False, sc
     grad = np.empty(flow.theta.size, dtype=flow.paramtype) if want_grad else None
     if isinstance(xs_or_n, (int, np.integer)):
         n = int(xs_or_n)
-        sd = int(rng.integers(0, 2 ** 63)) if rng is not None else int(_RNG.integers(0, 2 ** 63))
+        sd = seed if seed is not None else (int(rng.integers(0, 2 ** 63)) if rng is not None else int(_RNG.integers(0, 2 ** 63)))
         K.check(K.lib().nf_elbo_value_and_grad(flow.handle(), logp.handle(), K.ptr(flow.theta), n, None, sd, scale,
                                                C.byref(val), K.ptr(grad)))
     else:
@@ -475,10 +475,17 @@ def loglikelihood(*args):
 # AD seam + optimisation loop (reference src/optimize.jl)
 # ------------------------------------------------------------------------------------------------
 class AutoNFCUDA:
-    """The ADTypes-style backend tag a Julia user would pass as `ADbackend`."""
+    """The ADTypes-style backend tag a Julia user would pass as `ADbackend`.
+
+    `on_device=True` additionally keeps the optimiser step on the GPU (`nf_train_elbo_adam`): used by `optimize` when the
+    objective is elbo/elbo_batch with a sample count, the optimiser is Adam and there is neither a callback nor a
+    convergence test that needs theta on the host every iteration."""
+
+    def __init__(self, on_device: bool = False, chunk: int = 100):
+        self.on_device, self.chunk = on_device, chunk
 
     def __repr__(self):
-        return "AutoNFCUDA()"
+        return "AutoNFCUDA(on_device=%r)" % self.on_device
 
 
 @dataclass
@@ -546,6 +553,10 @@ def optimize(adbackend, loss, theta0, reconstruct, *args, max_iters=10000, optim
              callback=None, hasconverged=None, prog=None):
     """optimize(ad, loss, theta0, re, args...; ...) -- reference src/optimize.jl:57-108."""
     optimiser = optimiser or Adam()
+    if (getattr(adbackend, "on_device", False) and callback is None and hasconverged is None and isinstance(optimiser, Adam)
+            and isinstance(loss, _Loss) and loss.vo in (elbo, elbo_batch) and len(args) == 3 and isinstance(args[2], (int, np.integer))):
+        return _optimize_on_device(adbackend, loss, theta0, reconstruct, *args, max_iters=max_iters, optimiser=optimiser,
+                                   show_progress=show_progress)
     hasconverged = hasconverged or (lambda i, stats, re, theta, st: False)
     opt_stats = []
     theta = np.array(theta0, copy=True)
@@ -568,6 +579,32 @@ def optimize(adbackend, loss, theta0, reconstruct, *args, max_iters=10000, optim
         if show_progress and (i % 100 == 0 or converged or i > max_iters):
             print("Training %d/%d  loss=%.6g  |g|=%.4g  (%.1f it/s)" % (i - 1, max_iters, ls, stat["gradient_norm"],
                                                                       (i - 1) / max(time.time() - t0, 1e-9)))
+    return theta, opt_stats, st
+
+
+def _optimize_on_device(adbackend, loss, theta0, reconstruct, rng, logp, n, max_iters, optimiser, show_progress):
+    """The same loop with the Adam step fused on the device; theta visits the host once per `chunk` iterations."""
+    flow = loss.re(theta0)
+    dt = flow.paramtype
+    theta = np.array(theta0, dtype=dt, copy=True)
+    m = np.zeros_like(theta); v = np.zeros_like(theta)
+    opt_stats, done = [], 0
+    t_start = time.time()
+    while done < max_iters:
+        k = min(adbackend.chunk, max_iters - done)
+        stats = np.empty((k, 2), dtype=np.float64)
+        seed = int(rng.integers(0, 2 ** 62))
+        K.check(K.lib().nf_train_elbo_adam(flow.handle(), logp.handle(), K.ptr(theta), int(n), seed, k, done, float(optimiser.eta),
+                                           float(optimiser.beta[0]), float(optimiser.beta[1]), float(optimiser.epsilon),
+                                           K.ptr(m), K.ptr(v), stats.ctypes.data_as(C.POINTER(C.c_double))))
+        for i in range(k):
+            opt_stats.append({"iteration": done + i + 1, "loss": dt(stats[i, 0]), "gradient_norm": float(stats[i, 1])})
+        done += k
+        if show_progress:
+            print("Training %d/%d  loss=%.6g  |g|=%.4g  (%.1f it/s, on-device Adam)" % (done, max_iters, stats[-1, 0], stats[-1, 1],
+                                                                                       done / max(time.time() - t_start, 1e-9)))
+    b1, b2 = optimiser.beta
+    st = {"m": m, "v": v, "bt": (b1 ** (done + 1), b2 ** (done + 1))}
     return theta, opt_stats, st
 
 

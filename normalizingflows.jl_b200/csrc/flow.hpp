@@ -114,6 +114,9 @@ struct Flow {
   void* d_theta = nullptr;             // dtype[P]
   double* d_gsum = nullptr;            // double[P+1] un-normalised gradient sums + ELBO sum
   void* d_out = nullptr;               // dtype[P+1] scaled outputs
+  void* d_adam = nullptr;              // dtype[2P]: Adam first / second moments (on-device optimiser loop)
+  double* d_stats = nullptr;           // [iters][2]: loss, |g|^2
+  int stats_cap = 0;
   void* h_pinned = nullptr;            // pinned staging (P+1 of dtype + 1 double)
   size_t h_pinned_bytes = 0;
 

@@ -44,6 +44,27 @@ __global__ void scale_out_kernel(const double* __restrict__ gsum, int64_t n, dou
   if (i < n) out[i] = (T)(gsum[i] * factor);
 }
 
+// Optimisers.Adam step on the device (reference src/optimize.jl:99), in the flow's element type:
+//   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; theta <- theta - eta * (m / (1-b1^t)) / (sqrt(v / (1-b2^t)) + eps)
+// g = -gsum/N is the gradient of the loss -vo.  Also records (loss, |g|^2) of this iteration.
+template <typename T>
+__global__ void adam_step_kernel(const double* __restrict__ gsum, int64_t P, double inv_n, T b1, T b2, T omb1t, T omb2t, T eta,
+                                 T eps, T* __restrict__ theta, T* __restrict__ m, T* __restrict__ v, double* __restrict__ stat) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double g2 = 0;
+  if (i < P) {
+    const T g = (T)(-gsum[i] * inv_n);
+    const T mi = b1 * m[i] + (T(1) - b1) * g;
+    const T vi = b2 * v[i] + (T(1) - b2) * g * g;
+    m[i] = mi; v[i] = vi;
+    theta[i] -= mi / omb1t / (Num<T>::sqrt(vi / omb2t) + eps) * eta;
+    g2 = (double)g * (double)g;
+  }
+  g2 = warp_sum(g2);
+  if ((threadIdx.x & 31) == 0 && g2 != 0) atomicAdd(&stat[1], g2);
+  if (i == 0) stat[0] = -gsum[P] * inv_n;
+}
+
 static int check_device() {
   int dev = 0;
   NF_CUDA(cudaGetDevice(&dev));
@@ -194,6 +215,7 @@ static void flow_destroy(Flow* f) {
   for (auto& L : f->layers) { cudaFree(L.d_idx1); cudaFree(L.d_idx2); cudaFree(L.d_pos); }
   cudaFree(f->d_base); cudaFree(f->d_ew_meta); cudaFree(f->d_ew_kinds);
   cudaFree(f->d_theta); cudaFree(f->d_gsum); cudaFree(f->d_out); cudaFreeHost(f->h_pinned);
+  cudaFree(f->d_adam); cudaFree(f->d_stats);
   cudaFree(f->ws.base);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
@@ -525,6 +547,70 @@ int nf_loglik_value_and_grad_dev(nf_flow_t flow, const void* theta_dev, int64_t 
   f.ws_reset();
   NF_TRY(general_plan_workspace(f, OP_LOGLIK, N, 0));
   return value_and_grad_dev(f, OP_LOGLIK, nullptr, theta_dev, N, xs_dev, 0, scale, value_out, grad_dev_out);
+}
+
+int nf_train_elbo_adam(nf_flow_t flow, nf_target_t target, void* theta_host_inout, int64_t N, uint64_t seed, int n_iters,
+                       int t0, double eta, double beta1, double beta2, double eps, void* m_host_inout, void* v_host_inout,
+                       double* stats_out) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  const Target* t = reinterpret_cast<Target*>(target);
+  NF_TRY(check_target(f, t));
+  NF_REQUIRE(theta_host_inout && stats_out && n_iters > 0 && N > 0 && t0 >= 0, "bad argument");
+  NF_CUDA(cudaSetDevice(f.device));
+  const size_t es = f.esize();
+  const int64_t P = f.P;
+  if (!f.d_adam) {
+    NF_CUDA(cudaMalloc(&f.d_adam, 2 * P * es));
+  }
+  if (f.stats_cap < n_iters) {
+    if (f.d_stats) cudaFree(f.d_stats);
+    NF_CUDA(cudaMalloc((void**)&f.d_stats, (size_t)n_iters * 2 * sizeof(double)));
+    f.stats_cap = n_iters;
+  }
+  char* dm = (char*)f.d_adam;
+  char* dv = dm + P * es;
+  NF_CUDA(cudaMemcpyAsync(f.d_theta, theta_host_inout, P * es, cudaMemcpyHostToDevice, f.stream));
+  if (m_host_inout && v_host_inout && t0 > 0) {
+    NF_CUDA(cudaMemcpyAsync(dm, m_host_inout, P * es, cudaMemcpyHostToDevice, f.stream));
+    NF_CUDA(cudaMemcpyAsync(dv, v_host_inout, P * es, cudaMemcpyHostToDevice, f.stream));
+  } else {
+    NF_CUDA(cudaMemsetAsync(dm, 0, 2 * P * es, f.stream));
+  }
+  NF_CUDA(cudaMemsetAsync(f.d_stats, 0, (size_t)n_iters * 2 * sizeof(double), f.stream));
+  NF_CUDA(cudaEventRecord(f.ev0, f.stream));
+  for (int it = 0; it < n_iters; ++it) {
+    f.ws_reset();
+    NF_TRY(general_plan_workspace(f, OP_ELBO, N, 0));
+    Job j;
+    j.op = OP_ELBO; j.tgt = t; j.theta_dev = f.d_theta; j.in_dev = nullptr; j.N = N; j.seed = seed + (uint64_t)it; j.want_grad = true;
+    NF_TRY(run_job(f, j));
+    const int step = t0 + it + 1;
+    const double omb1t = 1.0 - std::pow(beta1, step), omb2t = 1.0 - std::pow(beta2, step);
+    const int threads = 256;
+    const int blocks = (int)ceil_div(P, threads);
+    if (f.dtype == NF_F32)
+      adam_step_kernel<float><<<blocks, threads, 0, f.stream>>>(f.d_gsum, P, 1.0 / (double)N, (float)beta1, (float)beta2, (float)omb1t,
+                                                               (float)omb2t, (float)eta, (float)eps, (float*)f.d_theta, (float*)dm,
+                                                               (float*)dv, f.d_stats + 2 * it);
+    else
+      adam_step_kernel<double><<<blocks, threads, 0, f.stream>>>(f.d_gsum, P, 1.0 / (double)N, beta1, beta2, omb1t, omb2t, eta, eps,
+                                                                (double*)f.d_theta, (double*)dm, (double*)dv, f.d_stats + 2 * it);
+    NF_LAUNCH_CHECK();
+  }
+  NF_CUDA(cudaEventRecord(f.ev1, f.stream));
+  NF_CUDA(cudaMemcpyAsync(theta_host_inout, f.d_theta, P * es, cudaMemcpyDeviceToHost, f.stream));
+  if (m_host_inout && v_host_inout) {
+    NF_CUDA(cudaMemcpyAsync(m_host_inout, dm, P * es, cudaMemcpyDeviceToHost, f.stream));
+    NF_CUDA(cudaMemcpyAsync(v_host_inout, dv, P * es, cudaMemcpyDeviceToHost, f.stream));
+  }
+  NF_CUDA(cudaMemcpyAsync(stats_out, f.d_stats, (size_t)n_iters * 2 * sizeof(double), cudaMemcpyDeviceToHost, f.stream));
+  NF_CUDA(cudaStreamSynchronize(f.stream));
+  for (int it = 0; it < n_iters; ++it) stats_out[2 * it + 1] = std::sqrt(stats_out[2 * it + 1]);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, f.ev0, f.ev1);
+  f.last_ms = ms;
+  return NF_OK;
 }
 
 int nf_forward(nf_flow_t flow, const void* theta_host, int64_t N, const void* x_host, void* y_host_out, void* logdet_host_out) {

@@ -107,3 +107,51 @@ def test_device_sampling_statistics(gpu):
     assert np.allclose(kurt, 3.0, atol=0.1)
     ys = flow.rand(1000, seed=3)
     assert ys.shape == (1000, 3) and np.all(np.isfinite(ys))
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64], ids=["f32", "f64"])
+def test_on_device_adam_matches_host_loop(gpu, T):
+    """nf_train_elbo_adam == the reference loop body (value_and_gradient + Optimisers.Adam update) run from the host
+    with the same per-iteration Philox seeds."""
+    import ctypes as C
+    nf = gpu
+    K = nf._capi
+    nf.seed(11)
+    flow = nf.planarflow(nf.MvNormal(np.zeros(2)), 5, T)
+    target = nf.Banana(2, 1.0, 10.0)
+    n, iters, seed0 = 256, 25, 1234
+    # host loop
+    theta = flow.theta.copy()
+    opt = nf.Adam(1e-2)
+    st = opt.setup(theta)
+    _, re = nf.destructure(flow)
+    losses = []
+    for i in range(iters):
+        ls, g = nf.api._elbo_impl(re(theta), target, n, want_grad=True, scale=-1.0, seed=seed0 + i)
+        losses.append(ls)
+        st, theta = opt.update(st, theta, g)
+    # device loop
+    theta_d = flow.theta.copy()
+    m = np.zeros_like(theta_d); v = np.zeros_like(theta_d)
+    stats = np.empty((iters, 2))
+    K.check(K.lib().nf_train_elbo_adam(flow.handle(), target.handle(), K.ptr(theta_d), n, seed0, iters, 0, 1e-2, 0.9, 0.999, 1e-8,
+                                       K.ptr(m), K.ptr(v), stats.ctypes.data_as(C.POINTER(C.c_double))))
+    tol = 2e-4 if T == np.float32 else 1e-9
+    assert np.allclose(theta_d, theta, rtol=tol, atol=tol)
+    assert np.allclose(stats[:, 0], np.array(losses, dtype=np.float64), rtol=tol, atol=tol)
+    assert np.allclose(m, st["m"], rtol=10 * tol, atol=tol)
+
+
+def test_train_flow_on_device_converges(gpu):
+    """reference test/interface.jl convergence criterion with the optimiser step kept on the GPU."""
+    nf = gpu
+    mu = 10 * np.ones(2)
+    target = nf.DiagNormal(mu, 2 * np.ones(2))
+    flow = nf.transformed(nf.MvNormal(np.zeros(2), np.ones(2)), nf.Shift(np.zeros(2)) @ nf.Scale(np.ones(2)), np.float32)
+    rng = np.random.Generator(np.random.PCG64(0))
+    flow_trained, stats, st = nf.train_flow(rng, nf.elbo, flow, target, 10, max_iters=3000, optimiser=nf.Adam(0.01),
+                                            ADbackend=nf.AutoNFCUDA(on_device=True, chunk=500), show_progress=False)
+    theta, _ = nf.destructure(flow_trained)
+    assert len(stats) == 3000 and stats[0]["iteration"] == 1 and "gradient_norm" in stats[-1]
+    assert np.all(np.abs(theta[:2] - mu) < 0.2) and np.all(np.abs(theta[2:] - 2) < 0.2)
+    assert stats[-1]["loss"] < stats[0]["loss"]
