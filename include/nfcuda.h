@@ -68,7 +68,10 @@ typedef enum nf_layer_kind {
   NF_AFFINE_COUPLING = 3,   /* theta: s-chain, t-chain; chain = W1(:),b1,W2(:),b2,...  (W out x in, column major) */
   NF_SPLINE_COUPLING = 4,   /* theta: nn-chain with (3K-1)*n_mask outputs */
   NF_SHIFT           = 5,   /* theta: a(d) */
-  NF_SCALE           = 6    /* theta: a(d) */
+  NF_SCALE           = 6,   /* theta: a(d) */
+  /* Hamiltonian flow on z = [x, rho], dim = 2h (reference example/demo_hamiltonian_flow.jl): */
+  NF_MOMENTUM_AFFINE = 7,   /* Stacked((identity, Shift(b) ∘ Scale(a)), [1:h, h+1:2h]) (:94-99); theta: b(h), a(h) */
+  NF_LEAPFROG        = 8    /* LeapFrog bijector (:27-91), logdet 0; theta: log_eps(h) (`@functor LeapFrog (logϵ,)` :39) */
 } nf_layer_kind;
 
 typedef struct nf_layer_desc {
@@ -79,6 +82,9 @@ typedef struct nf_layer_desc {
   int        n_hidden;
   int        K;          /* spline: number of bins   (reference src/flows/neuralspline.jl:37) */
   double     B;          /* spline: domain half-width (reference src/flows/neuralspline.jl:39) */
+  int        n_steps;    /* leapfrog: number of leapfrog steps L (demo_hamiltonian_flow.jl:30) */
+  const void* score_target; /* leapfrog: nf_target_t over the h position coordinates whose score drives the dynamics
+                              (`∇logp`, :31); Banana, Funnel or DiagNormal; copied at nf_flow_create */
 } nf_layer_desc;
 
 /* Built-in target log-densities with device-side logp and score (reference example/targets/*.jl). */
@@ -124,6 +130,9 @@ NF_API int64_t nf_flow_param_offset(nf_flow_t flow, int layer);
 
 /* ---- targets --------------------------------------------------------------------------------- */
 NF_API int  nf_target_create(nf_target_t* out, int kind, int dim, const double* params, int n_params);
+/* logp_joint(z) = logp(x) + sum(logpdf(Normal(), rho)) on z = [x, rho] (reference example/demo_hamiltonian_flow.jl:117-124);
+ * dimension 2 * dim(inner).  `inner` is copied. */
+NF_API int  nf_target_create_joint(nf_target_t* out, nf_target_t inner);
 NF_API void nf_target_destroy(nf_target_t target);
 
 /* ---- objectives: value and gradient ---------------------------------------------------------- */

@@ -11,13 +11,15 @@ LIB_PATH = os.path.join(_HERE, "libnfcuda.so")
 
 NF_F32, NF_F64 = 0, 1
 NF_PLANAR, NF_RADIAL, NF_AFFINE_COUPLING, NF_SPLINE_COUPLING, NF_SHIFT, NF_SCALE = 1, 2, 3, 4, 5, 6
+NF_MOMENTUM_AFFINE, NF_LEAPFROG = 7, 8
 NF_TARGET_BANANA, NF_TARGET_FUNNEL, NF_TARGET_WARPED_GAUSS, NF_TARGET_CROSS, NF_TARGET_DIAG_NORMAL = 1, 2, 3, 4, 5
 NF_MMA_SIMT, NF_MMA_F16X3, NF_MMA_F16X1 = 0, 1, 2
 
 
 class LayerDesc(C.Structure):
     _fields_ = [("kind", C.c_int), ("mask_idx", C.POINTER(C.c_int)), ("n_mask", C.c_int),
-                ("hdims", C.POINTER(C.c_int)), ("n_hidden", C.c_int), ("K", C.c_int), ("B", C.c_double)]
+                ("hdims", C.POINTER(C.c_int)), ("n_hidden", C.c_int), ("K", C.c_int), ("B", C.c_double),
+                ("n_steps", C.c_int), ("score_target", C.c_void_p)]
 
 
 class NFCudaError(RuntimeError):
@@ -41,6 +43,7 @@ SIGNATURES = {
     "nf_flow_set_workspace_limit": (_i, [_vp, _sz]),
     "nf_flow_param_offset": (_i64, [_vp, _i]),
     "nf_target_create": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(_d), _i]),
+    "nf_target_create_joint": (_i, [C.POINTER(_vp), _vp]),
     "nf_target_destroy": (None, [_vp]),
     "nf_elbo_value_and_grad": (_i, [_vp, _vp, _vp, _i64, _vp, _u64, _d, C.POINTER(_d), _vp]),
     "nf_elbo_value_and_grad_dev": (_i, [_vp, _vp, _vp, _i64, _vp, _u64, _d, C.POINTER(_d), _vp]),

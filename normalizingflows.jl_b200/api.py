@@ -151,6 +151,21 @@ class DiagNormal(_Target):
         return np.concatenate([self.mu, self.sigma])
 
 
+class JointTarget(_Target):
+    """logp_joint(z) = logp(x) + sum(logpdf(Normal(), rho)) on z = [x, rho]
+    (reference example/demo_hamiltonian_flow.jl:117-124)."""
+
+    def __init__(self, inner: _Target):
+        self.inner, self.dim = inner, 2 * inner.dim
+
+    def handle(self):
+        if getattr(self, "_h", None) is None:
+            h = C.c_void_p()
+            K.check(K.lib().nf_target_create_joint(C.byref(h), self.inner.handle()))
+            self._h = h
+        return self._h
+
+
 # ------------------------------------------------------------------------------------------------
 # layers (structure + initial parameters; all arithmetic lives in the CUDA library)
 # ------------------------------------------------------------------------------------------------
@@ -172,6 +187,8 @@ class _Layer:
     hdims: Optional[List[int]] = None
     K: int = 0
     B: float = 0.0
+    n_steps: int = 0
+    score_target: Optional[object] = None
 
     def __matmul__(self, other):            # l1 @ l2  ==  l1 ∘ l2
         return Composed(_flatten(self) + _flatten(other))
@@ -212,6 +229,27 @@ def Shift(a) -> _Layer:
 def Scale(a) -> _Layer:
     a = np.asarray(a, dtype=np.float64).reshape(-1)
     return _Layer(K.NF_SCALE, a.size, a.copy())
+
+
+def MomentumAffine(shift, scale) -> _Layer:
+    """`Stacked((identity, Shift(b) ∘ Scale(a)), [1:h, h+1:2h])`: the momentum normalisation layer of
+    reference example/demo_hamiltonian_flow.jl:94-99 on z = [x, rho]; theta = [b; a]."""
+    b = np.asarray(shift, dtype=np.float64).reshape(-1)
+    a = np.asarray(scale, dtype=np.float64).reshape(-1)
+    if a.shape != b.shape:
+        raise ValueError("shift and scale must have the same length")
+    return _Layer(K.NF_MOMENTUM_AFFINE, 2 * a.size, np.concatenate([b, a]))
+
+
+def LeapFrog(dim: int, log_eps, L: int, target) -> _Layer:
+    """LeapFrog(dim, logϵ, L, ∇logp) -- reference example/demo_hamiltonian_flow.jl:27-47: `dim` position coordinates,
+    per-dimension log step sizes (trainable), L leapfrog steps, the score of `target` (a device target) inside."""
+    le = np.asarray(log_eps, dtype=np.float64).reshape(-1)
+    if le.size == 1:
+        le = np.full(dim, float(le[0]))
+    if le.size != dim or target.dim != dim:
+        raise ValueError("log_eps and target must have dimension %d" % dim)
+    return _Layer(K.NF_LEAPFROG, 2 * dim, le.copy(), n_steps=int(L), score_target=target)
 
 
 def _fnn_theta(n_in: int, hdims: Sequence[int], n_out: int) -> np.ndarray:
@@ -297,6 +335,10 @@ class Flow:
                     descs[i].hdims = h; descs[i].n_hidden = len(l.hdims)
                 descs[i].K = l.K
                 descs[i].B = l.B
+                descs[i].n_steps = l.n_steps
+                if l.score_target is not None:
+                    descs[i].score_target = l.score_target.handle()
+                    keep.append(l.score_target)
             h = C.c_void_p()
             K.check(K.lib().nf_flow_create(C.byref(h), descs, n, self.dim, _dt(self.paramtype)))
             self._h = h
@@ -399,6 +441,20 @@ def realnvp(q0: MvNormal, hdims: Sequence[int] = (32, 32), nlayers: int = 10, pa
 def nsf(q0: MvNormal, hdims: Sequence[int] = (32, 32), K_: int = 10, B: float = 30.0, nlayers: int = 10, paramtype=Float64) -> Flow:
     """nsf(q0, hdims, K, B, nlayers; paramtype) -- reference src/flows/neuralspline.jl:218-234."""
     return create_flow([NSF_layer(len(q0), hdims, K_, B, paramtype) for _ in range(nlayers)], q0, paramtype)
+
+
+def hamiltonian_flow(target, nlayers: int = 15, L: int = 3, log_eps0: float = math.log(0.05), paramtype=Float64) -> Flow:
+    """The Hamiltonian flow of reference example/demo_hamiltonian_flow.jl:128-147 for a device target over `dims`
+    coordinates: q0 = transformed(MvNormal(0, I_2dims), Shift(0) ∘ Scale(1)) and
+    Ls = [momentum_normalization_layer ∘ LeapFrog(dims, log ϵ0, L, ∇logp) for _ in 1:nlayers].  Train it against
+    `JointTarget(target)`.  theta order (Optimisers.destructure of `transformed(q0, ∘(Ls...))`): per layer
+    [b; a; logϵ], then q0's shift, scale -- which are applied first (App. A.5)."""
+    h = target.dim
+    layers: List[_Layer] = []
+    for _ in range(nlayers):
+        layers += _flatten(MomentumAffine(np.zeros(h), np.ones(h)) @ LeapFrog(h, log_eps0, L, target))
+    layers += _flatten(Shift(np.zeros(2 * h)) @ Scale(np.ones(2 * h)))
+    return Flow(layers, MvNormal(np.zeros(2 * h)), paramtype)
 
 
 def destructure(flow: Flow):

@@ -22,6 +22,8 @@ namespace nf {
 //   radial: c0 = alpha, c1 = beta_hat ; v0 = z0
 //   shift : v0 = a
 //   scale : c0 = sum log|a| ; v0 = a, v1 = 1/a
+//   momentum affine (z = [x, rho], h = DP/2): c0 = sum log|a| ; v0 = [0.., b], v1 = [1.., a]
+//   leapfrog: c0 = number of steps ; v0[0:h] = eps = exp(log_eps)
 template <int DP> constexpr int ew_stride() { return 4 + 2 * DP; }
 template <int DP> constexpr int ew_nacc() { return 2 * DP + 2; }
 
@@ -64,7 +66,88 @@ __global__ void ew_prep_kernel(const T* __restrict__ theta, const EwLayerMeta* _
       e[0] = sl;
       break;
     }
+    case NF_MOMENTUM_AFFINE: {  // theta: b(h), a(h); d == DP == 2h
+      const int h = d / 2;
+      T sl = 0;
+      for (int k = 0; k < DP; ++k) { v0[k] = 0; v1[k] = 1; }
+      for (int k = 0; k < h; ++k) { v0[h + k] = p[k]; v1[h + k] = p[h + k]; sl += N::log(N::abs(p[h + k])); }
+      e[0] = sl;
+      break;
+    }
+    case NF_LEAPFROG: {  // theta: log_eps(h)
+      const int h = d / 2;
+      for (int k = 0; k < h; ++k) v0[k] = N::exp(p[k]);
+      e[0] = (T)meta[l].aux;
+      break;
+    }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LeapFrog bijector of the Hamiltonian flow (reference example/demo_hamiltonian_flow.jl:27-91):
+//   rho += eps/2 .* s(x);  { x += eps .* rho;  rho += eps .* s(x) } x (L-1);  x += eps .* rho;  rho += eps/2 .* s(x)
+// with s = score of the target.  Volume preserving (logdet 0, :84-91); the inverse is the same map with -eps (:63-82).
+// The reverse sweep needs no stash: each elementary update is undone exactly (up to rounding) while its adjoint is
+// applied, the second-order term being a Hessian-vector product of the target.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int HD>
+__device__ __forceinline__ void leapfrog_apply(const TargetParams<T>& sp, T* x, T* v, const T* eps, T sgn, int nsteps) {
+  T g[HD];
+#pragma unroll
+  for (int k = 0; k < HD; ++k) g[k] = 0;
+  target_logp_score<T, HD>(sp, x, g);
+#pragma unroll
+  for (int k = 0; k < HD; ++k) v[k] += sgn * eps[k] / 2 * g[k];
+  for (int it = 0; it < nsteps; ++it) {
+#pragma unroll
+    for (int k = 0; k < HD; ++k) x[k] += sgn * eps[k] * v[k];
+    target_logp_score<T, HD>(sp, x, g);
+    const T c = (it == nsteps - 1) ? sgn / 2 : sgn;
+#pragma unroll
+    for (int k = 0; k < HD; ++k) v[k] += c * eps[k] * g[k];
+  }
+}
+
+// (x, v): OUTPUT state of leapfrog_apply(sgn) on entry, its input state on exit; (gx, gv): adjoints of the output on
+// entry, of the input on exit; geps += d/d(eps) (the derivative w.r.t. the signed step is folded in through sgn).
+template <typename T, int HD>
+__device__ __forceinline__ void leapfrog_backward(const TargetParams<T>& sp, T* x, T* v, T* gx, T* gv, const T* eps,
+                                                  T sgn, int nsteps, T* geps) {
+  T g[HD], w[HD], hw[HD];
+#pragma unroll
+  for (int k = 0; k < HD; ++k) { g[k] = 0; hw[k] = 0; }
+  for (int it = nsteps - 1; it >= 0; --it) {
+    // undo  v += c eps s(x)
+    const T c = (it == nsteps - 1) ? sgn / 2 : sgn;
+    target_logp_score<T, HD>(sp, x, g);
+#pragma unroll
+    for (int k = 0; k < HD; ++k) {
+      v[k] -= c * eps[k] * g[k];
+      geps[k] += c * gv[k] * g[k];
+      w[k] = c * eps[k] * gv[k];
+    }
+    target_hvp<T, HD>(sp, x, w, hw);
+#pragma unroll
+    for (int k = 0; k < HD; ++k) gx[k] += hw[k];
+    // undo  x += eps v
+#pragma unroll
+    for (int k = 0; k < HD; ++k) {
+      x[k] -= sgn * eps[k] * v[k];
+      geps[k] += sgn * gx[k] * v[k];
+      gv[k] += sgn * eps[k] * gx[k];
+    }
+  }
+  // undo the opening half kick
+  target_logp_score<T, HD>(sp, x, g);
+#pragma unroll
+  for (int k = 0; k < HD; ++k) {
+    v[k] -= sgn * eps[k] / 2 * g[k];
+    geps[k] += sgn / 2 * gv[k] * g[k];
+    w[k] = sgn * eps[k] / 2 * gv[k];
+  }
+  target_hvp<T, HD>(sp, x, w, hw);
+#pragma unroll
+  for (int k = 0; k < HD; ++k) gx[k] += hw[k];
 }
 
 enum : int { EW_GRAD = 1, EW_TARGET = 2, EW_WRITE_Y = 4, EW_WRITE_LD = 8, EW_WRITE_TERMS = 16, EW_GEN_Z0 = 32 };
@@ -76,6 +159,7 @@ template <typename T> struct EwArgs {
   const T* base;        // mu[d], sigma[d] or nullptr
   T base_c0;            // -d/2 log2pi - sum log sigma
   TargetParams<T> tp;
+  TargetParams<T> sp;   // score target of the LeapFrog layers (dim d/2)
   T* y_out;             // [N, d]
   T* ld_out;            // [N]
   T* terms_out;         // [N]
@@ -91,6 +175,7 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
   using N_ = Num<T>;
   constexpr int STR = ew_stride<DP>();
   constexpr int NACC = ew_nacc<DP>();
+  constexpr int HD = DP / 2;
   const int L = a.L, d = a.d, tid = threadIdx.x, nthr = blockDim.x;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* s_tab = reinterpret_cast<T*>(smem_raw);                 // L*STR
@@ -178,13 +263,27 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
         for (int s = 0; s < S; ++s)
 #pragma unroll
           for (int k = 0; k < DP; ++k) z[s][k] += e[4 + k];
-      } else {  // NF_SCALE
+      } else if (kind == NF_SCALE) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
 #pragma unroll
           for (int k = 0; k < DP; ++k) z[s][k] *= e[4 + k];
           ld[s] += e[0];
         }
+      } else if (kind == NF_MOMENTUM_AFFINE) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+          for (int k = HD; k < DP; ++k) z[s][k] = z[s][k] * e[4 + DP + k] + e[4 + k];
+          ld[s] += e[0];
+        }
+      } else {  // NF_LEAPFROG
+        T eps[HD];
+#pragma unroll
+        for (int k = 0; k < HD; ++k) eps[k] = e[4 + k];
+        const int nst = (int)e[0];
+#pragma unroll
+        for (int s = 0; s < S; ++s) leapfrog_apply<T, HD>(a.sp, z[s], z[s] + HD, eps, T(1), nst);
       }
     }
     // ---- outputs of a pure forward pass ----
@@ -207,7 +306,16 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
     for (int s = 0; s < S; ++s) {
 #pragma unroll
       for (int k = 0; k < DP; ++k) gy[s][k] = 0;
-      const T lp = target_logp_score<T, DP>(a.tp, z[s], gy[s]);
+      T lp;
+      if (a.tp.joint) {   // logp(x) + sum logN(rho; 0, 1)   (demo_hamiltonian_flow.jl:117-124); d == DP here
+        lp = target_logp_score<T, HD>(a.tp, z[s], gy[s]);
+        T q = 0;
+#pragma unroll
+        for (int k = HD; k < DP; ++k) { q += z[s][k] * z[s][k]; gy[s][k] = -z[s][k]; }
+        lp -= q / 2 + T(HD) * T(NF_LOG2PI / 2);
+      } else {
+        lp = target_logp_score<T, DP>(a.tp, z[s], gy[s]);
+      }
       const T term = lp - lq[s] + ld[s];
       if (live[s]) {
         elbo_local += term;
@@ -304,7 +412,7 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
           for (int s = 0; s < S; ++s) { v += gy[s][k]; z[s][k] -= e[4 + k]; }
           if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
         }
-      } else {  // NF_SCALE
+      } else if (kind == NF_SCALE) {
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
           T v = 0;
@@ -315,6 +423,34 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
             gy[s][k] *= e[4 + k];
           }
           if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+        }
+      } else if (kind == NF_MOMENTUM_AFFINE) {
+#pragma unroll
+        for (int k = HD; k < DP; ++k) {
+          T gb = 0, ga = 0;
+          const T ia = 1 / e[4 + DP + k];
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            z[s][k] = (z[s][k] - e[4 + k]) * ia;
+            gb += gy[s][k];
+            ga += gy[s][k] * z[s][k];
+            gy[s][k] *= e[4 + DP + k];
+          }
+          gb = warp_sum(gb); ga = warp_sum(ga);
+          if (lane == 0) { atomicAdd(&acc[k], gb); atomicAdd(&acc[DP + k], ga); }
+        }
+      } else {  // NF_LEAPFROG
+        T eps[HD], ge[HD];
+#pragma unroll
+        for (int k = 0; k < HD; ++k) { eps[k] = e[4 + k]; ge[k] = 0; }
+        const int nst = (int)e[0];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          leapfrog_backward<T, HD>(a.sp, z[s], z[s] + HD, gy[s], gy[s] + HD, eps, T(1), nst, ge);
+#pragma unroll
+        for (int k = 0; k < HD; ++k) {
+          const T v = warp_sum(ge[k]);
+          if (lane == 0) atomicAdd(&acc[k], v);
         }
       }
     }
@@ -352,6 +488,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
   using N_ = Num<T>;
   constexpr int STR = ew_stride<DP>();
   constexpr int NACC = ew_nacc<DP>();
+  constexpr int HD = DP / 2;
   const int L = a.L, d = a.d, tid = threadIdx.x, nthr = blockDim.x;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* s_tab = reinterpret_cast<T*>(smem_raw);
@@ -427,13 +564,27 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
         for (int s = 0; s < S; ++s)
 #pragma unroll
           for (int k = 0; k < DP; ++k) z[s][k] -= e[4 + k];
-      } else {
+      } else if (kind == NF_SCALE) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
 #pragma unroll
           for (int k = 0; k < DP; ++k) z[s][k] *= e[4 + DP + k];
           ld[s] -= e[0];
         }
+      } else if (kind == NF_MOMENTUM_AFFINE) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+          for (int k = HD; k < DP; ++k) z[s][k] = (z[s][k] - e[4 + k]) / e[4 + DP + k];
+          ld[s] -= e[0];
+        }
+      } else {  // NF_LEAPFROG: inverse = same map with -eps (demo_hamiltonian_flow.jl:63-82)
+        T eps[HD];
+#pragma unroll
+        for (int k = 0; k < HD; ++k) eps[k] = e[4 + k];
+        const int nst = (int)e[0];
+#pragma unroll
+        for (int s = 0; s < S; ++s) leapfrog_apply<T, HD>(a.sp, z[s], z[s] + HD, eps, T(-1), nst);
       }
     }
     if (a.flags & (EW_WRITE_Y | EW_WRITE_LD)) {
@@ -572,7 +723,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
           for (int s = 0; s < S; ++s) { v -= gz[s][k]; z[s][k] += e[4 + k]; }
           if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
         }
-      } else {  // NF_SCALE: z = y / a
+      } else if (kind == NF_SCALE) {  // z = y / a
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
           T v = 0;
@@ -583,6 +734,34 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
             z[s][k] *= e[4 + k];
           }
           if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+        }
+      } else if (kind == NF_MOMENTUM_AFFINE) {  // rho_in = (rho_out - b) / a
+#pragma unroll
+        for (int k = HD; k < DP; ++k) {
+          T gb = 0, ga = 0;
+          const T ia = 1 / e[4 + DP + k];
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            gz[s][k] *= ia;
+            gb -= gz[s][k];
+            ga -= gz[s][k] * z[s][k];
+            z[s][k] = z[s][k] * e[4 + DP + k] + e[4 + k];
+          }
+          gb = warp_sum(gb); ga = warp_sum(ga);
+          if (lane == 0) { atomicAdd(&acc[k], gb); atomicAdd(&acc[DP + k], ga); }
+        }
+      } else {  // NF_LEAPFROG (applied with -eps)
+        T eps[HD], ge[HD];
+#pragma unroll
+        for (int k = 0; k < HD; ++k) { eps[k] = e[4 + k]; ge[k] = 0; }
+        const int nst = (int)e[0];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          leapfrog_backward<T, HD>(a.sp, z[s], z[s] + HD, gz[s], gz[s] + HD, eps, T(-1), nst, ge);
+#pragma unroll
+        for (int k = 0; k < HD; ++k) {
+          const T v = warp_sum(ge[k]);
+          if (lane == 0) atomicAdd(&acc[k], v);
         }
       }
     }
@@ -653,6 +832,19 @@ __global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMet
     case NF_SCALE:
       for (int k = 0; k < d; ++k) g[k] = G[k] + (inverse ? -1.0 : 1.0) * (double)N / (double)p[k];
       break;
+    case NF_MOMENTUM_AFFINE: {
+      const int h = d / 2;
+      for (int k = 0; k < h; ++k) {
+        g[k] = G[h + k];
+        g[h + k] = G[DP + h + k] + (inverse ? -1.0 : 1.0) * (double)N / (double)p[h + k];
+      }
+      break;
+    }
+    case NF_LEAPFROG: {
+      const int h = d / 2;
+      for (int k = 0; k < h; ++k) g[k] = G[k] * exp((double)p[k]);
+      break;
+    }
   }
 }
 
@@ -690,6 +882,7 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
   a.base = f.base_is_standard ? nullptr : (const T*)f.d_base;
   a.base_c0 = (T)f.base_c0;
   if (tgt) a.tp = tgt->params<T>();
+  if (f.score_target) a.sp = f.score_target->params<T>();
   a.y_out = y_out; a.ld_out = ld_out; a.terms_out = terms_out;
   a.gpart = gpart; a.epart = epart; a.N = N; a.L = L; a.d = d;
   a.flags = flags | (z0_dev ? 0 : EW_GEN_Z0);
@@ -716,6 +909,10 @@ int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const v
   if (ld_out) flags |= EW_WRITE_LD;
   if (terms_out) flags |= EW_WRITE_TERMS;
   const int d = f.dim;
+  if ((f.hamiltonian || (tgt && tgt->joint)) && (d & (d - 1)) != 0) {
+    set_error("Hamiltonian flows / joint targets need dim a power of two, got %d", d);
+    return NF_ERR_UNSUPPORTED;
+  }
 #define NF_EW_CASE(DPV, SV)                                                                              \
   return ew_launch<T, DPV, SV>(f, tgt, (const T*)theta_dev, N, (const T*)z0_dev, seed, flags, (T*)y_out, \
                                (T*)ld_out, (T*)terms_out, gsum_dev, inverse)

@@ -15,6 +15,7 @@ namespace nf {
 
 struct EwLayerMeta {
   int kind;
+  int aux;              // leapfrog: number of steps
   int64_t theta_off;
 };
 
@@ -84,6 +85,7 @@ struct Profiler {
   std::string cur;
 };
 
+struct Target;
 struct Workspace {
   char* base = nullptr;
   size_t cap = 0, off = 0;
@@ -94,6 +96,8 @@ struct Flow {
   std::vector<LayerDesc> layers;
   int64_t P = 0;
   bool all_elementwise = true, any_elementwise = false;
+  bool hamiltonian = false;            // has NF_MOMENTUM_AFFINE / NF_LEAPFROG layers (z = [x, rho])
+  struct Target* score_target = nullptr;   // owned copy of the LeapFrog layers' target
   int mma_mode = NF_MMA_SIMT;
   size_t ws_limit = (size_t)64 << 30;
   cudaStream_t stream = nullptr;
@@ -139,6 +143,7 @@ struct Flow {
 
 struct Target {
   int kind = 0, dim = 0;
+  bool joint = false;        // dim is then 2 * (inner dim)
   std::vector<double> p;
   double c0 = 0;
   void* d_vec_f32 = nullptr;
@@ -150,6 +155,8 @@ struct Target {
     tp.p1 = p.size() > 1 ? (T)p[1] : T(0);
     tp.c0 = (T)c0;
     tp.vec = (const T*)(sizeof(T) == 4 ? d_vec_f32 : d_vec_f64);
+    tp.joint = joint ? 1 : 0;
+    if (joint) tp.dim = dim / 2;
     return tp;
   }
 };

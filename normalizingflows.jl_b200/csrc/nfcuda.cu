@@ -77,6 +77,19 @@ static int check_device() {
   return NF_OK;
 }
 
+static int clone_target(const Target& src, Target& dst) {
+  dst = src;
+  dst.d_vec_f32 = dst.d_vec_f64 = nullptr;
+  if (src.d_vec_f32) {
+    const int n = 2 * (src.joint ? src.dim / 2 : src.dim);
+    NF_CUDA(cudaMalloc(&dst.d_vec_f32, n * sizeof(float)));
+    NF_CUDA(cudaMalloc(&dst.d_vec_f64, n * sizeof(double)));
+    NF_CUDA(cudaMemcpy(dst.d_vec_f32, src.d_vec_f32, n * sizeof(float), cudaMemcpyDeviceToDevice));
+    NF_CUDA(cudaMemcpy(dst.d_vec_f64, src.d_vec_f64, n * sizeof(double), cudaMemcpyDeviceToDevice));
+  }
+  return NF_OK;
+}
+
 static int build_mlp(MLPDesc& m, int n_in, const int* hdims, int n_hidden, int n_out, int out_act, int64_t& off) {
   m.dims.clear();
   m.dims.push_back(n_in);
@@ -132,6 +145,26 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
       case NF_PLANAR: off += 2 * dim + 1; f->any_elementwise = true; break;
       case NF_RADIAL: off += dim + 2; f->any_elementwise = true; break;
       case NF_SHIFT: case NF_SCALE: off += dim; f->any_elementwise = true; break;
+      case NF_MOMENTUM_AFFINE: case NF_LEAPFROG: {
+        NF_REQUIRE(dim == 2 || dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64,
+                   "layer %d: Hamiltonian layers need dim = 2h with h a power of two <= 32 in this build, got %d", i, dim);
+        f->any_elementwise = true; f->hamiltonian = true;
+        if (ds.kind == NF_MOMENTUM_AFFINE) { off += dim; break; }
+        NF_REQUIRE(ds.n_steps >= 1, "layer %d: leapfrog needs n_steps >= 1", i);
+        const Target* st = reinterpret_cast<const Target*>(ds.score_target);
+        NF_REQUIRE(st && !st->joint && st->dim == dim / 2, "layer %d: leapfrog needs a score target over dim/2 = %d coordinates", i, dim / 2);
+        NF_REQUIRE(target_has_hvp(st->kind), "layer %d: leapfrog supports Banana, Funnel and DiagNormal score targets", i);
+        if (!f->score_target) {
+          f->score_target = new Target();
+          NF_TRY(clone_target(*st, *f->score_target));
+        } else {
+          NF_REQUIRE(f->score_target->kind == st->kind && f->score_target->p == st->p,
+                     "layer %d: all leapfrog layers of a flow must share one score target", i);
+        }
+        L.K = ds.n_steps;
+        off += dim / 2;
+        break;
+      }
       case NF_AFFINE_COUPLING: case NF_SPLINE_COUPLING: {
         f->all_elementwise = false;
         NF_REQUIRE(ds.mask_idx && ds.n_mask > 0 && ds.n_mask < dim, "layer %d: coupling needs 0 < n_mask < dim", i);
@@ -190,7 +223,7 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
   {
     std::vector<EwLayerMeta> meta(n_layers);
     std::vector<int> kinds(n_layers);
-    for (int i = 0; i < n_layers; ++i) { meta[i].kind = f->layers[i].kind; meta[i].theta_off = f->layers[i].theta_off; kinds[i] = f->layers[i].kind; }
+    for (int i = 0; i < n_layers; ++i) { meta[i].kind = f->layers[i].kind; meta[i].aux = f->layers[i].K; meta[i].theta_off = f->layers[i].theta_off; kinds[i] = f->layers[i].kind; }
     NF_CUDA(cudaMalloc((void**)&f->d_ew_meta, n_layers * sizeof(EwLayerMeta)));
     NF_CUDA(cudaMalloc((void**)&f->d_ew_kinds, n_layers * sizeof(int)));
     NF_CUDA(cudaMemcpy(f->d_ew_meta, meta.data(), n_layers * sizeof(EwLayerMeta), cudaMemcpyHostToDevice));
@@ -217,6 +250,7 @@ static void flow_destroy(Flow* f) {
   cudaFree(f->d_theta); cudaFree(f->d_gsum); cudaFree(f->d_out); cudaFreeHost(f->h_pinned);
   cudaFree(f->d_adam); cudaFree(f->d_stats);
   cudaFree(f->ws.base);
+  if (f->score_target) { cudaFree(f->score_target->d_vec_f32); cudaFree(f->score_target->d_vec_f64); delete f->score_target; }
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
   if (f->stream) cudaStreamDestroy(f->stream);
@@ -463,6 +497,18 @@ int nf_target_create(nf_target_t* out, int kind, int dim, const double* params, 
   return NF_OK;
 }
 
+int nf_target_create_joint(nf_target_t* out, nf_target_t inner) {
+  NF_REQUIRE(out && inner, "null argument");
+  const Target* in = reinterpret_cast<const Target*>(inner);
+  NF_REQUIRE(!in->joint, "inner target is already a joint target");
+  std::unique_ptr<Target> t(new Target());
+  NF_TRY(clone_target(*in, *t));
+  t->joint = true;
+  t->dim = 2 * in->dim;
+  *out = reinterpret_cast<nf_target_t>(t.release());
+  return NF_OK;
+}
+
 void nf_target_destroy(nf_target_t target) {
   Target* t = reinterpret_cast<Target*>(target);
   if (!t) return;
@@ -473,6 +519,10 @@ void nf_target_destroy(nf_target_t target) {
 static int check_target(const Flow& f, const Target* t) {
   NF_REQUIRE(t, "null target");
   NF_REQUIRE(t->dim == f.dim, "target dim %d != flow dim %d", t->dim, f.dim);
+  if (t->joint && !(f.all_elementwise && f.dim == 2 * (t->dim / 2) && (f.dim & (f.dim - 1)) == 0 && f.dim <= 64)) {
+    set_error("joint [x, rho] targets are implemented for elementwise / Hamiltonian flows with dim a power of two <= 64");
+    return NF_ERR_UNSUPPORTED;
+  }
   return NF_OK;
 }
 

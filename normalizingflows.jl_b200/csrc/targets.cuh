@@ -11,6 +11,7 @@ template <typename T> struct TargetParams {
   T p0, p1;        // scalar parameters
   T c0;            // precomputed constant part of logp
   const T* vec;    // DiagNormal: mu[dim] then sigma[dim] (device memory)
+  int joint;       // 1: logp(z) = logp_inner(z[0:dim]) + sum logN(z[dim:2dim]; 0, 1)  (demo_hamiltonian_flow.jl:117-124)
 };
 
 #define NF_LOG2PI 1.8378770664093454835606594728112
@@ -109,6 +110,59 @@ __device__ __forceinline__ T target_logp_score(const TargetParams<T>& tp, const 
     }
   }
   return 0;
+}
+
+// out = (Hessian of logp at x) * w -- the second-order term the reverse sweep through a LeapFrog layer needs
+// (reference example/demo_hamiltonian_flow.jl:49-61 differentiates through `∇logp`).  Supported for the targets
+// whose score is smooth and closed-form: Banana, Funnel, DiagNormal.
+template <typename T, int DP>
+__device__ __forceinline__ void target_hvp(const TargetParams<T>& tp, const T* x, const T* w, T* out) {
+  using N = Num<T>;
+  const int d = tp.dim;
+  constexpr int UB = DP > 0 ? DP : 1 << 30;
+  switch (tp.kind) {
+    case NF_TARGET_BANANA: {
+      const T b = tp.p0, v = tp.p1;
+      const T u2 = x[1] + b * x[0] * x[0] - v * b;
+      const T h11 = -1 / v - 2 * b * u2 - 4 * b * b * x[0] * x[0];
+      const T h12 = -2 * b * x[0];
+      out[0] = h11 * w[0] + h12 * w[1];
+      out[1] = h12 * w[0] - w[1];
+#pragma unroll
+      for (int k = 2; k < UB; ++k) {
+        if (k >= d) break;
+        out[k] = -w[k];
+      }
+      return;
+    }
+    case NF_TARGET_FUNNEL: {
+      const T sg = tp.p1;
+      const T a = N::exp(-x[0]);
+      T ss = 0, xw = 0;
+#pragma unroll
+      for (int k = 1; k < UB; ++k) {
+        if (k >= d) break;
+        ss += x[k] * x[k];
+        xw += x[k] * w[k];
+        out[k] = a * (x[k] * w[0] - w[k]);
+      }
+      out[0] = (-1 / (sg * sg) - a * ss / 2) * w[0] + a * xw;
+      return;
+    }
+    case NF_TARGET_DIAG_NORMAL: {
+#pragma unroll
+      for (int k = 0; k < UB; ++k) {
+        if (k >= d) break;
+        const T is = 1 / tp.vec[d + k];
+        out[k] = -w[k] * is * is;
+      }
+      return;
+    }
+  }
+}
+
+__host__ __device__ inline bool target_has_hvp(int kind) {
+  return kind == NF_TARGET_BANANA || kind == NF_TARGET_FUNNEL || kind == NF_TARGET_DIAG_NORMAL;
 }
 
 }  // namespace nf

@@ -281,6 +281,58 @@ class AffineCoupling(Layer):
         return x, -s.sum(dim=1)
 
 
+class MomentumAffine(Layer):
+    """`Stacked((identity, Shift(b) ∘ Scale(a)), [1:d, d+1:2d])` -- the momentum normalisation layer of
+    example/demo_hamiltonian_flow.jl:94-99: position block untouched, rho <- a .* rho .+ b.  theta: shift(d), scale(d)."""
+    kind = "momentum_affine"
+
+    def __init__(self, shift, scale):
+        self.shift, self.scale = shift, scale
+
+    def params(self):
+        return [self.shift, self.scale]
+
+    def forward(self, z):
+        d = self.shift.numel()
+        y = torch.cat([z[:, :d], z[:, d:] * self.scale + self.shift], dim=1)
+        return y, torch.log(torch.abs(self.scale)).sum().expand(z.shape[0])
+
+    def inverse(self, y):
+        d = self.shift.numel()
+        z = torch.cat([y[:, :d], (y[:, d:] - self.shift) / self.scale], dim=1)
+        return z, (-torch.log(torch.abs(self.scale)).sum()).expand(y.shape[0])
+
+
+class LeapFrog(Layer):
+    """`LeapFrog` bijector of example/demo_hamiltonian_flow.jl:27-91: L leapfrog steps on z = [x, rho] with per-dimension
+    step sizes exp(log_eps) (the only trainable field, `@functor LeapFrog (logϵ,)`, :39) and the target score inside the
+    transform (:49-61).  Symplectic: logabsdetjac = 0 (:84-91).  `score` must be differentiable (second-order terms)."""
+    kind = "leapfrog"
+
+    def __init__(self, log_eps, L, score, target=None):
+        self.log_eps, self.L, self.score, self.target = log_eps, int(L), score, target
+
+    def params(self):
+        return [self.log_eps]
+
+    def _run(self, z, eps):
+        d = self.log_eps.numel()
+        x, v = z[:, :d], z[:, d:]
+        v = v + eps / 2 * self.score(x)
+        for _ in range(self.L - 1):
+            x = x + eps * v
+            v = v + eps * self.score(x)
+        x = x + eps * v
+        v = v + eps / 2 * self.score(x)
+        return torch.cat([x, v], dim=1)
+
+    def forward(self, z):
+        return self._run(z, torch.exp(self.log_eps)), torch.zeros(z.shape[0], dtype=z.dtype)
+
+    def inverse(self, z):
+        return self._run(z, -torch.exp(self.log_eps)), torch.zeros(z.shape[0], dtype=z.dtype)
+
+
 # ---- rational-quadratic splines (MonotonicSplines v0.3.3, App. A.4) --------------------------
 def rqs_slot_rows(c: int, K: int):
     """Row -> (coordinate, slot) map of the (3K-1)*c conditioner outputs.  Returns three index
@@ -506,6 +558,10 @@ def _rebind(layer: Layer, theta: torch.Tensor, off: int):
 
     if isinstance(layer, (Shift, Scale)):
         layer.a = take(layer.a.shape)
+    elif isinstance(layer, MomentumAffine):
+        layer.shift = take(layer.shift.shape); layer.scale = take(layer.scale.shape)
+    elif isinstance(layer, LeapFrog):
+        layer.log_eps = take(layer.log_eps.shape)
     elif isinstance(layer, Planar):
         layer.w = take(layer.w.shape); layer.u = take(layer.u.shape); layer.b = take(layer.b.shape)
     elif isinstance(layer, Radial):
@@ -693,6 +749,60 @@ class Cross(Target):
             k = rng.integers(0, 4, size=n)
             out[:, j:j + 2] = means[k] + sds[k] * rng.standard_normal((n, 2))
         return torch.from_numpy(out).to(dtype)
+
+
+def _score_funnel(x, mu, sigma):
+    """`score(::Funnel, x)` of example/targets/neal_funnel.jl:63-72, batched."""
+    d = x.shape[1]
+    a = torch.exp(-x[:, :1])
+    ss = (x[:, 1:] ** 2).sum(dim=1, keepdim=True)
+    g1 = (mu - x[:, :1]) / sigma ** 2 - (d - 1) / 2 + a * ss / 2
+    return torch.cat([g1, -a * x[:, 1:]], dim=1)
+
+
+def _score_banana(x, b, var):
+    u2 = x[:, 1:2] + b * x[:, :1] ** 2 - var * b
+    g1 = -x[:, :1] / var - 2 * b * x[:, :1] * u2
+    return torch.cat([g1, -u2, -x[:, 2:]], dim=1)
+
+
+def target_score(target):
+    """Differentiable score function d logp / dx of a built-in target (used inside LeapFrog)."""
+    if isinstance(target, Funnel):
+        return lambda x: _score_funnel(x, target.mu, target.sigma)
+    if isinstance(target, Banana):
+        return lambda x: _score_banana(x, target.b, target.var)
+    if isinstance(target, DiagNormal):
+        return lambda x: -(x - target.mu.to(x.dtype)) / target.sigma.to(x.dtype) ** 2
+    raise TypeError("no score function for %r" % (target,))
+
+
+class JointTarget(Target):
+    """logp_joint(z) = logp(x) + sum(logpdf(Normal(), rho)) on z = [x, rho] (example/demo_hamiltonian_flow.jl:117-124)."""
+    kind = "joint"
+
+    def __init__(self, inner):
+        self.inner, self.dim = inner, 2 * inner.dim
+
+    def logp(self, z):
+        d = self.inner.dim
+        rho = z[:, d:]
+        return self.inner.logp(z[:, :d]) - 0.5 * d * LOG2PI - 0.5 * (rho * rho).sum(dim=1)
+
+
+def hamiltonian_flow(target, nlayers: int, L: int, log_eps0: float, dtype=torch.float64) -> "Flow":
+    """The flow of example/demo_hamiltonian_flow.jl:128-147: Ls = [momentum_normalization ∘ LeapFrog] x nlayers on top of
+    q0 = transformed(MvNormal(0, I_2d), Shift ∘ Scale); `transformed(q0, ts)` composes, so theta ends with q0's Shift, Scale
+    (App. A.5) and those are applied first."""
+    d = target.dim
+    sc = target_score(target)
+    Ls: List[Layer] = []
+    for _ in range(nlayers):
+        Ls.append(MomentumAffine(torch.zeros(d, dtype=dtype), torch.ones(d, dtype=dtype)))
+        Ls.append(LeapFrog(torch.full((d,), float(log_eps0), dtype=dtype), L, sc, target))
+    Ls.append(Shift(torch.zeros(2 * d, dtype=dtype)))
+    Ls.append(Scale(torch.ones(2 * d, dtype=dtype)))
+    return Flow(2 * d, Ls, dtype=dtype)
 
 
 class DiagNormal(Target):

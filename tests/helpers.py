@@ -18,6 +18,13 @@ def oracle_flow(kind, dim, dtype, seed=123, **kw):
         return O.realnvp(dim, kw.get("hdims", [32, 32]), kw.get("nlayers", 2), td, rng)
     if kind == "nsf":
         return O.nsf(dim, kw.get("hdims", [32, 32]), kw.get("K", 10), kw.get("B", 5.0), kw.get("nlayers", 2), td, rng)
+    if kind == "hamiltonian":   # dim = 2h; LeapFrog on Funnel(h, -8, 5) (example/demo_hamiltonian_flow.jl:104-147), jittered theta
+        import math
+        tgt = O.Funnel(dim // 2, -8.0, 5.0)
+        f = O.hamiltonian_flow(tgt, kw.get("nlayers", 15), kw.get("L", 3), math.log(0.05), dtype=td)
+        th = f.theta().double().numpy()
+        f.set_theta(torch.from_numpy(th + 0.05 * rng.standard_normal(th.size)).to(td))
+        return f
     raise ValueError(kind)
 
 
@@ -33,6 +40,10 @@ def gpu_flow(nf, of, dtype, base=None):
             layers.append(nf.Shift(l.a.detach().numpy()))
         elif isinstance(l, O.Scale):
             layers.append(nf.Scale(l.a.detach().numpy()))
+        elif isinstance(l, O.MomentumAffine):
+            layers.append(nf.MomentumAffine(l.shift.detach().numpy(), l.scale.detach().numpy()))
+        elif isinstance(l, O.LeapFrog):
+            layers.append(nf.LeapFrog(l.log_eps.numel(), l.log_eps.detach().numpy(), l.L, gpu_target(nf, l.target)))
         elif isinstance(l, O.AffineCoupling):
             hd = [W.shape[1] for W in l.s.Wts[:-1]]
             layers.append(nf.AffineCoupling(of.dim, hd, l.idx1, dtype))
@@ -57,6 +68,8 @@ def oracle_target(name, dim):
         return O.WarpedGauss(1.0, 0.12)
     if name == "cross":
         return O.Cross(dim, 2.0, 0.15)
+    if name == "joint_funnel":
+        return O.JointTarget(O.Funnel(dim // 2, -8.0, 5.0))
     if name == "diag":
         rng = np.random.Generator(np.random.PCG64(7))
         return O.DiagNormal(rng.standard_normal(dim), rng.uniform(0.5, 1.5, dim))
@@ -74,6 +87,8 @@ def gpu_target(nf, ot):
         return nf.Cross(ot.mu, ot.sigma, ot.dim)
     if isinstance(ot, O.DiagNormal):
         return nf.DiagNormal(ot.mu.numpy(), ot.sigma.numpy())
+    if isinstance(ot, O.JointTarget):
+        return nf.JointTarget(gpu_target(nf, ot.inner))
     raise TypeError(ot)
 
 

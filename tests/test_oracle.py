@@ -164,3 +164,52 @@ def test_targets_match_closed_forms():
     # Funnel(2, 0, 9)
     ref = (-0.5 * np.log(2 * np.pi) - np.log(9) - 0.09 / 162) + (-0.5 * (np.log(2 * np.pi) + 0.3) - 0.5 * np.exp(-0.3) * 1.44)
     assert float(O.Funnel(2).logp(y)[0]) == pytest.approx(ref, rel=1e-12)
+
+
+# ---- Hamiltonian flow (reference example/demo_hamiltonian_flow.jl) ---------------------------------------------
+def _ham(tgt, nlayers=4, L=3, seed=0):
+    f = O.hamiltonian_flow(tgt, nlayers, L, np.log(0.05))
+    rng = np.random.default_rng(seed)
+    th = f.theta().numpy()
+    f.set_theta(torch.from_numpy(th + 0.05 * rng.standard_normal(th.size)))
+    return f
+
+
+def test_leapfrog_is_reversible_and_volume_preserving():
+    """demo_hamiltonian_flow.jl:63-91: inverse = leapfrog with -eps; logabsdetjac = 0 (checked against autograd's Jacobian)."""
+    tgt = O.Funnel(2, -2.0, 3.0)
+    lf = O.LeapFrog(torch.tensor([-2.0, -2.5], dtype=torch.float64), 3, O.target_score(tgt))
+    z = torch.from_numpy(np.random.default_rng(1).standard_normal((5, 4)))
+    y, ld = lf.forward(z)
+    zr, _ = lf.inverse(y)
+    assert float((zr - z).abs().max()) < 1e-12 and float(ld.abs().max()) == 0.0
+    J = torch.autograd.functional.jacobian(lambda v: lf.forward(v[None, :])[0][0], z[0])
+    assert abs(float(torch.linalg.det(J)) - 1.0) < 1e-10
+
+
+def test_target_scores_match_autograd():
+    rng = np.random.default_rng(2)
+    for tgt in (O.Funnel(3, -1.0, 2.0), O.Banana(3, 0.4, 5.0), O.DiagNormal(rng.standard_normal(3), rng.uniform(0.5, 2, 3))):
+        x = torch.from_numpy(rng.standard_normal((7, 3))).requires_grad_(True)
+        (g,) = torch.autograd.grad(tgt.logp(x).sum(), x)
+        assert float((g - O.target_score(tgt)(x.detach())).abs().max()) < 1e-12
+
+
+def test_hamiltonian_flow_theta_layout_and_gradient():
+    """theta = per layer [b; a; log_eps], then q0's shift, scale; autograd gradient vs central differences."""
+    tgt = O.Funnel(2, -2.0, 3.0)
+    f = _ham(tgt)
+    assert f.n_params() == 4 * 6 + 8
+    jt = O.JointTarget(tgt)
+    xs = torch.from_numpy(np.random.default_rng(3).standard_normal((32, 4)))
+    th = f.theta().numpy().copy()
+    v, g = O.elbo_value_and_grad(f, jt, th, xs)
+    for i in (0, 3, 5, 11, 24, 30):
+        e = np.zeros_like(th); e[i] = 1e-6
+        vp, _ = O.elbo_value_and_grad(f, jt, th + e, xs)
+        vm, _ = O.elbo_value_and_grad(f, jt, th - e, xs)
+        assert abs((vp - vm) / 2e-6 - g[i]) < 1e-6 * max(1.0, abs(g[i]))
+    # joint target = target + standard normal momentum
+    z = xs[:3]
+    ref = tgt.logp(z[:, :2]) + torch.distributions.Normal(0, 1).log_prob(z[:, 2:]).sum(dim=1)
+    assert float((jt.logp(z) - ref).abs().max()) < 1e-12
