@@ -26,9 +26,12 @@ struct NFLayerDesc
     n_hidden::Cint
     K::Cint
     B::Cdouble
+    n_steps::Cint              # leapfrog steps (example/demo_hamiltonian_flow.jl:30)
+    score_target::Ptr{Cvoid}   # nf_target_t whose score drives the leapfrog dynamics
 end
+NFLayerDesc(kind, mi, nm, hd, nh, K, B) = NFLayerDesc(kind, mi, nm, hd, nh, K, B, 0, C_NULL)
 const NF_F32, NF_F64 = Cint(0), Cint(1)
-const NF_PLANAR, NF_RADIAL, NF_AFFINE, NF_SPLINE, NF_SHIFT, NF_SCALE = Cint.(1:6)
+const NF_PLANAR, NF_RADIAL, NF_AFFINE, NF_SPLINE, NF_SHIFT, NF_SCALE, NF_MOMENTUM_AFFINE, NF_LEAPFROG = Cint.(1:8)
 
 function check(status::Cint)
     status == 0 && return nothing
@@ -54,10 +57,21 @@ export AutoNFCUDA
 # ---- flow structure -> nf_layer_desc[] in theta (= Ls) order ------------------------------------------
 flatten_layers(f::ComposedFunction) = vcat(flatten_layers(f.outer), flatten_layers(f.inner))
 flatten_layers(f) = Any[f]
+# `transformed(transformed(q₀, t₀), t)` (the Hamiltonian demo, example/demo_hamiltonian_flow.jl:139-147): t's layers come
+# first in θ, then t₀'s; the innermost distribution is the base.
+function unwrap(flow::Bijectors.TransformedDistribution)
+    layers = flatten_layers(flow.transform)
+    base = flow.dist
+    while base isa Bijectors.TransformedDistribution
+        append!(layers, flatten_layers(base.transform))
+        base = base.dist
+    end
+    return layers, base
+end
 
 hidden_dims(c) = Cint[size(l.weight, 1) for l in c.layers[1:(end - 1)]]
 
-function describe(layer, keep::Vector{Any})
+function describe(layer, keep::Vector{Any}; score_target::Ptr{Cvoid}=C_NULL)
     z = Ptr{Cint}(C_NULL)
     if layer isa Bijectors.PlanarLayer
         return NFLayerDesc(NF_PLANAR, z, 0, z, 0, 0, 0.0)
@@ -77,6 +91,13 @@ function describe(layer, keep::Vector{Any})
         hd = hidden_dims(layer.nn)
         push!(keep, idx, hd)
         return NFLayerDesc(NF_SPLINE, pointer(idx), length(idx), pointer(hd), length(hd), layer.K, Float64(layer.B))
+    elseif layer isa Bijectors.Stacked && length(layer.bs) == 2 && layer.bs[1] === identity
+        # momentum_normalization_layer of example/demo_hamiltonian_flow.jl:94-99: Stacked((identity, Shift ∘ Scale), ...)
+        return NFLayerDesc(NF_MOMENTUM_AFFINE, z, 0, z, 0, 0, 0.0)
+    elseif hasproperty(layer, :logϵ) && hasproperty(layer, :L) && hasproperty(layer, :∇logp)
+        # the demo's LeapFrog bijector (:27-47); its ∇logp closure is replaced by the device score of `score_target`
+        score_target == C_NULL && error("NFCUDA: a LeapFrog layer needs target = (:joint, kind, params...)")
+        return NFLayerDesc(NF_LEAPFROG, z, 0, z, 0, 0, 0.0, Cint(layer.L), score_target)
     end
     error("NFCUDA: unsupported bijector $(typeof(layer))")
 end
@@ -93,17 +114,28 @@ target_kind(s::Symbol) = Dict(:banana => 1, :funnel => 2, :warped_gauss => 3, :c
 function make_prep(flow::Bijectors.TransformedDistribution, ad::AutoNFCUDA, ::Type{T}) where {T}
     check(ccall((:nf_init, libnfcuda), Cint, (Cint,), ad.device))
     keep = Any[]
-    descs = [describe(l, keep) for l in flatten_layers(flow.transform)]
-    d = length(flow.dist)
+    layers, base = unwrap(flow)
+    d = length(base)
+    # targets first: a Hamiltonian flow's LeapFrog layers need the inner target's handle
+    joint = ad.target[1] === :joint                      # (:joint, :funnel, μ, σ): logp(x) + logN(ρ) on z = [x, ρ]
+    spec = joint ? ad.target[2:end] : ad.target
+    tp = Float64[x for p in spec[2:end] for x in p]
+    t = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:nf_target_create, libnfcuda), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cdouble}, Cint),
+        t, target_kind(spec[1]), joint ? d ÷ 2 : d, tp, length(tp)))
+    inner = joint ? t[] : Ptr{Cvoid}(C_NULL)
+    if joint
+        tj = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:nf_target_create_joint, libnfcuda), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}), tj, inner))
+        t[] = tj[]
+    end
+    descs = [describe(l, keep; score_target=inner) for l in layers]
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep descs check(ccall((:nf_flow_create, libnfcuda), Cint,
         (Ref{Ptr{Cvoid}}, Ptr{NFLayerDesc}, Cint, Cint, Cint), h, descs, length(descs), d, T === Float32 ? NF_F32 : NF_F64))
-    μ = Float64.(Distributions.mean(flow.dist)); σ = Float64.(sqrt.(Distributions.var(flow.dist)))   # diagonal q₀
+    μ = Float64.(Distributions.mean(base)); σ = Float64.(sqrt.(Distributions.var(base)))   # diagonal q₀
     check(ccall((:nf_flow_set_base, libnfcuda), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h[], μ, σ))
-    tp = Float64[x for p in ad.target[2:end] for x in p]
-    t = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:nf_target_create, libnfcuda), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Cdouble}, Cint),
-        t, target_kind(ad.target[1]), d, tp, length(tp)))
+    joint && ccall((:nf_target_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), inner)   # both users hold copies
     P = ccall((:nf_flow_num_params, libnfcuda), Int64, (Ptr{Cvoid},), h[])
     prep = Prep(h[], t[], P, T)
     finalizer(prep) do p

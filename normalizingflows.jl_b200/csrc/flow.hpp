@@ -100,6 +100,11 @@ struct Flow {
   struct Target* score_target = nullptr;   // owned copy of the LeapFrog layers' target
   int mma_mode = NF_MMA_SIMT;
   size_t ws_limit = (size_t)64 << 30;
+  // cached workspace plan (general_plan_workspace)
+  bool plan_valid = false;
+  int plan_op = 0, plan_mode = 0;
+  int64_t plan_N = 0, plan_chunk = 0;
+  size_t plan_extra = 0, plan_limit = 0, plan_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0;

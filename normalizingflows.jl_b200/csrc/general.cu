@@ -181,13 +181,13 @@ int simt_mlp_forward(Flow& f, const MLPDesc& md, const T* theta, int64_t n, cons
 // gradient sums into gsum (theta order) and scatter-adds the conditioner-input gradient into G[:, idx2].
 template <typename T>
 int simt_mlp_backward(Flow& f, const MLPDesc& md, const T* theta, int64_t n, const T* act0, std::vector<void*>& acts,
-                      T* g_last, T* tmp0, T* tmp1, T* G, int d, const int* d_idx2, double* gsum) {
+                      T* g_last, T* tmp0, T* tmp1, T* G, int d, const int* d_idx2, double* gsum, bool last_bias_done = false) {
   const int nd = md.n_dense();
   T* g = g_last;
   for (int i = nd - 1; i >= 0; --i) {
     const T* in = (i == 0) ? act0 : (const T*)acts[i - 1];
     const int kin = md.dims[i], kout = md.dims[i + 1];
-    {
+    if (!(last_bias_done && i == nd - 1)) {
       const int64_t rpb = 4096;
       colsum_atomic_kernel<T><<<(unsigned)ceil_div(n, rpb), 256, 0, f.stream>>>(g, n, kout, rpb, gsum + md.b_off[i]);
       NF_LAUNCH_CHECK();
@@ -212,6 +212,25 @@ int simt_mlp_backward(Flow& f, const MLPDesc& md, const T* theta, int64_t n, con
 // ---------------------------------------------------------------------------------------------
 // one coupling layer, forward (INV = false: y = T(x)) or inverse direction
 // ---------------------------------------------------------------------------------------------
+// Launch shape of the spline kernels: threads per block (= pairs per tile), ring depth and grid such that
+// stages * tile fits in shared memory with several blocks resident per SM.
+struct RqsLaunch { int threads, stages; size_t smem; unsigned grid; };
+template <typename T>
+RqsLaunch rqs_launch_shape(int K, int64_t pairs) {
+  const size_t row = (size_t)(3 * K - 1) * sizeof(T);
+  int thr = 128;
+  while (thr > 32 && 2 * thr * row > (size_t)96 * 1024) thr >>= 1;
+  const size_t tile = thr * row;
+  // one tile of prefetch is enough (a tile's arithmetic takes far longer than the HBM latency); the shared memory is
+  // better spent on resident warps to hide the dependent cumsum / division chains
+  int stages = 2;
+  if (const char* e = getenv("NFCUDA_RQS_STAGES")) stages = std::max(2, std::min(rq::kMaxStages, atoi(e)));
+  const size_t smem = stages * tile;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)216 * 1024) / (smem + 1024)));
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(pairs, thr), (int64_t)per_sm * kNumSMs));
+  return RqsLaunch{thr, stages, smem, grid};
+}
+
 template <typename T, bool INV>
 int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, int64_t n, const T* Xin, T* Xout, T* ld,
                    int32_t* bins, const float* amax_in, float* amax_out) {
@@ -229,22 +248,21 @@ int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, i
     affine_apply_kernel<T, INV><<<(unsigned)std::min<int64_t>(ceil_div(n * d, 256), 16 * kNumSMs), 256, 0, f.stream>>>(
         Xin, (const T*)b.acts[0].back(), (const T*)b.acts[1].back(), Ld.d_pos, c, d, n, Xout, ld, amax_out);
   } else {
-    const size_t sm = (size_t)128 * (3 * Ld.K - 1) * sizeof(T);
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n * c, 128), 32 * kNumSMs);
-    if (Ld.K <= 8) {
-      rqs_apply_kernel<T, 8, INV><<<grid, 128, sm, f.stream>>>(Xin, (const T*)b.acts[0].back(), Ld.d_idx1, Ld.d_pos, c, d, Ld.K,
-                                                               (T)Ld.B, n, Xout, ld, bins, amax_out);
-    } else if (Ld.K <= 10) {
-      rqs_apply_kernel<T, 10, INV><<<grid, 128, sm, f.stream>>>(Xin, (const T*)b.acts[0].back(), Ld.d_idx1, Ld.d_pos, c, d, Ld.K,
-                                                                (T)Ld.B, n, Xout, ld, bins, amax_out);
-    } else if (Ld.K <= 16) {
-      rqs_apply_kernel<T, 16, INV><<<grid, 128, sm, f.stream>>>(Xin, (const T*)b.acts[0].back(), Ld.d_idx1, Ld.d_pos, c, d, Ld.K,
-                                                                (T)Ld.B, n, Xout, ld, bins, amax_out);
-    } else {
-      auto kern = rqs_apply_kernel<T, 64, INV>;
-      NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      kern<<<grid, 128, sm, f.stream>>>(Xin, (const T*)b.acts[0].back(), Ld.d_idx1, Ld.d_pos, c, d, Ld.K, (T)Ld.B, n, Xout, ld, bins, amax_out);
-    }
+    const RqsLaunch rl = rqs_launch_shape<T>(Ld.K, n * c);
+    const T* raw = (const T*)b.acts[0].back();
+#define NF_RQS_APPLY(KM)                                                                                              \
+    do {                                                                                                                \
+      auto kern = rqs_apply_kernel<T, KM, INV>;                                                                         \
+      if (rl.smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.smem)); \
+      kern<<<rl.grid, rl.threads, rl.smem, f.stream>>>(Xin, raw, Ld.d_idx1, Ld.d_pos, c, d, Ld.K, (T)Ld.B, n, Xout, ld, bins, amax_out, rl.stages); \
+    } while (0)
+    f.prof.begin("rqs_apply", f.stream);
+    if (Ld.K <= 8) NF_RQS_APPLY(8);
+    else if (Ld.K <= 10) NF_RQS_APPLY(10);
+    else if (Ld.K <= 16) NF_RQS_APPLY(16);
+    else NF_RQS_APPLY(64);
+    f.prof.end(f.stream);
+#undef NF_RQS_APPLY
   }
   NF_LAUNCH_CHECK();
   return NF_OK;
@@ -282,22 +300,29 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
   } else {
     float* mR = tc ? tc_alloc_meta(f) : nullptr;
     if (tc) NF_REQUIRE(mR, "tcgen05 path: out of tensor metadata slots");
-    const size_t sm = (size_t)128 * (3 * Ld.K - 1) * sizeof(T);
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n * cc, 128), 32 * kNumSMs);
-    if (Ld.K <= 8) {
-      rqs_bwd_kernel<T, 8, INV><<<grid, 128, sm, f.stream>>>(G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR);
-    } else if (Ld.K <= 10) {
-      rqs_bwd_kernel<T, 10, INV><<<grid, 128, sm, f.stream>>>(G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR);
-    } else if (Ld.K <= 16) {
-      rqs_bwd_kernel<T, 16, INV><<<grid, 128, sm, f.stream>>>(G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR);
-    } else {
-      auto kern = rqs_bwd_kernel<T, 64, INV>;
-      NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      kern<<<grid, 128, sm, f.stream>>>(G, Xin, (const T*)b.acts[0].back(), gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR);
-    }
+    bool fused_bias = false;
+    const RqsLaunch rl = rqs_launch_shape<T>(Ld.K, n * cc);
+    // bias gradient of the conditioner's last Dense = column sums of graw: folded into the kernel when a tile is whole samples
+    const MLPDesc& md = Ld.mlps[0];
+    fused_bias = (rl.threads % cc == 0) && (cc * (3 * Ld.K - 1) <= 4 * rl.threads);
+    double* cs = fused_bias ? f.d_gsum + md.b_off[md.n_dense() - 1] : nullptr;
+    const T* raw = (const T*)b.acts[0].back();
+#define NF_RQS_BWD(KM)                                                                                                \
+    do {                                                                                                                \
+      auto kern = rqs_bwd_kernel<T, KM, INV>;                                                                           \
+      if (rl.smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.smem)); \
+      kern<<<rl.grid, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR, cs, rl.stages); \
+    } while (0)
+    f.prof.begin("rqs_bwd", f.stream);
+    if (Ld.K <= 8) NF_RQS_BWD(8);
+    else if (Ld.K <= 10) NF_RQS_BWD(10);
+    else if (Ld.K <= 16) NF_RQS_BWD(16);
+    else NF_RQS_BWD(64);
+    f.prof.end(f.stream);
+#undef NF_RQS_BWD
     NF_LAUNCH_CHECK();
-    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, mR, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum));
-    else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, need_input_grad ? G : nullptr, d, Ld.d_idx2, f.d_gsum));
+    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, mR, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum, fused_bias));
+    else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, need_input_grad ? G : nullptr, d, Ld.d_idx2, f.d_gsum, fused_bias));
   }
   return NF_OK;
 }
@@ -505,6 +530,13 @@ int general_plan_workspace(Flow& f, int op, int64_t N, size_t extra_bytes) {
     return f.ws_reserve(extra_bytes + ((size_t)16 << 20));
   }
   const bool stash = (op == OP_ELBO || op == OP_LOGLIK || op == OP_FORWARD_STASH);
+  // the plan of the previous call is reused when nothing it depends on changed (cudaMemGetInfo is a driver round trip
+  // that can stall for milliseconds while the GPU is busy; a training loop asks the same question every iteration)
+  if (f.plan_valid && f.plan_op == op && f.plan_N == N && f.plan_extra == extra_bytes && f.plan_limit == f.ws_limit &&
+      f.plan_mode == f.mma_mode && f.ws.cap >= f.plan_cap) {
+    f.chunk_N = f.plan_chunk;
+    return NF_OK;
+  }
   const size_t per = per_sample_bytes(f, stash);
   const size_t fixed = extra_bytes + ((size_t)32 << 20) + tc_weight_bytes(f);
   size_t budget = f.ws_limit > fixed ? f.ws_limit - fixed : 0;
@@ -521,7 +553,10 @@ int general_plan_workspace(Flow& f, int op, int64_t N, size_t extra_bytes) {
     NF_REQUIRE(Nc >= 1024, "workspace limit too small: %zu B per sample, budget %zu B", per, budget);
   }
   f.chunk_N = Nc;
-  return f.ws_reserve(fixed + per * (size_t)(Nc + 1024));
+  NF_TRY(f.ws_reserve(fixed + per * (size_t)(Nc + 1024)));
+  f.plan_valid = true; f.plan_op = op; f.plan_N = N; f.plan_extra = extra_bytes; f.plan_limit = f.ws_limit;
+  f.plan_mode = f.mma_mode; f.plan_chunk = Nc; f.plan_cap = fixed + per * (size_t)(Nc + 1024);
+  return NF_OK;
 }
 
 int general_run(Flow& f, const GeneralJob& job) {

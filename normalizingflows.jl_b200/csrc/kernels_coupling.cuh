@@ -354,75 +354,132 @@ __device__ __forceinline__ void rqs_eval_inv(const RqsBin<T>& b, T y, T& x, T& l
   xi_out = xi;
 }
 
-// Shared evaluation of one (sample, coordinate) spline from its 3K-1 logits held in registers/local memory:
-// exp() of every width/height logit is computed once and reused by the bin search, the knots and the softmax backward.
-template <typename T, int KMAX> struct RqsLocal {
-  T ew[KMAX], eh[KMAX];
-  T Sw, Sh;
-};
-
+// Evaluation of one (sample, coordinate) spline from its 3K-1 logits, which stay in the thread's private row of the
+// shared-memory staging tile (row stride 3K-1 words is odd for every K: conflict-free).  exp() of each width/height
+// logit is computed once and written back in place, so the bin search, the knots and the softmax backward all read
+// the numerators from shared memory and nothing indexed dynamically lives in registers or local memory.
+// On return row[0..2K) = exp(logit); row[2K..3K-1) still holds the derivative logits.
 template <typename T, int KMAX, bool INV>
-__device__ __forceinline__ void rqs_locate_cached(const T* __restrict__ tl, int K, T B, T v, RqsLocal<T, KMAX>& L, RqsBin<T>& b) {
+__device__ __forceinline__ void rqs_locate_row(T* __restrict__ row, int K, T B, T v, RqsBin<T>& b) {
   using N = Num<T>;
   T Sw = 0, Sh = 0;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
+  for (int k = 0; k < KMAX; ++k)
     if (k < K) {
-      L.ew[k] = N::exp(tl[k]); L.eh[k] = N::exp(tl[K + k]);
-      Sw = add_rn(Sw, L.ew[k]); Sh = add_rn(Sh, L.eh[k]);
+      const T ew = N::exp(row[k]), eh = N::exp(row[K + k]);
+      row[k] = ew; row[K + k] = eh;
+      Sw = add_rn(Sw, ew); Sh = add_rn(Sh, eh);
     }
-  }
-  L.Sw = Sw; L.Sh = Sh;
-  const T* es = INV ? L.eh : L.ew;
-  const T* eo = INV ? L.ew : L.eh;
+  b.Sw = Sw; b.Sh = Sh;
+  const T* es = INV ? row + K : row;
+  const T* eo = INV ? row : row + K;
   const T rSs = 1 / (INV ? Sh : Sw), rSo = 1 / (INV ? Sw : Sh);   // softmax by reciprocal multiply (one division per family)
   const T twoB = 2 * B;
   // knots of the searched family: sequential cumsum, knot = (2B)*cs - B without FMA contraction
   T cs = 0, prev = -B, prevc = 0, s0 = 0, s1 = 0, c0 = 0, c1 = 0;
   int bin = K + 1;
-  bool found = !(prev < v);
-  if (found) bin = 0;
-#pragma unroll
-  for (int k = 1; k <= KMAX; ++k) {
-    if (k <= K && !found) {
+  if (!(prev < v)) bin = 0;
+  else
+    for (int k = 1; k <= K; ++k) {
       cs = add_rn(cs, mul_rn(es[k - 1], rSs));
       const T knot = add_rn(mul_rn(twoB, cs), -B);
-      if (!(knot < v)) { bin = k; s0 = prev; s1 = knot; c0 = prevc; c1 = cs; found = true; }
-      else { prev = knot; prevc = cs; }
+      if (!(knot < v)) { bin = k; s0 = prev; s1 = knot; c0 = prevc; c1 = cs; break; }
+      prev = knot; prevc = cs;
     }
-  }
   b.k = bin;
   if (bin < 1 || bin > K) return;
-  T co = 0, o0 = -B, o1 = 0, oc0 = 0, oc1 = 0;
-#pragma unroll
-  for (int k = 1; k <= KMAX; ++k) {
-    if (k <= bin) {
-      co = add_rn(co, mul_rn(eo[k - 1], rSo));
-      const T knot = add_rn(mul_rn(twoB, co), -B);
-      if (k == bin - 1) { o0 = knot; oc0 = co; }
-      if (k == bin) { o1 = knot; oc1 = co; }
-    }
+  T co = 0, o0 = -B, o1 = -B, oc0 = 0, oc1 = 0;
+  for (int k = 1; k <= bin; ++k) {
+    o0 = o1; oc0 = oc1;
+    co = add_rn(co, mul_rn(eo[k - 1], rSo));
+    o1 = add_rn(mul_rn(twoB, co), -B); oc1 = co;
   }
   if (!INV) { b.x0 = s0; b.x1 = s1; b.cx0 = c0; b.cx1 = c1; b.y0 = o0; b.y1 = o1; b.cy0 = oc0; b.cy1 = oc1; }
   else      { b.y0 = s0; b.y1 = s1; b.cy0 = c0; b.cy1 = c1; b.x0 = o0; b.x1 = o1; b.cx0 = oc0; b.cx1 = oc1; }
-  b.Sw = Sw; b.Sh = Sh;
-  b.d0 = (bin - 1 == 0) ? T(1) : N::log(N::exp(tl[2 * K + bin - 2]) + 1);
-  b.d1 = (bin == K) ? T(1) : N::log(N::exp(tl[2 * K + bin - 1]) + 1);
+  b.d0 = (bin - 1 == 0) ? T(1) : N::log(N::exp(row[2 * K + bin - 2]) + 1);
+  b.d1 = (bin == K) ? T(1) : N::log(N::exp(row[2 * K + bin - 1]) + 1);
 }
 
-// One thread per (sample, transformed coordinate).  The block's 3K-1 logits per thread are one contiguous chunk
-// of theta_raw: staged through shared memory so global traffic is coalesced (row stride 3K-1 is conflict-free).
-// Passthrough columns are copied by a separate coalesced loop.  Dynamic smem: blockDim * (3K-1) * sizeof(T).
+// ---- bulk-copy (TMA 1-D) staging for the spline kernels -------------------------------------------------------
+// A block's tile = blockDim.x consecutive (sample, coordinate) pairs = blockDim.x * (3K-1) contiguous logits: one
+// cp.async.bulk per tile into a ring of shared-memory buffers (mbarrier complete_tx), issued RQS ring-depth - 1 tiles
+// ahead so the HBM latency hides behind the arithmetic of the current tile; gradients leave the same way (bulk store).
+namespace rq {
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void load_tile(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void store_tile(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void wait_stores_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 28)) __trap();   // fail loudly instead of hanging the GPU
+  }
+}
+constexpr int kMaxStages = 4;
+}  // namespace rq
+
+template <typename T, int KMAX, bool INV>
+__device__ __forceinline__ void rqs_apply_row(T* __restrict__ row, int64_t e, const T* __restrict__ Xin, const int* __restrict__ idx1,
+                                              int c, int d, int K, T B, T* __restrict__ Xout, int32_t* __restrict__ bins,
+                                              float& run_max, T& lj_out, int64_t& r_out, int& i_out) {
+  const int64_t r = e / c;
+  const int i = (int)(e - r * c);
+  const int j = idx1[i];
+  const T v = Xin[r * d + j];
+  RqsBin<T> b;
+  rqs_locate_row<T, KMAX, INV>(row, K, B, v, b);
+  if (bins) bins[e] = b.k;
+  T o = v, lj = 0, tmp;
+  if (b.k >= 1 && b.k <= K) { if (!INV) rqs_eval_fwd(b, v, o, lj); else rqs_eval_inv(b, v, o, lj, tmp); }
+  Xout[r * d + j] = o;
+  run_max = fmaxf(run_max, fabsf((float)o));
+  lj_out = lj; r_out = r; i_out = i;
+}
+
+// One thread per (sample, transformed coordinate); tiles of blockDim.x pairs stream through a `stages`-deep ring of
+// shared-memory buffers (see rq:: above).  Passthrough columns are copied by a separate coalesced loop.
+// Dynamic smem: stages * blockDim.x * (3K-1) * sizeof(T).
 template <typename T, int KMAX, bool INV>
 __global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict__ raw, const int* __restrict__ idx1,
                                  const int* __restrict__ pos, int c, int d, int K, T B, int64_t N, T* __restrict__ Xout,
-                                 T* __restrict__ ld, int32_t* __restrict__ bins, float* __restrict__ amax_meta) {
-  extern __shared__ __align__(16) unsigned char rqs_smem[];
-  T* sm = reinterpret_cast<T*>(rqs_smem);
+                                 T* __restrict__ ld, int32_t* __restrict__ bins, float* __restrict__ amax_meta, int stages) {
+  extern __shared__ __align__(128) unsigned char rqs_smem[];
+  __shared__ uint64_t full_bar[rq::kMaxStages];
+  T* tiles = reinterpret_cast<T*>(rqs_smem);
   const int P3 = 3 * K - 1;
+  const int tile_elems = blockDim.x * P3;
+  const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(T));
   const int64_t total = N * c;
+  const int64_t nfull = total / blockDim.x;
   float run_max = 0.f;
-  // passthrough columns
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < stages; ++q) rq::bar_init(rq::s32(&full_bar[q]));
+    rq::bar_fence_init();
+  }
+  __syncthreads();
+  const int64_t n_my = blockIdx.x < nfull ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (threadIdx.x == 0)
+    for (int q = 0; q < stages - 1 && q < n_my; ++q)
+      rq::load_tile(rq::s32(tiles + (size_t)q * tile_elems), raw + (blockIdx.x + (int64_t)q * gridDim.x) * tile_elems, tile_bytes,
+                    rq::s32(&full_bar[q]));
+  // passthrough columns (overlaps the first tiles' flight)
   {
     const int64_t nd = N * d;
     const bool small = nd < ((int64_t)1 << 31);
@@ -431,155 +488,231 @@ __global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict_
       if (pos[j] < 0) { const T x = Xin[e]; Xout[e] = x; run_max = fmaxf(run_max, fabsf((float)x)); }
     }
   }
-  const int64_t nblk = (total + blockDim.x - 1) / blockDim.x;
-  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int64_t e0 = blk * blockDim.x;
-    const int64_t cnt = (total - e0 < blockDim.x ? total - e0 : blockDim.x) * P3;
+  const bool pow2 = (c & (c - 1)) == 0 && c <= 32 && (blockDim.x % c) == 0;
+  for (int64_t it = 0; it < n_my; ++it) {
+    const int buf = (int)(it % stages);
+    const int64_t blk = blockIdx.x + it * gridDim.x;
+    // refill the buffer tile it-1 used (every thread finished with it before the barrier below; the proxy fence orders
+    // the in-place exp() writes before the bulk copy that overwrites them)
+    rq::fence_async();
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) sm[i] = raw[e0 * P3 + i];
-    __syncthreads();
-    const int64_t e = e0 + threadIdx.x;
-    T lj_out = 0; int64_t r_out = 0; int i_out = -1;
-    if (e < total) {
-      T tl[3 * KMAX];
-#pragma unroll
-      for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) tl[k] = sm[threadIdx.x * P3 + k];
-      const int64_t r = e / c;
-      const int i = (int)(e - r * c);
-      const int j = idx1[i];
-      const T v = Xin[r * d + j];
-      RqsLocal<T, KMAX> L;
-      RqsBin<T> b;
-      rqs_locate_cached<T, KMAX, INV>(tl, K, B, v, L, b);
-      if (bins) bins[e] = b.k;
-      T o = v, lj = 0, tmp;
-      if (b.k >= 1 && b.k <= K) { if (!INV) rqs_eval_fwd(b, v, o, lj); else rqs_eval_inv(b, v, o, lj, tmp); }
-      Xout[r * d + j] = o;
-      run_max = fmaxf(run_max, fabsf((float)o));
-      lj_out = lj; r_out = r; i_out = i;
+    if (threadIdx.x == 0 && it + stages - 1 < n_my) {
+      const int nb = (int)((it + stages - 1) % stages);
+      rq::load_tile(rq::s32(tiles + (size_t)nb * tile_elems), raw + (blk + (int64_t)(stages - 1) * gridDim.x) * tile_elems, tile_bytes,
+                    rq::s32(&full_bar[nb]));
     }
+    rq::wait(rq::s32(&full_bar[buf]), (uint32_t)((it / stages) & 1));
+    T lj_out = 0; int64_t r_out = 0; int i_out = -1;
+    const int64_t e = blk * blockDim.x + threadIdx.x;
+    rqs_apply_row<T, KMAX, INV>(tiles + (size_t)buf * tile_elems + threadIdx.x * P3, e, Xin, idx1, c, d, K, B, Xout, bins, run_max,
+                                lj_out, r_out, i_out);
     if (ld) {
-      const bool pow2 = (c & (c - 1)) == 0 && c <= 32 && (blockDim.x % c) == 0;
       if (pow2) {          // the c coordinates of a sample sit in c adjacent lanes: segmented butterfly, one add per sample
         for (int o = c >> 1; o > 0; o >>= 1) lj_out += __shfl_xor_sync(0xffffffffu, lj_out, o);
-        if (e < total && i_out == 0) atomicAdd(&ld[r_out], lj_out);
-      } else if (e < total && lj_out != T(0)) {
+        if (i_out == 0) atomicAdd(&ld[r_out], lj_out);
+      } else if (lj_out != T(0)) {
         atomicAdd(&ld[r_out], lj_out);
       }
+    }
+  }
+  // ragged tail (total % blockDim.x pairs): plain staging by the block whose turn it would be
+  const int rem = (int)(total - nfull * blockDim.x);
+  if (rem > 0 && blockIdx.x == (unsigned)(nfull % gridDim.x)) {
+    __syncthreads();
+    const int64_t e0 = nfull * blockDim.x;
+    for (int i = threadIdx.x; i < rem * P3; i += blockDim.x) tiles[i] = raw[e0 * P3 + i];
+    __syncthreads();
+    if ((int)threadIdx.x < rem) {
+      T lj_out = 0; int64_t r_out = 0; int i_out = -1;
+      rqs_apply_row<T, KMAX, INV>(tiles + threadIdx.x * P3, e0 + threadIdx.x, Xin, idx1, c, d, K, B, Xout, bins, run_max, lj_out, r_out, i_out);
+      if (ld && lj_out != T(0)) atomicAdd(&ld[r_out], lj_out);
     }
   }
   if (amax_meta) amax_update(amax_meta, run_max);
 }
 
+// One row of the backward: turns the thread's private row of logits into its row of gradients in place.
+template <typename T, int KMAX, bool INV>
+__device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t e, T* __restrict__ G, const T* __restrict__ Vsrc,
+                                            const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int K, T B,
+                                            float& run_max) {
+  using Nm = Num<T>;
+  const int P3 = 3 * K - 1;
+  const int64_t r = e / c;
+  const int i = (int)(e - r * c);
+  const int j = idx1[i];
+  const T v = Vsrc[r * d + j];
+  const T go = G[r * d + j];
+  const T gl = gld ? gld[r] : T(1);
+  RqsBin<T> b;
+  rqs_locate_row<T, KMAX, INV>(row, K, B, v, b);
+  if (b.k >= 1 && b.k <= K) {
+    const T dx = b.x1 - b.x0, dy = b.y1 - b.y0;
+    const T idx_ = 1 / dx;
+    const T s = dy * idx_;
+    T x, xi;
+    if (!INV) { x = v; xi = (x - b.x0) * idx_; }
+    else { T lj_; rqs_eval_inv(b, v, x, lj_, xi); }
+    const T om = 1 - xi;
+    const T tt = b.d1 + b.d0 - 2 * s;
+    const T den = s + tt * xi * om;
+    const T iden = 1 / den;
+    const T num = s * xi * xi + b.d0 * xi * om;
+    const T q = b.d1 * xi * xi + 2 * s * xi * om + b.d0 * om * om;
+    const T iq = 1 / q;
+    const T dq_dxi = 2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om;
+    T gy, glj, g_in = 0;
+    if (!INV) { gy = go; glj = gl; }
+    else {
+      // L = go*x - gl*lj(x,p):  dL/dy = (go - gl*lj_x)/F_x =: a,  dL/dp = -a*F_p - gl*lj_p
+      const T lj_xi = dq_dxi * iq - 2 * tt * (om - xi) * iden;
+      const T Fx = s * s * q * iden * iden;
+      const T a = (go - gl * (lj_xi * idx_)) / Fx;
+      gy = -a; glj = -gl; g_in = a;
+    }
+    T g_y0 = gy, g_dy = gy * num * iden;
+    const T g_num = gy * dy * iden;
+    T g_den = -gy * dy * num * iden * iden - 2 * glj * iden;
+    T g_s = 2 * glj / s;
+    const T g_q = glj * iq;
+    T g_d1 = g_q * xi * xi, g_d0 = g_q * om * om;
+    g_s += g_q * 2 * xi * om;
+    T g_xi = g_q * dq_dxi;
+    g_s += g_num * xi * xi; g_d0 += g_num * xi * om; g_xi += g_num * (2 * s * xi + b.d0 * (om - xi));
+    g_s += g_den * (1 - 2 * xi * om); g_d1 += g_den * xi * om; g_d0 += g_den * xi * om; g_xi += g_den * tt * (om - xi);
+    T g_x0 = -g_xi * idx_, g_dx = -g_xi * xi * idx_;
+    if (!INV) g_in = g_xi * idx_;
+    g_dy += g_s * idx_; g_dx += -g_s * s * idx_;
+    const T g_y1 = g_dy; g_y0 -= g_dy;
+    const T g_x1 = g_dx; g_x0 -= g_dx;
+    G[r * d + j] = g_in;
+    const T twoB = 2 * B;
+    const T rSw = 1 / b.Sw, rSh = 1 / b.Sh;
+    const int bk = b.k;
+    {   // knots -> width logits: X_j = 2B c_j - B, c_j = sum_{k<=j} p_k, p = softmax  (row[k] holds exp(logit))
+      const T a0 = (bk - 1 >= 1) ? g_x0 : T(0), a1 = g_x1;
+      const T dotp = twoB * (a0 * b.cx0 + a1 * b.cx1);
+      const T gp0 = (twoB * (a0 + a1) - dotp) * rSw, gp1 = (twoB * a1 - dotp) * rSw, gp2 = -dotp * rSw;
+#pragma unroll
+      for (int k = 1; k <= KMAX; ++k) if (k <= K) {
+        const T gv = row[k - 1] * (k <= bk - 1 ? gp0 : (k <= bk ? gp1 : gp2));
+        row[k - 1] = gv; run_max = fmaxf(run_max, fabsf((float)gv));
+      }
+    }
+    {   // height logits
+      const T a0 = (bk - 1 >= 1) ? g_y0 : T(0), a1 = g_y1;
+      const T dotp = twoB * (a0 * b.cy0 + a1 * b.cy1);
+      const T gp0 = (twoB * (a0 + a1) - dotp) * rSh, gp1 = (twoB * a1 - dotp) * rSh, gp2 = -dotp * rSh;
+#pragma unroll
+      for (int k = 1; k <= KMAX; ++k) if (k <= K) {
+        const T gv = row[K + k - 1] * (k <= bk - 1 ? gp0 : (k <= bk ? gp1 : gp2));
+        row[K + k - 1] = gv; run_max = fmaxf(run_max, fabsf((float)gv));
+      }
+    }
+    T gd0 = 0, gd1 = 0;   // through softplus: d/dlogit log(exp(t)+1) = exp(t)/(exp(t)+1)
+    if (bk - 1 >= 1) { const T ex = Nm::exp(row[2 * K + bk - 2]); gd0 = g_d0 * ex / (ex + 1); }
+    if (bk <= K - 1) { const T ex = Nm::exp(row[2 * K + bk - 1]); gd1 = g_d1 * ex / (ex + 1); }
+    run_max = fmaxf(run_max, fmaxf(fabsf((float)gd0), fabsf((float)gd1)));
+#pragma unroll
+    for (int k = 1; k < KMAX; ++k) if (k < K)
+      row[2 * K + k - 1] = (k == bk - 1) ? gd0 : ((k == bk) ? gd1 : T(0));
+  } else {   // identity tails: dy/dx = 1, no parameter gradient; G unchanged
+#pragma unroll
+    for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) row[k] = 0;
+  }
+}
+
 // Backward of the spline coupling arithmetic: G (in place on idx1 columns) and graw = d/dtheta_raw.
-// Vsrc = the spline input (Xin): x1 for forward, y1 for inverse.  Same staging as rqs_apply_kernel, both ways.
+// Vsrc = the spline input (Xin): x1 for forward, y1 for inverse.  Tiles stream in through the bulk-copy ring, every
+// thread rewrites its private row in place, and the tile streams back out with one bulk store.
+// colsum (optional, needs blockDim % c == 0 and c*(3K-1) <= 4*blockDim): sum over samples of every graw column = the
+// bias gradient of the conditioner's last Dense, accumulated per thread across the block's tiles and flushed once.
 template <typename T, int KMAX, bool INV>
 __global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restrict__ raw,
                                const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int K, T B,
-                               int64_t N, T* __restrict__ graw, float* __restrict__ amax_meta) {
-  using Nm = Num<T>;
-  extern __shared__ __align__(16) unsigned char rqs_smem[];
-  T* sm = reinterpret_cast<T*>(rqs_smem);
+                               int64_t N, T* __restrict__ graw, float* __restrict__ amax_meta, double* __restrict__ colsum,
+                               int stages) {
+  extern __shared__ __align__(128) unsigned char rqs_smem[];
+  __shared__ uint64_t full_bar[rq::kMaxStages];
+  T* tiles = reinterpret_cast<T*>(rqs_smem);
   const int P3 = 3 * K - 1;
+  const int ncol = c * P3;
+  const int tile_elems = blockDim.x * P3;
+  const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(T));
   const int64_t total = N * c;
+  const int64_t nfull = total / blockDim.x;
   float run_max = 0.f;
-  const int64_t nblk = (total + blockDim.x - 1) / blockDim.x;
-  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int64_t e0 = blk * blockDim.x;
-    const int64_t cnt = (total - e0 < blockDim.x ? total - e0 : blockDim.x) * P3;
+  T csum[4] = {0, 0, 0, 0};
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < stages; ++q) rq::bar_init(rq::s32(&full_bar[q]));
+    rq::bar_fence_init();
+  }
+  __syncthreads();
+  const int64_t n_my = blockIdx.x < nfull ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (threadIdx.x == 0)
+    for (int q = 0; q < stages - 1 && q < n_my; ++q)
+      rq::load_tile(rq::s32(tiles + (size_t)q * tile_elems), raw + (blockIdx.x + (int64_t)q * gridDim.x) * tile_elems, tile_bytes,
+                    rq::s32(&full_bar[q]));
+  for (int64_t it = 0; it < n_my; ++it) {
+    const int buf = (int)(it % stages);
+    const int64_t blk = blockIdx.x + it * gridDim.x;
+    T* tile = tiles + (size_t)buf * tile_elems;
+    rq::wait(rq::s32(&full_bar[buf]), (uint32_t)((it / stages) & 1));
+    rqs_bwd_row<T, KMAX, INV>(tile + threadIdx.x * P3, blk * blockDim.x + threadIdx.x, G, Vsrc, gld, idx1, c, d, K, B, run_max);
+    rq::fence_async();       // generic-proxy writes of the rows -> visible to the bulk store
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) sm[i] = raw[e0 * P3 + i];
-    __syncthreads();
-    const int64_t e = e0 + threadIdx.x;
-    T tl[3 * KMAX];
-    if (e < total) {
-#pragma unroll
-      for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) tl[k] = sm[threadIdx.x * P3 + k];
-    }
-    __syncthreads();
-    if (e < total) {
-      T* gw = sm + threadIdx.x * P3;      // this thread's output row, written into the staging tile
-#pragma unroll
-      for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) gw[k] = 0;
-      const int64_t r = e / c;
-      const int i = (int)(e - r * c);
-      const int j = idx1[i];
-      const T v = Vsrc[r * d + j];
-      const T go = G[r * d + j];
-      const T gl = gld ? gld[r] : T(1);
-      RqsLocal<T, KMAX> L;
-      RqsBin<T> b;
-      rqs_locate_cached<T, KMAX, INV>(tl, K, B, v, L, b);
-      if (b.k >= 1 && b.k <= K) {   // identity tails: dy/dx = 1, no parameter gradient; G unchanged
-        const T dx = b.x1 - b.x0, dy = b.y1 - b.y0;
-        const T s = dy / dx;
-        T x, xi;
-        if (!INV) { x = v; xi = (x - b.x0) / dx; }
-        else { T lj_; rqs_eval_inv(b, v, x, lj_, xi); }
-        const T om = 1 - xi;
-        const T tt = b.d1 + b.d0 - 2 * s;
-        const T den = s + tt * xi * om;
-        const T num = s * xi * xi + b.d0 * xi * om;
-        const T q = b.d1 * xi * xi + 2 * s * xi * om + b.d0 * om * om;
-        const T lj_xi = (2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om) / q - 2 * tt * (om - xi) / den;
-        T gy, glj, g_in = 0;
-        if (!INV) { gy = go; glj = gl; }
-        else {
-          // L = go*x - gl*lj(x,p):  dL/dy = (go - gl*lj_x)/F_x =: a,  dL/dp = -a*F_p - gl*lj_p
-          const T Fx = s * s * q / (den * den);
-          const T a = (go - gl * (lj_xi / dx)) / Fx;
-          gy = -a; glj = -gl; g_in = a;
-        }
-        T g_y0 = gy, g_dy = gy * num / den;
-        const T g_num = gy * dy / den;
-        T g_den = -gy * dy * num / (den * den) - 2 * glj / den;
-        T g_s = 2 * glj / s;
-        const T g_q = glj / q;
-        T g_d1 = g_q * xi * xi, g_d0 = g_q * om * om;
-        g_s += g_q * 2 * xi * om;
-        T g_xi = g_q * (2 * b.d1 * xi + 2 * s * (om - xi) - 2 * b.d0 * om);
-        g_s += g_num * xi * xi; g_d0 += g_num * xi * om; g_xi += g_num * (2 * s * xi + b.d0 * (om - xi));
-        g_s += g_den * (1 - 2 * xi * om); g_d1 += g_den * xi * om; g_d0 += g_den * xi * om; g_xi += g_den * tt * (om - xi);
-        T g_x0 = -g_xi / dx, g_dx = -g_xi * xi / dx;
-        if (!INV) g_in = g_xi / dx;
-        g_dy += g_s / dx; g_dx += -g_s * s / dx;
-        const T g_y1 = g_dy; g_y0 -= g_dy;
-        const T g_x1 = g_dx; g_x0 -= g_dx;
-        G[r * d + j] = g_in;
-        const T twoB = 2 * B;
-        const T rSw = 1 / L.Sw, rSh = 1 / L.Sh;
-        {   // knots -> width logits: X_j = 2B c_j - B, c_j = sum_{k<=j} p_k, p = softmax
-          const T a0 = (b.k - 1 >= 1) ? g_x0 : T(0), a1 = g_x1;
-          const T dotp = twoB * (a0 * b.cx0 + a1 * b.cx1);
-#pragma unroll
-          for (int k = 1; k <= KMAX; ++k) if (k <= K) {
-            const T p = L.ew[k - 1] * rSw;
-            const T gp = twoB * ((k <= b.k - 1 ? a0 : T(0)) + (k <= b.k ? a1 : T(0)));
-            gw[k - 1] = p * (gp - dotp);
-          }
-        }
-        {   // height logits
-          const T a0 = (b.k - 1 >= 1) ? g_y0 : T(0), a1 = g_y1;
-          const T dotp = twoB * (a0 * b.cy0 + a1 * b.cy1);
-#pragma unroll
-          for (int k = 1; k <= KMAX; ++k) if (k <= K) {
-            const T p = L.eh[k - 1] * rSh;
-            const T gp = twoB * ((k <= b.k - 1 ? a0 : T(0)) + (k <= b.k ? a1 : T(0)));
-            gw[K + k - 1] = p * (gp - dotp);
-          }
-        }
-        if (b.k - 1 >= 1) { const T ex = Nm::exp(tl[2 * K + b.k - 2]); gw[2 * K + b.k - 2] = g_d0 * ex / (ex + 1); }
-        if (b.k <= K - 1) { const T ex = Nm::exp(tl[2 * K + b.k - 1]); gw[2 * K + b.k - 1] = g_d1 * ex / (ex + 1); }
+    if (threadIdx.x == 0) {
+      rq::store_tile(graw + blk * tile_elems, rq::s32(tile), tile_bytes);
+      if (it + stages - 1 < n_my) {
+        // the buffer of tile it-1 is next in the ring: its store must have finished reading shared memory (every
+        // thread's column-sum reads of it completed before the barrier above)
+        rq::wait_stores_read<1>();
+        const int nb = (int)((it + stages - 1) % stages);
+        rq::load_tile(rq::s32(tiles + (size_t)nb * tile_elems), raw + (blk + (int64_t)(stages - 1) * gridDim.x) * tile_elems, tile_bytes,
+                      rq::s32(&full_bar[nb]));
       }
     }
+    if (colsum) {   // the tile is whole samples: blockDim / c rows of ncol columns
+      const int rows = tile_elems / ncol;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int col = threadIdx.x + q * blockDim.x;
+        if (col < ncol) {
+          T sacc = 0;
+          for (int rr = 0; rr < rows; ++rr) sacc += tile[rr * ncol + col];
+          csum[q] += sacc;
+        }
+      }
+    }
+  }
+  if (threadIdx.x == 0) rq::wait_stores_read<0>();
+  // ragged tail (total % blockDim.x pairs): plain staging by the block whose turn it would be
+  const int rem = (int)(total - nfull * blockDim.x);
+  if (rem > 0 && blockIdx.x == (unsigned)(nfull % gridDim.x)) {
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const T gv = sm[i];
-      graw[e0 * P3 + i] = gv;
-      run_max = fmaxf(run_max, fabsf((float)gv));
+    const int64_t e0 = nfull * blockDim.x;
+    for (int i = threadIdx.x; i < rem * P3; i += blockDim.x) tiles[i] = raw[e0 * P3 + i];
+    __syncthreads();
+    if ((int)threadIdx.x < rem) rqs_bwd_row<T, KMAX, INV>(tiles + threadIdx.x * P3, e0 + threadIdx.x, G, Vsrc, gld, idx1, c, d, K, B, run_max);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rem * P3; i += blockDim.x) graw[e0 * P3 + i] = tiles[i];
+    if (colsum) {
+      const int rows = rem * P3 / ncol;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int col = threadIdx.x + q * blockDim.x;
+        if (col < ncol) for (int rr = 0; rr < rows; ++rr) csum[q] += tiles[rr * ncol + col];
+      }
     }
   }
   if (amax_meta) amax_update(amax_meta, run_max);
+  if (colsum) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = threadIdx.x + q * blockDim.x;
+      if (col < ncol) atomicAdd(&colsum[col], (double)csum[q]);
+    }
+  }
 }
 
 template <typename T>

@@ -2,6 +2,7 @@
 #include "flow.hpp"
 #include "general.hpp"
 #include "tc_gemm.hpp"
+#include <chrono>
 #include <cstring>
 #include <mutex>
 
@@ -233,7 +234,7 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
   NF_CUDA(cudaMalloc(&f->d_theta, (f->P + 1) * es));
   NF_CUDA(cudaMalloc((void**)&f->d_gsum, (f->P + 1) * sizeof(double)));
   NF_CUDA(cudaMalloc(&f->d_out, (f->P + 1) * es));
-  f->h_pinned_bytes = (f->P + 1) * es + 64;
+  f->h_pinned_bytes = (((f->P + 1) * es + 15) / 16) * 16 + 64;
   NF_CUDA(cudaMallocHost(&f->h_pinned, f->h_pinned_bytes));
   NF_TRY(f->ws_reserve((size_t)8 << 20));
   *out = reinterpret_cast<nf_flow_t>(f.release());
@@ -300,23 +301,41 @@ static int scale_outputs(Flow& f, double factor, void* out_dev, int64_t n) {
 }
 
 // value+grad with everything already on the device
+// NFCUDA_TRACE_HOST=<ms>: report calls whose host wall time exceeds the device time by more than <ms> (where the host
+// thread was held up: planning, enqueue, or the final wait).
+struct HostTrace {
+  double thr = -1;
+  std::chrono::steady_clock::time_point t[5];
+  HostTrace() { if (const char* e = getenv("NFCUDA_TRACE_HOST")) thr = atof(e); }
+  void mark(int i) { if (thr >= 0) t[i] = std::chrono::steady_clock::now(); }
+  double ms(int a, int b) const { return std::chrono::duration<double, std::milli>(t[b] - t[a]).count(); }
+};
+static HostTrace g_trace;
+
 static int value_and_grad_dev(Flow& f, int op, const Target* tgt, const void* theta_dev, int64_t N, const void* in_dev,
                               uint64_t seed, double scale, double* value_out, void* grad_dev_out) {
   Job j;
   j.op = op; j.tgt = tgt; j.theta_dev = theta_dev; j.in_dev = in_dev; j.N = N; j.seed = seed;
   j.want_grad = grad_dev_out != nullptr;
+  g_trace.mark(1);
   NF_CUDA(cudaEventRecord(f.ev0, f.stream));
   NF_TRY(run_job(f, j));
   const double factor = scale / (double)N;
   if (grad_dev_out) NF_TRY(scale_outputs(f, factor, grad_dev_out, f.P));
   NF_CUDA(cudaEventRecord(f.ev1, f.stream));
-  double vsum = 0;
-  NF_CUDA(cudaMemcpyAsync(&vsum, f.d_gsum + f.P, sizeof(double), cudaMemcpyDeviceToHost, f.stream));
+  // the objective sum comes back through the pinned staging buffer (a pageable destination would make the copy synchronous)
+  double* vsum = reinterpret_cast<double*>((char*)f.h_pinned + f.h_pinned_bytes - 16);
+  NF_CUDA(cudaMemcpyAsync(vsum, f.d_gsum + f.P, sizeof(double), cudaMemcpyDeviceToHost, f.stream));
+  g_trace.mark(2);
   NF_CUDA(cudaStreamSynchronize(f.stream));
+  g_trace.mark(3);
   float ms = 0;
   cudaEventElapsedTime(&ms, f.ev0, f.ev1);
   f.last_ms = ms;
-  if (value_out) *value_out = vsum * factor;
+  if (value_out) *value_out = *vsum * factor;
+  if (g_trace.thr >= 0 && g_trace.ms(0, 3) - ms > g_trace.thr)
+    fprintf(stderr, "[nfcuda host trace] plan %.2f ms, enqueue %.2f ms, wait %.2f ms, device %.2f ms\n", g_trace.ms(0, 1),
+            g_trace.ms(1, 2), g_trace.ms(2, 3), (double)ms);
   return NF_OK;
 }
 
@@ -324,6 +343,7 @@ static int value_and_grad_host(Flow& f, int op, const Target* tgt, const void* t
                                uint64_t seed, double scale, double* value_out, void* grad_host_out) {
   NF_REQUIRE(theta_host, "theta is null");
   NF_REQUIRE(N > 0, "N must be positive");
+  g_trace.mark(0);
   NF_CUDA(cudaSetDevice(f.device));
   const size_t es = f.esize();
   f.ws_reset();
@@ -542,6 +562,7 @@ int nf_elbo_value_and_grad_dev(nf_flow_t flow, nf_target_t target, const void* t
   const Target* t = reinterpret_cast<Target*>(target);
   NF_TRY(check_target(f, t));
   NF_REQUIRE(theta_dev, "theta is null");
+  g_trace.mark(0);
   NF_CUDA(cudaSetDevice(f.device));
   f.ws_reset();
   NF_TRY(general_plan_workspace(f, OP_ELBO, N, 0));

@@ -498,26 +498,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
               *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_float4(o4[0], o4[1], o4[2], o4[3]);
             }
             __syncwarp();
+            const int cq = cc0 + (lane & 3) * 4;
+            if (p.epi == EPI_F32_ACT) {
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-              const int rr = ps * 8 + (lane >> 2);
-              const int cq = cc0 + (lane & 3) * 4;
-              const float4 val = *reinterpret_cast<const float4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
-              const int64_t grow = row_base + rr;
-              if (grow < p.M) {
-                const float vv[4] = {val.x, val.y, val.z, val.w};
-                if (p.epi == EPI_F32_ACT) {
+              for (int ps = 0; ps < 4; ++ps) {
+                const int rr = ps * 8 + (lane >> 2);
+                const float4 val = *reinterpret_cast<const float4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+                const int64_t grow = row_base + rr;
+                if (grow < p.M) {
+                  const float vv[4] = {val.x, val.y, val.z, val.w};
                   float* o = p.out_f32 + grow * p.out_f32_ld + cq;
                   if (cq + 3 < p.n_store && (p.out_f32_ld & 3) == 0) *reinterpret_cast<float4*>(o) = val;
                   else {
 #pragma unroll
                     for (int u = 0; u < 4; ++u) if (cq + u < p.n_store) o[u] = vv[u];
                   }
-                } else {  // EPI_SCATTER_ADD: G[row, idx[col]] += v
-                  float* g = p.G + grow * p.ldg;
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) if (cq + u < p.n_store) g[p.idx[cq + u]] += vv[u];
                 }
+              }
+            } else {  // EPI_SCATTER_ADD: G[row, idx[col]] += v.  idx is injective, so the 16 read-modify-writes of a lane are
+                      // independent: all loads are issued before the first store (one HBM round trip instead of sixteen)
+              int ci[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) ci[u] = (cq + u < p.n_store) ? p.idx[cq + u] : -1;
+              float old[4][4], add[4][4];
+#pragma unroll
+              for (int ps = 0; ps < 4; ++ps) {
+                const int rr = ps * 8 + (lane >> 2);
+                const int64_t grow = row_base + rr;
+                const float4 val = *reinterpret_cast<const float4*>(stg + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+                add[ps][0] = val.x; add[ps][1] = val.y; add[ps][2] = val.z; add[ps][3] = val.w;
+                const float* g = p.G + grow * p.ldg;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) old[ps][u] = (grow < p.M && ci[u] >= 0) ? __ldcg(g + ci[u]) : 0.f;
+              }
+#pragma unroll
+              for (int ps = 0; ps < 4; ++ps) {
+                const int64_t grow = row_base + ps * 8 + (lane >> 2);
+                float* g = p.G + grow * p.ldg;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (grow < p.M && ci[u] >= 0) g[ci[u]] = old[ps][u] + add[ps][u];
               }
             }
             __syncwarp();
@@ -697,44 +716,91 @@ __global__ void absmax_kernel(const float* __restrict__ X, int d, const int* __r
   if ((threadIdx.x & 31) == 0) meta_amax(meta, m);
 }
 
-// planes [rows_pad, ld]: hi plane then lo plane (+plane_elems); one thread per pair of adjacent columns.
-// amax_src[1] bounds max |X|; meta receives the scale and the same bound for downstream layers.
-template <typename I>
-__global__ void gather_split_kernel(const float* __restrict__ X, int d, const int* __restrict__ idx, int n_idx, int64_t n,
-                                    __half* __restrict__ out, int ld, int64_t plane_elems, const float* __restrict__ amax_src,
-                                    float* __restrict__ meta) {
-  const I e = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x;
+// fp32 rows -> fp16 hi/lo planes [rows_pad, ld] (hi plane, then lo plane at +plane_elems), optionally gathering columns.
+// A thread owns one pair of adjacent plane columns and walks rows grid-stride (column indices hoisted, float2 loads when
+// there is no gather); amax_src[1] bounds max |X|, meta receives the scale and the same bound for downstream layers.
+// colsum (no-gather use): per-column sums of the unscaled input over all rows = bias gradient of the Dense whose
+// pre-activation gradient X is; accumulated per thread, reduced over the block's row lanes, one double atomic per column.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ X, int d, const int* __restrict__ idx, int n_idx,
+                                                         int64_t n, __half* __restrict__ out, int ld, int64_t plane_elems,
+                                                         const float* __restrict__ amax_src, float* __restrict__ meta,
+                                                         double* __restrict__ colsum) {
+  __shared__ float red[512];
+  const int half_ld = ld >> 1;
+  const int tx = threadIdx.x % half_ld, ty = threadIdx.x / half_ld, RY = blockDim.x / half_ld;
   const unsigned int abits = reinterpret_cast<const unsigned int*>(amax_src)[1];
   const float s = pow2_scale(__uint_as_float(abits));
-  if (e == 0) { meta[0] = s; reinterpret_cast<unsigned int*>(meta)[1] = abits; }
-  const I half_ld = (I)(ld >> 1);
-  if (e >= (I)n * half_ld) return;
-  const I r = e / half_ld;
-  const int k = (int)(e - r * half_ld) * 2;
-  float v0 = 0.f, v1 = 0.f;
-  const float* xr = X + (int64_t)r * d;
-  if (k < n_idx) v0 = (idx ? xr[idx[k]] : xr[k]) * s;
-  if (k + 1 < n_idx) v1 = (idx ? xr[idx[k + 1]] : xr[k + 1]) * s;
-  uint32_t hi, lo;
-  split_pair(v0, v1, hi, lo);
-  const int64_t o = (int64_t)r * ld + k;
-  *reinterpret_cast<uint32_t*>(out + o) = hi;
-  *reinterpret_cast<uint32_t*>(out + plane_elems + o) = lo;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { meta[0] = s; reinterpret_cast<unsigned int*>(meta)[1] = abits; }
+  const int k = 2 * tx;
+  int c0 = -1, c1 = -1;
+  if (k < n_idx) c0 = idx ? idx[k] : k;
+  if (k + 1 < n_idx) c1 = idx ? idx[k + 1] : k + 1;
+  const bool vec = !idx && (d & 1) == 0 && c1 >= 0;
+  float a0 = 0.f, a1 = 0.f;
+  const int64_t step = (int64_t)gridDim.x * RY;
+#pragma unroll 4
+  for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += step) {
+    const float* xr = X + r * d;
+    float v0 = 0.f, v1 = 0.f;
+    if (vec) { const float2 t = *reinterpret_cast<const float2*>(xr + k); v0 = t.x; v1 = t.y; }
+    else { if (c0 >= 0) v0 = xr[c0]; if (c1 >= 0) v1 = xr[c1]; }
+    a0 += v0; a1 += v1;
+    uint32_t hi, lo;
+    split_pair(v0 * s, v1 * s, hi, lo);
+    const int64_t o = r * ld + k;
+    *reinterpret_cast<uint32_t*>(out + o) = hi;
+    *reinterpret_cast<uint32_t*>(out + plane_elems + o) = lo;
+  }
+  if (colsum) {
+    red[2 * threadIdx.x] = a0; red[2 * threadIdx.x + 1] = a1;
+    __syncthreads();
+    if (ty == 0) {
+      for (int q = 1; q < RY; ++q) { a0 += red[2 * (q * half_ld + tx)]; a1 += red[2 * (q * half_ld + tx) + 1]; }
+      if (c0 >= 0) atomicAdd(&colsum[c0], (double)a0);
+      if (c1 >= 0) atomicAdd(&colsum[c1], (double)a1);
+    }
+  }
 }
 
-__global__ void plane_colsum_kernel(const __half* __restrict__ P, int ld, int64_t plane_elems, int64_t n, int ncols,
-                                    int64_t rows_per_block, int use_lo, const float* __restrict__ meta, double* __restrict__ out) {
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
-  const float inv = 1.f / meta[0];
-  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
-    float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      float v = __half2float(P[r * ld + c]);
-      if (use_lo) v += __half2float(P[plane_elems + r * ld + c]);
-      s += v;
+// Same job for ungathered inputs whose width is a multiple of 4: a thread owns four adjacent columns (one 16-byte load,
+// two 8-byte plane stores per row), which doubles the bytes in flight per thread -- the wide case (the spline
+// conditioner's [N, (3K-1)c] gradient) is purely HBM-latency bound otherwise.
+__global__ void __launch_bounds__(256) split_rows4_kernel(const float* __restrict__ X, int ncols, int64_t n, __half* __restrict__ out,
+                                                          int ld, int64_t plane_elems, const float* __restrict__ amax_src,
+                                                          float* __restrict__ meta, double* __restrict__ colsum) {
+  __shared__ float red[1024];
+  const int qld = ld >> 2;
+  const int tx = threadIdx.x % qld, ty = threadIdx.x / qld, RY = blockDim.x / qld;
+  const unsigned int abits = reinterpret_cast<const unsigned int*>(amax_src)[1];
+  const float s = pow2_scale(__uint_as_float(abits));
+  if (blockIdx.x == 0 && threadIdx.x == 0) { meta[0] = s; reinterpret_cast<unsigned int*>(meta)[1] = abits; }
+  const int k = 4 * tx;
+  const bool live = k < ncols;          // ncols % 4 == 0: a quad is all live or all padding
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int64_t step = (int64_t)gridDim.x * RY;
+#pragma unroll 4
+  for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += step) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) v = *reinterpret_cast<const float4*>(X + r * ncols + k);
+    a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+    uint2 hi, lo;
+    split_pair(v.x * s, v.y * s, hi.x, lo.x);
+    split_pair(v.z * s, v.w * s, hi.y, lo.y);
+    const int64_t o = r * ld + k;
+    *reinterpret_cast<uint2*>(out + o) = hi;
+    *reinterpret_cast<uint2*>(out + plane_elems + o) = lo;
+  }
+  if (colsum) {
+    red[4 * threadIdx.x] = a0; red[4 * threadIdx.x + 1] = a1; red[4 * threadIdx.x + 2] = a2; red[4 * threadIdx.x + 3] = a3;
+    __syncthreads();
+    if (ty == 0 && live) {
+      for (int q = 1; q < RY; ++q) {
+        const float* p = red + 4 * (q * qld + tx);
+        a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3];
+      }
+      atomicAdd(&colsum[k], (double)a0); atomicAdd(&colsum[k + 1], (double)a1);
+      atomicAdd(&colsum[k + 2], (double)a2); atomicAdd(&colsum[k + 3], (double)a3);
     }
-    atomicAdd(&out[c], (double)(s * inv));
   }
 }
 
@@ -1081,7 +1147,8 @@ inline Planes planes_of(void* buf, int64_t n, int width) { return Planes{(__half
 // fp32 [n, ld_src] (optionally gathered columns) -> split planes.  The scale comes from `amax_src` (a bound on
 // max |X| recorded by the producer of X) when given, else from an exact absmax pass.
 int split_into_planes(Flow& f, TcState* st, const float* X, int d, const int* d_idx, int n_idx, int64_t n, void* buf,
-                      const float* amax_src) {
+                      const float* amax_src, double* colsum = nullptr) {
+  NF_REQUIRE(!(colsum && d_idx), "split_into_planes: column sums are for ungathered inputs");
   Planes P = planes_of(buf, n, n_idx);
   float* meta = new_meta(st, buf);
   NF_REQUIRE(meta, "tcgen05 path: out of tensor metadata slots");
@@ -1091,11 +1158,18 @@ int split_into_planes(Flow& f, TcState* st, const float* X, int d, const int* d_
     NF_LAUNCH_CHECK();
     amax_src = meta;
   }
-  const int64_t pairs = n * (P.ld / 2);
-  if (pairs < (int64_t)1 << 31)
-    gather_split_kernel<int><<<(unsigned)ceil_div(pairs, 256), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, P.p, P.ld, P.plane_elems(), amax_src, meta);
-  else
-    gather_split_kernel<int64_t><<<(unsigned)ceil_div(pairs, 256), 256, 0, f.stream>>>(X, d, d_idx, n_idx, n, P.p, P.ld, P.plane_elems(), amax_src, meta);
+  if (!d_idx && d == n_idx && (n_idx & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    const int qld = P.ld / 4;
+    const int ry = std::max(1, 256 / qld);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, ry), 8 * kNumSMs);
+    split_rows4_kernel<<<grid, qld * ry, 0, f.stream>>>(X, n_idx, n, P.p, P.ld, P.plane_elems(), amax_src, meta, colsum);
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+  }
+  const int half_ld = P.ld / 2;
+  const int ry = std::max(1, 256 / half_ld);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, ry), 8 * kNumSMs);
+  split_rows_kernel<<<grid, half_ld * ry, 0, f.stream>>>(X, d, d_idx, n_idx, n, P.p, P.ld, P.plane_elems(), amax_src, meta, colsum);
   NF_LAUNCH_CHECK();
   return NF_OK;
 }
@@ -1199,7 +1273,7 @@ int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, s
 }
 
 int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts, float* g_last,
-                    const float* g_last_amax, void* scratch0, void* scratch1, float* G, double* gsum) {
+                    const float* g_last_amax, void* scratch0, void* scratch1, float* G, double* gsum, bool last_bias_done) {
   TcState* st = get_state(f);
   const int li = (int)(&Ld - f.layers.data());
   const MLPDesc& md = Ld.mlps[m];
@@ -1208,12 +1282,9 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
   void* gbuf = scratch0;
   void* gnext = scratch1;
   // gradient w.r.t. the last pre-activation -> split planes
-  NF_TRY(split_into_planes(f, st, g_last, md.dims[nd], nullptr, md.dims[nd], n, gbuf, g_last_amax));
-  {  // bias gradient of the last Dense straight from the fp32 gradient
-    const int64_t rpb = 4096;
-    colsum_atomic_kernel<float><<<(unsigned)ceil_div(n, rpb), 256, 0, f.stream>>>(g_last, n, md.dims[nd], rpb, gsum + md.b_off[nd - 1]);
-    NF_LAUNCH_CHECK();
-  }
+  // ... and, in the same pass, the bias gradient of the last Dense (column sums of the fp32 gradient)
+  NF_TRY(split_into_planes(f, st, g_last, md.dims[nd], nullptr, md.dims[nd], n, gbuf, g_last_amax,
+                           last_bias_done ? nullptr : gsum + md.b_off[nd - 1]));
   for (int i = nd - 1; i >= 0; --i) {
     const int pi = st->index[li][m][i];
     const DensePrep& dp = st->preps[pi];

@@ -21,7 +21,7 @@ int tc_absmax(Flow& f, const float* X, int64_t count, float* meta);
 int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts);
 // g_last: fp32 [n, out] gradient w.r.t. the last Dense's pre-activation; scratch0/1: activation-sized buffers
 int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts, float* g_last,
-                    const float* g_last_amax, void* scratch0, void* scratch1, float* G, double* gsum);
+                    const float* g_last_amax, void* scratch0, void* scratch1, float* G, double* gsum, bool last_bias_done = false);
 void tc_release(Flow& f);
 int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* Wt_host, const float* b_host, int terms,
                      float* Y_host);
