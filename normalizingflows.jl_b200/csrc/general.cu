@@ -245,8 +245,18 @@ int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, i
     for (size_t m = 0; m < Ld.mlps.size(); ++m) NF_TRY(simt_mlp_forward<T>(f, Ld.mlps[m], theta, n, (const T*)b.act0, b.acts[m]));
   }
   if (Ld.kind == NF_AFFINE_COUPLING) {
-    affine_apply_kernel<T, INV><<<(unsigned)std::min<int64_t>(ceil_div(n * d, 256), 16 * kNumSMs), 256, 0, f.stream>>>(
-        Xin, (const T*)b.acts[0].back(), (const T*)b.acts[1].back(), Ld.d_pos, c, d, n, Xout, ld, amax_out);
+    const T* Sv = (const T*)b.acts[0].back();
+    const T* Tv = (const T*)b.acts[1].back();
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, 8), 8 * kNumSMs);
+    f.prof.begin("affine_apply", f.stream);
+    if (d <= 32) affine_apply_rows_kernel<T, INV, 1><<<grid, 256, 0, f.stream>>>(Xin, Sv, Tv, Ld.d_pos, c, d, n, Xout, ld, amax_out);
+    else if (d <= 64) affine_apply_rows_kernel<T, INV, 2><<<grid, 256, 0, f.stream>>>(Xin, Sv, Tv, Ld.d_pos, c, d, n, Xout, ld, amax_out);
+    else if (d <= 128) affine_apply_rows_kernel<T, INV, 4><<<grid, 256, 0, f.stream>>>(Xin, Sv, Tv, Ld.d_pos, c, d, n, Xout, ld, amax_out);
+    else if (d <= 256) affine_apply_rows_kernel<T, INV, 8><<<grid, 256, 0, f.stream>>>(Xin, Sv, Tv, Ld.d_pos, c, d, n, Xout, ld, amax_out);
+    else
+      affine_apply_kernel<T, INV><<<(unsigned)std::min<int64_t>(ceil_div(n * d, 256), 16 * kNumSMs), 256, 0, f.stream>>>(
+          Xin, Sv, Tv, Ld.d_pos, c, d, n, Xout, ld, amax_out);
+    f.prof.end(f.stream);
   } else {
     const RqsLaunch rl = rqs_launch_shape<T>(Ld.K, n * c);
     const T* raw = (const T*)b.acts[0].back();

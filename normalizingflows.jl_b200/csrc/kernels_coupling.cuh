@@ -221,6 +221,68 @@ __global__ void affine_apply_kernel(const T* __restrict__ Xin, const T* __restri
   if (amax_meta) amax_update(amax_meta, run_max);
 }
 
+// Row-oriented version for d <= 256 (every practical coupling flow): a warp owns R rows at a time, lane l handles columns
+// l, l+32, ... so the mask lookup is loop-invariant, every access is a contiguous 128-byte segment, the logdet of a row is
+// ONE warp reduction and a plain (non-atomic) update, and there is no per-element index arithmetic.
+template <typename T, bool INV, int JMAX>
+__global__ void __launch_bounds__(256, 3) affine_apply_rows_kernel(const T* __restrict__ Xin, const T* __restrict__ S,
+                                                                const T* __restrict__ Tt, const int* __restrict__ pos, int c, int d,
+                                                                int64_t N, T* __restrict__ Xout, T* __restrict__ ld,
+                                                                float* __restrict__ amax_meta) {
+  constexpr int R0 = JMAX <= 2 ? 4 : (JMAX <= 4 ? 2 : 1);
+  constexpr int R = (sizeof(T) == 8 && R0 > 1) ? R0 / 2 : R0;   // rows in flight per warp
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int kk[JMAX];
+#pragma unroll
+  for (int jj = 0; jj < JMAX; ++jj) { const int j = lane + 32 * jj; kk[jj] = j < d ? pos[j] : -2; }
+  float run_max = 0.f;
+  for (int64_t r0 = warp * R; r0 < N; r0 += nwarps * R) {
+    T x[R][JMAX], sv[R][JMAX], tv[R][JMAX];
+    // lane q < R owns row q's logdet slot: fetched with the other loads so the update is not a second HBM round trip
+    const bool ld_owner = ld && lane < R && r0 + lane < N;
+    const T ldv = ld_owner ? ld[r0 + lane] : T(0);
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int64_t r = r0 + q;
+#pragma unroll
+      for (int jj = 0; jj < JMAX; ++jj) {
+        x[q][jj] = 0; sv[q][jj] = 0; tv[q][jj] = 0;
+        if (r < N && kk[jj] >= -1) x[q][jj] = Xin[r * d + lane + 32 * jj];
+        if (r < N && kk[jj] >= 0) { sv[q][jj] = S[r * c + kk[jj]]; tv[q][jj] = Tt[r * c + kk[jj]]; }
+      }
+    }
+    T sum[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int64_t r = r0 + q;
+      sum[q] = 0;
+#pragma unroll
+      for (int jj = 0; jj < JMAX; ++jj) {
+        T y = x[q][jj];
+        if (kk[jj] >= 0) {
+          y = INV ? (x[q][jj] - tv[q][jj]) * Num<T>::exp(-sv[q][jj]) : Num<T>::exp(sv[q][jj]) * x[q][jj] + tv[q][jj];
+          sum[q] += INV ? -sv[q][jj] : sv[q][jj];
+        }
+        if (r < N && kk[jj] >= -1) {
+          Xout[r * d + lane + 32 * jj] = y;
+          run_max = fmaxf(run_max, fabsf((float)y));
+        }
+      }
+    }
+    if (ld) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) sum[q] = warp_sum(sum[q]);
+      T mine = sum[0];
+#pragma unroll
+      for (int q = 1; q < R; ++q) if (lane == q) mine = sum[q];
+      if (ld_owner) ld[r0 + lane] = ldv + mine;
+    }
+  }
+  if (amax_meta) amax_update(amax_meta, run_max);
+}
+
 // Backward of the coupling arithmetic.  In: G = d/dXout (in place -> d/dXin on idx1 columns; the idx2
 // columns receive the conditioner contribution later), gld = d/dlogdet per sample (nullptr -> 1).
 // Out: gS = gradient w.r.t. the PRE-tanh output of the s network, gT = gradient w.r.t. t.
