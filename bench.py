@@ -159,6 +159,16 @@ def run_side_config(args):
     elif cfg in ("c4", "c4b"):
         nl = 4 if cfg == "c4" else 8
         flow, tgt, n, name = nf.nsf(nf.MvNormal(np.zeros(16)), [32, 32], 10, 5.0, nl, np.float32), nf.Cross(2.0, 0.15, 16), 1 << 20, "NSF d=16 K=10 B=5 [32,32] %d couplings Cross x8 N=2^20" % (2 * nl)
+    elif cfg == "c4ll":
+        flow, tgt, n, name = nf.nsf(nf.MvNormal(np.zeros(16)), [32, 32], 10, 5.0, 4, np.float32), None, 1 << 20, "NSF d=16 K=10 B=5 [32,32] 8 couplings, forward-KL loglikelihood value+grad on exact Cross x8 samples, N=2^20"
+    elif cfg == "c3b":
+        nf.seed(123)
+        flow, tgt, n, name = nf.realnvp(nf.MvNormal(np.zeros(DIM)), HDIMS, 8, np.float32), nf.Funnel(DIM), 1 << 20, "RealNVP d=64 16 couplings (nlayers=8) 2x256 Funnel N=2^20"
+    elif cfg in ("c5", "c5f64"):
+        import math
+        inner = nf.Funnel(2, -8.0, 5.0)
+        dt_ = np.float64 if cfg == "c5f64" else np.float32
+        flow, tgt, n, name = nf.hamiltonian_flow(inner, 15, 3, math.log(0.05), dt_), nf.JointTarget(inner), 1 << 20, "Hamiltonian flow 15 x (momentum affine + LeapFrog L=3) on Funnel(2,-8,5) + N(0,I) momentum, %s, N=2^20" % dt_.__name__
     elif cfg == "c3x1":
         flow, tgt, n, name = make_theta(nf), nf.Funnel(DIM), 1 << 20, "RealNVP C3 in NF_MMA_F16X1 (single fp16 pass, NOT parity grade)"
         flow.set_mma_mode(nf.NF_MMA_F16X1)
@@ -167,15 +177,26 @@ def run_side_config(args):
     n = args.batch if args.batch != BATCH_PER_GPU else n
     dev = torch.device("cuda", 0)
     d = flow.dim
+    tdt = torch.float64 if flow.paramtype == np.float64 else torch.float32
     theta_dev = torch.from_numpy(flow.theta).to(dev)
-    z0 = torch.randn((n, d), device=dev, dtype=torch.float32)
-    grad = torch.empty(flow.num_params, device=dev, dtype=torch.float32)
+    z0 = torch.randn((n, d), device=dev, dtype=tdt)
+    if cfg == "c4ll":   # exact samples of the product of 8 Cross(2, 0.15) blocks (reference example/targets/cross.jl:30-38)
+        comp = torch.randint(0, 4, (n, d // 2), device=dev)
+        mu, sg = 2.0, 0.15
+        mx = torch.tensor([0.0, -mu, mu, 0.0], device=dev)[comp]; my = torch.tensor([mu, 1.0, 1.0, -mu], device=dev)[comp]
+        sx = torch.tensor([sg, 1.0, 1.0, sg], device=dev)[comp]; sy = torch.tensor([1.0, sg, sg, 1.0], device=dev)[comp]
+        z0 = torch.stack([mx + sx * z0[:, 0::2], my + sy * z0[:, 1::2]], dim=2).reshape(n, d).contiguous()
+    grad = torch.empty(flow.num_params, device=dev, dtype=tdt)
     val = C.c_double()
     torch.cuda.synchronize()
-    h, th = flow.handle(), tgt.handle()
+    h = flow.handle()
+    th = tgt.handle() if tgt is not None else None
 
     def step():
-        K.check(lib.nf_elbo_value_and_grad_dev(h, th, theta_dev.data_ptr(), n, z0.data_ptr(), 0, -1.0, C.byref(val), grad.data_ptr()))
+        if tgt is None:
+            K.check(lib.nf_loglik_value_and_grad_dev(h, theta_dev.data_ptr(), n, z0.data_ptr(), -1.0, C.byref(val), grad.data_ptr()))
+        else:
+            K.check(lib.nf_elbo_value_and_grad_dev(h, th, theta_dev.data_ptr(), n, z0.data_ptr(), 0, -1.0, C.byref(val), grad.data_ptr()))
     for _ in range(max(args.warmup, 3)):
         step()
     lib.nf_launch_count(1)
@@ -202,7 +223,7 @@ def run_side_config(args):
         cnt, ms = C.c_int64(), C.c_double()
         K.check(lib.nf_profile_collect(h, key.encode(), C.byref(cnt), C.byref(ms)))
         prof[key] = {"launches": cnt.value, "total_ms": ms.value}
-    if cfg in ("c4", "c4b") and prof.get("rqs_bwd", {}).get("launches"):
+    if cfg in ("c4", "c4b", "c4ll") and prof.get("rqs_bwd", {}).get("launches"):
         # dominant spline kernel: reads the 3K-1 conditioner outputs of every (sample, transformed coordinate), writes the same
         # number of gradients, plus the coordinate, its incoming gradient (read + write) and the per-sample logdet gradient
         c, P3 = d // 2, 3 * 10 - 1
@@ -289,7 +310,7 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="base draws per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c3", help="c3 (headline) | c1 | c2 | c2p | c4 | c4b | c3x1")
+    ap.add_argument("--config", default="c3", help="c3 (headline) | c1 | c2 | c2p | c3b | c3x1 | c4 | c4b | c4ll | c5 | c5f64")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -390,12 +411,20 @@ def main():
         avg_ms = prof[dom]["total_ms"] / prof[dom]["launches"]
         flops = 2.0 * n_local * 256 * 256
         ach = flops / (avg_ms * 1e-3) / 1e12
+        # the same launches seen from the memory side: the fp16 hi/lo planes make this kernel move 2 x 2 B per operand element in
+        # and out, so its HBM floor (2.15 GB / 6.46 TB/s = 0.33 ms) is ABOVE its tensor floor (3 x 137 GFLOP / 1442 TF/s = 0.29 ms)
+        plane_bytes = n_local * 256 * 2 * 2 * 2.0           # A planes in + output planes out (sign bits / weights are < 1 %)
+        hbm_ach = plane_bytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<256> (256x256 Dense fwd/dgrad, fp16x3 split = 3 MMAs per useful MAC)",
                     "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
                     "frac_issued_mma": 3 * ach / sustained, "avg_launch_ms": avg_ms, "launches_per_step": prof[dom]["launches"] / args.steps,
                     "share_of_step": prof[dom]["total_ms"] / (1e3 * dt_prof), "profiled_ms_per_step": 1e3 * dt_prof / args.steps,
                     "peak_source": peak_src + " bf16 dense, sustained",
-                    "traffic": None}
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N = 2^20 (profiles/r1_tc_gemm_full.txt, K=256 launch)
+                    "traffic": 2.150e9 * n_local / (1 << 20),
+                    "hbm_view": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm, "unit": "GB/s", "frac": hbm_ach / hbm,
+                                 "algorithmic_bytes_per_launch": plane_bytes,
+                                 "note": "split-plane operands: in + out planes per launch; this is the binding roof of the kernel as built"}}
     step_roof = {"achieved_tflops": value / world * FLOP_PER_SAMPLE / 1e12, "frac_of_bf16_sustained": value / world * FLOP_PER_SAMPLE / 1e12 / sustained,
                  "achieved_hbm_algorithmic_gbs": value / world * 4 * DIM / 1e9}
 
