@@ -75,7 +75,7 @@ class _Target:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h is not None and K._lib is not None:
+        if h is not None and K is not None and getattr(K, "_lib", None) is not None:   # K is None during interpreter shutdown
             K._lib.nf_target_destroy(h)
             self._h = None
 
@@ -351,7 +351,7 @@ class Flow:
         return self._h
 
     def __del__(self):
-        if getattr(self, "_h", None) is not None and K._lib is not None:
+        if getattr(self, "_h", None) is not None and K is not None and getattr(K, "_lib", None) is not None:
             K._lib.nf_flow_destroy(self._h)
             self._h = None
 
