@@ -1,7 +1,7 @@
 """Not a pytest: iterations/s of the training loop for BASELINE config 1 (planar x20, d=2, Banana, batch 10) -- the
 latency-bound demo shape -- host loop vs on-device Adam loop."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT]
 import numpy as np
 import nfload

@@ -1,6 +1,6 @@
 """Debug aid: accuracy of the tcgen05 GEMM vs fp64, incl. K-slab accumulation outside the tensor core."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT]
 import numpy as np, ctypes as C
 import nfload

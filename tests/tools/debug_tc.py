@@ -1,6 +1,6 @@
 """Debug aid (not a pytest): per-parameter-block error of the tcgen05 path vs the fp64 oracle."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import numpy as np, torch
 import nfload, nf_oracle as O

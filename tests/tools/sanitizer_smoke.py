@@ -1,6 +1,6 @@
 """Not a pytest: a tiny pass over every kernel family for `compute-sanitizer --tool memcheck`."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import numpy as np
 import nfload
@@ -14,10 +14,12 @@ for T in (np.float32, np.float64):
         ("realnvp", nf.realnvp(nf.MvNormal(np.zeros(6)), [16, 16], 1, T), nf.Funnel(6)),
         ("realnvp64", nf.realnvp(nf.MvNormal(np.zeros(64)), [256, 256], 1, T), nf.Funnel(64)),
         ("nsf", nf.nsf(nf.MvNormal(np.zeros(4)), [8, 8], 5, 3.0, 1, T), nf.Cross(2.0, 0.15, 4)),
+        ("nsf16", nf.nsf(nf.MvNormal(np.zeros(16)), [32, 32], 10, 5.0, 1, T), nf.Cross(2.0, 0.15, 16)),   # K=10 bulk-copy ring, 1 tile + ragged tail
+        ("hamiltonian", nf.hamiltonian_flow(nf.Funnel(2, -2.0, 3.0), 3, 2, -3.0, T), nf.JointTarget(nf.Funnel(2, -2.0, 3.0))),
     ]:
         if name == "realnvp64" and T == np.float64:
             continue
-        xs = rng.standard_normal((200, flow.dim)).astype(T)
+        xs = rng.standard_normal((333 if name == 'nsf16' else 200, flow.dim)).astype(T)
         v, g = nf.api._elbo_impl(flow, tgt, xs, want_grad=True)
         y, ld = flow.with_logabsdet_jacobian(xs)
         x2, ld2 = flow.inverse_with_logabsdet_jacobian(y)
