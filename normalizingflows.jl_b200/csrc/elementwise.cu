@@ -28,10 +28,8 @@ template <int DP> constexpr int ew_stride() { return 4 + 2 * DP; }
 template <int DP> constexpr int ew_nacc() { return 2 * DP + 2; }
 
 template <typename T, int DP>
-__global__ void ew_prep_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
-                               T* __restrict__ table) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= L) return;
+__device__ __forceinline__ void ew_prep_body(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int l, int d,
+                                             T* __restrict__ table) {
   using N = Num<T>;
   const T* p = theta + meta[l].theta_off;
   T* e = table + (size_t)l * ew_stride<DP>();
@@ -81,6 +79,13 @@ __global__ void ew_prep_kernel(const T* __restrict__ theta, const EwLayerMeta* _
       break;
     }
   }
+}
+
+template <typename T, int DP>
+__global__ void ew_prep_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
+                               T* __restrict__ table) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < L) ew_prep_body<T, DP>(theta, meta, l, d, table);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -171,7 +176,7 @@ template <typename T> struct EwArgs {
 };
 
 template <typename T, int DP, int S>
-__global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
+__device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, const int nblk) {
   using N_ = Num<T>;
   constexpr int STR = ew_stride<DP>();
   constexpr int NACC = ew_nacc<DP>();
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
   const int64_t group = (int64_t)nthr * S;
   const int64_t ngroups = (a.N + group - 1) / group;
 
-  for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
+  for (int64_t gi = bid; gi < ngroups; gi += nblk) {
     T z[S][DP], ld[S], lq[S];
     bool live[S];
     // ---- load base draws, base log-density (a15) ----
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
   // ---- per-CTA partials ----
   __syncthreads();
   if (a.gpart)
-    for (int i = tid; i < L * NACC; i += nthr) a.gpart[(size_t)blockIdx.x * L * NACC + i] = s_acc[i];
+    for (int i = tid; i < L * NACC; i += nthr) a.gpart[(size_t)bid * L * NACC + i] = s_acc[i];
   if (a.epart) {
     double ev = warp_sum((double)elbo_local);
     __shared__ double s_e[32];
@@ -467,9 +472,14 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
     if (tid == 0) {
       double t = 0;
       for (int w = 0; w < (nthr + 31) / 32; ++w) t += s_e[w];
-      a.epart[blockIdx.x] = t;
+      a.epart[bid] = t;
     }
   }
+}
+
+template <typename T, int DP, int S>
+__global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
+  ew_flow_body<T, DP, S>(a, (int)blockIdx.x, (int)gridDim.x);
 }
 
 
@@ -785,11 +795,10 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
 // Deterministic cross-CTA reduction + chain rule from the reduced per-layer sums to theta order.
 // One thread per layer; gsum[P+1] receives UNSCALED sums (gradient sums then the ELBO sum at [P]).
 template <typename T, int DP>
-__global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
-                                   const T* __restrict__ gpart, const double* __restrict__ epart, int nblocks,
-                                   int64_t N, int64_t P, int want_grad, int inverse, double* __restrict__ gsum) {
+__device__ __forceinline__ void ew_finalize_body(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
+                                                 const T* __restrict__ gpart, const double* __restrict__ epart, int nblocks,
+                                                 int64_t N, int64_t P, int want_grad, int inverse, double* __restrict__ gsum, int l) {
   constexpr int NACC = ew_nacc<DP>();
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l == 0) {
     double e = 0;
     for (int b = 0; b < nblocks; ++b) e += epart[b];
@@ -845,6 +854,73 @@ __global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMet
       for (int k = 0; k < h; ++k) g[k] = G[k] * exp((double)p[k]);
       break;
     }
+  }
+}
+
+template <typename T, int DP>
+__global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
+                                   const T* __restrict__ gpart, const double* __restrict__ epart, int nblocks,
+                                   int64_t N, int64_t P, int want_grad, int inverse, double* __restrict__ gsum) {
+  ew_finalize_body<T, DP>(theta, meta, L, d, gpart, epart, nblocks, N, P, want_grad, inverse, gsum, (int)(blockIdx.x * blockDim.x + threadIdx.x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent training loop for small batches (the reference's own demo regime: planar flow, batch 10-64, 10^4-10^5 Adam
+// iterations -- example/demo_planar_flow.jl:25-47).  One CTA runs EVERY iteration inside a single launch: layer-table prep,
+// fused forward + target + backward over the batch (device Philox draws, seed + iteration as in the multi-launch loop),
+// chain rule to theta, Optimisers.Adam step, and the (loss, |g|^2) record of reference src/optimize.jl:89 -- phases separated by
+// __syncthreads instead of kernel boundaries, so an iteration costs a few microseconds instead of four launches.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct EwTrain {
+  T* theta; T* m; T* v;            // [P] device
+  const EwLayerMeta* meta;
+  T* table;                        // [L, stride]
+  double* gsum;                    // [P+1]
+  double* stats;                   // [n_iters][2]: loss, |g|^2
+  int64_t P;
+  int n_iters, t0;
+  double eta, b1, b2, eps;
+  uint64_t seed0;
+};
+
+template <typename T, int DP, int S>
+__global__ void __launch_bounds__(128) ew_train_kernel(EwArgs<T> a, EwTrain<T> tr) {
+  __shared__ double s_g2[4];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const double inv_n = 1.0 / (double)a.N;
+  double b1t = pow(tr.b1, (double)tr.t0), b2t = pow(tr.b2, (double)tr.t0);     // beta^t, advanced by one product per iteration
+  for (int it = 0; it < tr.n_iters; ++it) {
+    for (int l = tid; l < a.L; l += nthr) ew_prep_body<T, DP>(tr.theta, tr.meta, l, a.d, tr.table);
+    __syncthreads();
+    EwArgs<T> ai = a;
+    ai.seed = tr.seed0 + (uint64_t)it;
+    ew_flow_body<T, DP, S>(ai, 0, 1);
+    __syncthreads();
+    for (int l = tid; l < a.L; l += nthr)
+      ew_finalize_body<T, DP>(tr.theta, tr.meta, a.L, a.d, a.gpart, a.epart, 1, a.N, tr.P, 1, 0, tr.gsum, l);
+    __syncthreads();
+    const T b1 = (T)tr.b1, b2 = (T)tr.b2, eta = (T)tr.eta, eps = (T)tr.eps;
+    b1t *= tr.b1; b2t *= tr.b2;
+    const T omb1t = (T)(1.0 - b1t), omb2t = (T)(1.0 - b2t);
+    double g2 = 0;
+    for (int64_t i = tid; i < tr.P; i += nthr) {
+      const T g = (T)(-tr.gsum[i] * inv_n);
+      const T mi = b1 * tr.m[i] + (T(1) - b1) * g;
+      const T vi = b2 * tr.v[i] + (T(1) - b2) * g * g;
+      tr.m[i] = mi; tr.v[i] = vi;
+      tr.theta[i] -= mi / omb1t / (Num<T>::sqrt(vi / omb2t) + eps) * eta;
+      g2 += (double)g * (double)g;
+    }
+    g2 = warp_sum(g2);
+    if ((tid & 31) == 0) s_g2[tid >> 5] = g2;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0;
+      for (int w = 0; w < (nthr + 31) / 32; ++w) t += s_g2[w];
+      tr.stats[2 * it] = -tr.gsum[tr.P] * inv_n;
+      tr.stats[2 * it + 1] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -926,6 +1002,66 @@ int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const v
   set_error("elementwise (planar/radial) flows support dim <= 64 in this build, got %d", d);
   return NF_ERR_UNSUPPORTED;
 }
+
+template <typename T, int DP, int S>
+static int ew_train_launch(Flow& f, const Target* tgt, int64_t N, uint64_t seed, int n_iters, int t0, double eta, double b1,
+                           double b2, double eps, void* m_dev, void* v_dev) {
+  const int L = (int)f.layers.size(), d = f.dim;
+  constexpr int STR = ew_stride<DP>(), NACC = ew_nacc<DP>();
+  const int threads = 128;
+  const size_t smem = ((size_t)L * STR + (size_t)L * NACC + (size_t)L * S * threads) * sizeof(T) + (size_t)L * sizeof(int) + 16;
+  if (smem > 200 * 1024) {
+    set_error("elementwise flow with %d layers needs %zu B of shared memory (limit 200 KiB)", L, smem);
+    return NF_ERR_UNSUPPORTED;
+  }
+  auto kern = ew_train_kernel<T, DP, S>;
+  NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  f.ws_reset();
+  NF_TRY(f.ws_reserve((size_t)4 << 20));
+  T* table = (T*)f.ws_alloc((size_t)L * STR * sizeof(T));
+  T* gpart = (T*)f.ws_alloc((size_t)L * NACC * sizeof(T));
+  double* epart = (double*)f.ws_alloc(sizeof(double));
+  if (!table || !gpart || !epart) return NF_ERR_OOM;
+  EwArgs<T> a{};
+  a.z0 = nullptr; a.table = table; a.kinds = f.d_ew_kinds;
+  a.base = f.base_is_standard ? nullptr : (const T*)f.d_base;
+  a.base_c0 = (T)f.base_c0;
+  a.tp = tgt->params<T>();
+  if (f.score_target) a.sp = f.score_target->params<T>();
+  a.gpart = gpart; a.epart = epart; a.N = N; a.L = L; a.d = d;
+  a.flags = EW_GRAD | EW_TARGET | EW_GEN_Z0;
+  EwTrain<T> tr{};
+  tr.theta = (T*)f.d_theta; tr.m = (T*)m_dev; tr.v = (T*)v_dev; tr.meta = f.d_ew_meta; tr.table = table; tr.gsum = f.d_gsum;
+  tr.stats = f.d_stats; tr.P = f.P; tr.n_iters = n_iters; tr.t0 = t0; tr.eta = eta; tr.b1 = b1; tr.b2 = b2; tr.eps = eps; tr.seed0 = seed;
+  f.prof.begin("ew_train", f.stream);
+  kern<<<1, threads, smem, f.stream>>>(a, tr);
+  f.prof.end(f.stream);
+  NF_LAUNCH_CHECK();
+  return NF_OK;
+}
+
+// n_iters Adam iterations of the ELBO objective in ONE launch (single CTA); for batches small enough that one CTA is the
+// right amount of hardware (see ew_train_kernel).  Returns NF_ERR_UNSUPPORTED when the flow / batch does not qualify.
+template <typename T>
+int ew_train(Flow& f, const Target* tgt, int64_t N, uint64_t seed, int n_iters, int t0, double eta, double b1, double b2,
+             double eps, void* m_dev, void* v_dev) {
+  const int d = f.dim;
+  if ((f.hamiltonian || tgt->joint) && (d & (d - 1)) != 0) {
+    set_error("Hamiltonian flows / joint targets need dim a power of two, got %d", d);
+    return NF_ERR_UNSUPPORTED;
+  }
+#define NF_EWT_CASE(DPV, SV) return ew_train_launch<T, DPV, SV>(f, tgt, N, seed, n_iters, t0, eta, b1, b2, eps, m_dev, v_dev)
+  // one sample per thread while the batch fits the CTA (a thread's S samples are a serial dependency chain)
+  if (d <= 2) { if (N <= 128) NF_EWT_CASE(2, 1); NF_EWT_CASE(2, 4); }
+  if (d <= 4) { if (N <= 128) NF_EWT_CASE(4, 1); NF_EWT_CASE(4, 2); }
+  if (d <= 8) NF_EWT_CASE(8, 1);
+  if (d <= 16) NF_EWT_CASE(16, 1);
+#undef NF_EWT_CASE
+  set_error("persistent training kernel supports dim <= 16, got %d", d);
+  return NF_ERR_UNSUPPORTED;
+}
+template int ew_train<float>(Flow&, const Target*, int64_t, uint64_t, int, int, double, double, double, double, void*, void*);
+template int ew_train<double>(Flow&, const Target*, int64_t, uint64_t, int, int, double, double, double, double, void*, void*);
 
 template int ew_run<float>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool, bool);
 template int ew_run<double>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool, bool);

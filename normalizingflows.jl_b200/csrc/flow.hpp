@@ -172,4 +172,9 @@ int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const v
            bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev, bool inverse = false,
            bool head = false);
 
+// single-launch Adam training loop for small batches of elementwise flows (elementwise.cu: ew_train_kernel)
+template <typename T>
+int ew_train(Flow& f, const Target* tgt, int64_t N, uint64_t seed, int n_iters, int t0, double eta, double b1, double b2,
+             double eps, void* m_dev, void* v_dev);
+
 }  // namespace nf

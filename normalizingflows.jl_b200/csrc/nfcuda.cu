@@ -650,7 +650,14 @@ int nf_train_elbo_adam(nf_flow_t flow, nf_target_t target, void* theta_host_inou
   }
   NF_CUDA(cudaMemsetAsync(f.d_stats, 0, (size_t)n_iters * 2 * sizeof(double), f.stream));
   NF_CUDA(cudaEventRecord(f.ev0, f.stream));
-  for (int it = 0; it < n_iters; ++it) {
+  // small batches of elementwise flows: every iteration inside one persistent single-CTA launch (NFCUDA_TRAIN_PERSISTENT=0 disables)
+  const bool persistent_ok = !(getenv("NFCUDA_TRAIN_PERSISTENT") && atoi(getenv("NFCUDA_TRAIN_PERSISTENT")) == 0);
+  const bool persistent = persistent_ok && f.all_elementwise && f.dim <= 16 && N <= 2048;
+  if (persistent) {
+    if (f.dtype == NF_F32) NF_TRY(ew_train<float>(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv));
+    else NF_TRY(ew_train<double>(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv));
+  }
+  for (int it = 0; it < n_iters && !persistent; ++it) {
     f.ws_reset();
     NF_TRY(general_plan_workspace(f, OP_ELBO, N, 0));
     Job j;
