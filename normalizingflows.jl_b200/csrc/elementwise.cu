@@ -184,11 +184,12 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
   const int L = a.L, d = a.d, tid = threadIdx.x, nthr = blockDim.x;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* s_tab = reinterpret_cast<T*>(smem_raw);                 // L*STR
-  T* s_acc = s_tab + (size_t)L * STR;                        // L*NACC
-  T* s_stash = s_acc + (size_t)L * NACC;                     // L*S*nthr
+  const int nwarp = nthr >> 5;
+  T* s_acc = s_tab + (size_t)L * STR;                        // nwarp*L*NACC: one row of sums per warp (lane 0 adds, no atomics)
+  T* s_stash = s_acc + (size_t)nwarp * L * NACC;             // L*S*nthr
   int* s_kind = reinterpret_cast<int*>(s_stash + (size_t)L * S * nthr);  // L
   for (int i = tid; i < L * STR; i += nthr) s_tab[i] = a.table[i];
-  for (int i = tid; i < L * NACC; i += nthr) s_acc[i] = 0;
+  for (int i = tid; i < nwarp * L * NACC; i += nthr) s_acc[i] = 0;
   for (int i = tid; i < L; i += nthr) s_kind[i] = a.kinds[i];
   __syncthreads();
 
@@ -230,6 +231,12 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
       }
       lq[s] = a.base_c0 - q / 2;
       ld[s] = 0;
+    }
+    {   // a warp without a single live sample (ragged last group, tiny batches) has nothing to add to any sum
+      bool any_live = false;
+#pragma unroll
+      for (int s = 0; s < S; ++s) any_live |= live[s];
+      if (!__any_sync(0xffffffffu, any_live)) continue;
     }
     // ---- forward sweep: layers applied last-to-first (create_flow, reference src/flows/utils.jl:23-26) ----
     for (int l = L - 1; l >= 0; --l) {
@@ -335,7 +342,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
     const int lane = tid & 31;
     for (int l = 0; l < L; ++l) {
       const T* e = s_tab + (size_t)l * STR;
-      T* acc = s_acc + (size_t)l * NACC;
+      T* acc = s_acc + ((size_t)(tid >> 5) * L + l) * NACC;
       const int kind = s_kind[l];
       if (kind == NF_PLANAR) {
         const T m = e[1];
@@ -364,11 +371,11 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
           }
           if (k < d) {
             gu = warp_sum(gu); gw = warp_sum(gw);
-            if (lane == 0) { atomicAdd(&acc[k], gu); atomicAdd(&acc[DP + k], gw); }
+            if (lane == 0) { acc[k] += gu; acc[DP + k] += gw; }
           }
         }
         g_m = warp_sum(g_m); g_b = warp_sum(g_b);
-        if (lane == 0) { atomicAdd(&acc[2 * DP], g_m); atomicAdd(&acc[2 * DP + 1], g_b); }
+        if (lane == 0) { acc[2 * DP] += g_m; acc[2 * DP + 1] += g_b; }
       } else if (kind == NF_RADIAL) {
         const T alpha = e[0], bh = e[1];
         T g_al = 0, g_bh = 0, gz0[DP];
@@ -405,17 +412,17 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
         for (int k = 0; k < DP; ++k)
           if (k < d) {
             const T v = warp_sum(gz0[k]);
-            if (lane == 0) atomicAdd(&acc[k], v);
+            if (lane == 0) acc[k] += v;
           }
         g_al = warp_sum(g_al); g_bh = warp_sum(g_bh);
-        if (lane == 0) { atomicAdd(&acc[2 * DP], g_al); atomicAdd(&acc[2 * DP + 1], g_bh); }
+        if (lane == 0) { acc[2 * DP] += g_al; acc[2 * DP + 1] += g_bh; }
       } else if (kind == NF_SHIFT) {
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
           T v = 0;
 #pragma unroll
           for (int s = 0; s < S; ++s) { v += gy[s][k]; z[s][k] -= e[4 + k]; }
-          if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+          if (k < d) { v = warp_sum(v); if (lane == 0) acc[k] += v; }
         }
       } else if (kind == NF_SCALE) {
 #pragma unroll
@@ -427,7 +434,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
             v += gy[s][k] * z[s][k];
             gy[s][k] *= e[4 + k];
           }
-          if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+          if (k < d) { v = warp_sum(v); if (lane == 0) acc[k] += v; }
         }
       } else if (kind == NF_MOMENTUM_AFFINE) {
 #pragma unroll
@@ -442,7 +449,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
             gy[s][k] *= e[4 + DP + k];
           }
           gb = warp_sum(gb); ga = warp_sum(ga);
-          if (lane == 0) { atomicAdd(&acc[k], gb); atomicAdd(&acc[DP + k], ga); }
+          if (lane == 0) { acc[k] += gb; acc[DP + k] += ga; }
         }
       } else {  // NF_LEAPFROG
         T eps[HD], ge[HD];
@@ -455,7 +462,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
 #pragma unroll
         for (int k = 0; k < HD; ++k) {
           const T v = warp_sum(ge[k]);
-          if (lane == 0) atomicAdd(&acc[k], v);
+          if (lane == 0) acc[k] += v;
         }
       }
     }
@@ -463,7 +470,11 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
   // ---- per-CTA partials ----
   __syncthreads();
   if (a.gpart)
-    for (int i = tid; i < L * NACC; i += nthr) a.gpart[(size_t)bid * L * NACC + i] = s_acc[i];
+    for (int i = tid; i < L * NACC; i += nthr) {
+      T t = 0;
+      for (int w = 0; w < nwarp; ++w) t += s_acc[(size_t)w * L * NACC + i];
+      a.gpart[(size_t)bid * L * NACC + i] = t;
+    }
   if (a.epart) {
     double ev = warp_sum((double)elbo_local);
     __shared__ double s_e[32];
@@ -502,10 +513,11 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
   const int L = a.L, d = a.d, tid = threadIdx.x, nthr = blockDim.x;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* s_tab = reinterpret_cast<T*>(smem_raw);
-  T* s_acc = s_tab + (size_t)L * STR;
-  int* s_kind = reinterpret_cast<int*>(s_acc + (size_t)L * NACC);
+  const int nwarp = nthr >> 5;
+  T* s_acc = s_tab + (size_t)L * STR;                        // nwarp*L*NACC (see ew_flow_body)
+  int* s_kind = reinterpret_cast<int*>(s_acc + (size_t)nwarp * L * NACC);
   for (int i = tid; i < L * STR; i += nthr) s_tab[i] = a.table[i];
-  for (int i = tid; i < L * NACC; i += nthr) s_acc[i] = 0;
+  for (int i = tid; i < nwarp * L * NACC; i += nthr) s_acc[i] = 0;
   for (int i = tid; i < L; i += nthr) s_kind[i] = a.kinds[i];
   __syncthreads();
   const bool want_grad = a.flags & EW_GRAD;
@@ -634,7 +646,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
     // ---- backward sweep: layers L-1 .. 0, walking the forward maps from x0 back to y ----
     for (int l = L - 1; l >= 0; --l) {
       const T* e = s_tab + (size_t)l * STR;
-      T* acc = s_acc + (size_t)l * NACC;
+      T* acc = s_acc + ((size_t)(tid >> 5) * L + l) * NACC;
       const int kind = s_kind[l];
       if (kind == NF_PLANAR) {
         const T b = e[0], m = e[1];
@@ -672,11 +684,11 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
           }
           if (k < d) {
             gu = warp_sum(gu); gw = warp_sum(gw);
-            if (lane == 0) { atomicAdd(&acc[k], gu); atomicAdd(&acc[DP + k], gw); }
+            if (lane == 0) { acc[k] += gu; acc[DP + k] += gw; }
           }
         }
         g_m = warp_sum(g_m); g_b = warp_sum(g_b);
-        if (lane == 0) { atomicAdd(&acc[2 * DP], g_m); atomicAdd(&acc[2 * DP + 1], g_b); }
+        if (lane == 0) { acc[2 * DP] += g_m; acc[2 * DP + 1] += g_b; }
 #pragma unroll
         for (int s = 0; s < S; ++s)
 #pragma unroll
@@ -721,17 +733,17 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
         for (int k = 0; k < DP; ++k)
           if (k < d) {
             const T v = warp_sum(gz0[k]);
-            if (lane == 0) atomicAdd(&acc[k], v);
+            if (lane == 0) acc[k] += v;
           }
         g_al = warp_sum(g_al); g_bh = warp_sum(g_bh);
-        if (lane == 0) { atomicAdd(&acc[2 * DP], g_al); atomicAdd(&acc[2 * DP + 1], g_bh); }
+        if (lane == 0) { acc[2 * DP] += g_al; acc[2 * DP + 1] += g_bh; }
       } else if (kind == NF_SHIFT) {
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
           T v = 0;
 #pragma unroll
           for (int s = 0; s < S; ++s) { v -= gz[s][k]; z[s][k] += e[4 + k]; }
-          if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+          if (k < d) { v = warp_sum(v); if (lane == 0) acc[k] += v; }
         }
       } else if (kind == NF_SCALE) {  // z = y / a
 #pragma unroll
@@ -743,7 +755,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
             gz[s][k] *= e[4 + DP + k];
             z[s][k] *= e[4 + k];
           }
-          if (k < d) { v = warp_sum(v); if (lane == 0) atomicAdd(&acc[k], v); }
+          if (k < d) { v = warp_sum(v); if (lane == 0) acc[k] += v; }
         }
       } else if (kind == NF_MOMENTUM_AFFINE) {  // rho_in = (rho_out - b) / a
 #pragma unroll
@@ -758,7 +770,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
             z[s][k] = z[s][k] * e[4 + DP + k] + e[4 + k];
           }
           gb = warp_sum(gb); ga = warp_sum(ga);
-          if (lane == 0) { atomicAdd(&acc[k], gb); atomicAdd(&acc[DP + k], ga); }
+          if (lane == 0) { acc[k] += gb; acc[DP + k] += ga; }
         }
       } else {  // NF_LEAPFROG (applied with -eps)
         T eps[HD], ge[HD];
@@ -771,14 +783,18 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
 #pragma unroll
         for (int k = 0; k < HD; ++k) {
           const T v = warp_sum(ge[k]);
-          if (lane == 0) atomicAdd(&acc[k], v);
+          if (lane == 0) acc[k] += v;
         }
       }
     }
   }
   __syncthreads();
   if (a.gpart)
-    for (int i = tid; i < L * NACC; i += nthr) a.gpart[(size_t)blockIdx.x * L * NACC + i] = s_acc[i];
+    for (int i = tid; i < L * NACC; i += nthr) {
+      T t = 0;
+      for (int w = 0; w < nwarp; ++w) t += s_acc[(size_t)w * L * NACC + i];
+      a.gpart[(size_t)blockIdx.x * L * NACC + i] = t;
+    }
   if (a.epart) {
     double ev = warp_sum((double)obj_local);
     __shared__ double s_e[32];
@@ -933,7 +949,7 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
   const int L = (int)f.layers.size(), d = f.dim;
   constexpr int STR = ew_stride<DP>(), NACC = ew_nacc<DP>();
   const int threads = 128;
-  const size_t smem = ((size_t)L * STR + (size_t)L * NACC + (inverse ? 0 : (size_t)L * S * threads)) * sizeof(T) + (size_t)L * sizeof(int) + 16;
+  const size_t smem = ((size_t)L * STR + (size_t)(threads / 32) * L * NACC + (inverse ? 0 : (size_t)L * S * threads)) * sizeof(T) + (size_t)L * sizeof(int) + 16;
   if (smem > 200 * 1024) {
     set_error("elementwise flow with %d layers needs %zu B of shared memory (limit 200 KiB)", L, smem);
     return NF_ERR_UNSUPPORTED;
@@ -992,8 +1008,9 @@ int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const v
 #define NF_EW_CASE(DPV, SV)                                                                              \
   return ew_launch<T, DPV, SV>(f, tgt, (const T*)theta_dev, N, (const T*)z0_dev, seed, flags, (T*)y_out, \
                                (T*)ld_out, (T*)terms_out, gsum_dev, inverse)
-  if (d <= 2) NF_EW_CASE(2, 4);
-  if (d <= 4) NF_EW_CASE(4, 2);
+  static const int s_override = getenv("NFCUDA_EW_S") ? atoi(getenv("NFCUDA_EW_S")) : 0;   // experiment knob: samples per thread
+  if (d <= 2) { if (s_override == 1) NF_EW_CASE(2, 1); if (s_override == 2) NF_EW_CASE(2, 2); if (s_override == 8) NF_EW_CASE(2, 8); NF_EW_CASE(2, 4); }
+  if (d <= 4) { if (s_override == 1) NF_EW_CASE(4, 1); NF_EW_CASE(4, 2); }
   if (d <= 8) NF_EW_CASE(8, 1);
   if (d <= 16) NF_EW_CASE(16, 1);
   if (d <= 32) NF_EW_CASE(32, 1);
@@ -1009,7 +1026,7 @@ static int ew_train_launch(Flow& f, const Target* tgt, int64_t N, uint64_t seed,
   const int L = (int)f.layers.size(), d = f.dim;
   constexpr int STR = ew_stride<DP>(), NACC = ew_nacc<DP>();
   const int threads = 128;
-  const size_t smem = ((size_t)L * STR + (size_t)L * NACC + (size_t)L * S * threads) * sizeof(T) + (size_t)L * sizeof(int) + 16;
+  const size_t smem = ((size_t)L * STR + (size_t)(threads / 32) * L * NACC + (size_t)L * S * threads) * sizeof(T) + (size_t)L * sizeof(int) + 16;
   if (smem > 200 * 1024) {
     set_error("elementwise flow with %d layers needs %zu B of shared memory (limit 200 KiB)", L, smem);
     return NF_ERR_UNSUPPORTED;
