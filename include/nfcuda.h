@@ -93,7 +93,9 @@ typedef enum nf_target_kind {
   NF_TARGET_FUNNEL       = 2,  /* params: mu, sigma         (neal_funnel.jl:54-61)      */
   NF_TARGET_WARPED_GAUSS = 3,  /* params: sigma1, sigma2    (warped_gaussian.jl:81-87)  */
   NF_TARGET_CROSS        = 4,  /* params: mu, sigma; dim = 2m -> product of m Cross blocks (cross.jl:30-38) */
-  NF_TARGET_DIAG_NORMAL  = 5   /* params: mu[dim], sigma[dim] (standard deviations; MvNormal(mu, Diagonal(sigma.^2))) */
+  NF_TARGET_DIAG_NORMAL  = 5,  /* params: mu[dim], sigma[dim] (standard deviations; MvNormal(mu, Diagonal(sigma.^2))) */
+  NF_TARGET_LOGREG       = 6   /* synthetic Bayesian logistic-regression posterior (BASELINE config 5): params: sigma0, n, X[n*dim] row major,
+                                  y[n] in {0,1};  logp(b) = sum_i [y_i x_i.b - softplus(x_i.b)] + log N(b; 0, sigma0^2 I) */
 } nf_target_kind;
 
 /* MMA issue mode of the coupling-MLP contractions (fp32 flows).  F16X3 is the parity mode. */

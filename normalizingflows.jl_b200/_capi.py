@@ -13,6 +13,7 @@ NF_F32, NF_F64 = 0, 1
 NF_PLANAR, NF_RADIAL, NF_AFFINE_COUPLING, NF_SPLINE_COUPLING, NF_SHIFT, NF_SCALE = 1, 2, 3, 4, 5, 6
 NF_MOMENTUM_AFFINE, NF_LEAPFROG = 7, 8
 NF_TARGET_BANANA, NF_TARGET_FUNNEL, NF_TARGET_WARPED_GAUSS, NF_TARGET_CROSS, NF_TARGET_DIAG_NORMAL = 1, 2, 3, 4, 5
+NF_TARGET_LOGREG = 6
 NF_MMA_SIMT, NF_MMA_F16X3, NF_MMA_F16X1 = 0, 1, 2
 
 

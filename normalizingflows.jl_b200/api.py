@@ -151,6 +151,25 @@ class DiagNormal(_Target):
         return np.concatenate([self.mu, self.sigma])
 
 
+class LogReg(_Target):
+    """Synthetic Bayesian logistic-regression posterior over `dim` coefficients (BASELINE config 5; not in the reference):
+    logp(b) = sum_i [y_i x_i.b - softplus(x_i.b)] + log N(b; 0, sigma0^2 I) for X [n, dim], y in {0,1}^n.  The data set is
+    copied to the device once; logp, score and Hessian-vector products are evaluated inside the kernels."""
+    kind = K.NF_TARGET_LOGREG
+
+    def __init__(self, X, y, sigma0=1.0):
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        if self.X.ndim != 2 or self.X.shape[0] != self.y.size:
+            raise ValueError("X must be [n, dim] and y of length n")
+        if sigma0 <= 0:
+            raise ValueError("sigma0 must be > 0")
+        self.dim, self.sigma0 = int(self.X.shape[1]), float(sigma0)
+
+    def _params(self):
+        return np.concatenate([[self.sigma0, float(self.y.size)], self.X.reshape(-1), self.y])
+
+
 class JointTarget(_Target):
     """logp_joint(z) = logp(x) + sum(logpdf(Normal(), rho)) on z = [x, rho]
     (reference example/demo_hamiltonian_flow.jl:117-124)."""

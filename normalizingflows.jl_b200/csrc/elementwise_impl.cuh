@@ -12,6 +12,7 @@
 //   planar  (Bijectors.PlanarLayer, restated in reference test/ext/CUDA/cuda.jl:12-30; App. A.1)
 //   radial  (Bijectors.RadialLayer; App. A.2)
 //   elbo_j = logp(T(x_j)) - log q0(x_j) + logdet_j          (reference src/objectives/elbo.jl:4-7,65-70)
+#pragma once
 #include "flow.hpp"
 #include "targets.cuh"
 
@@ -95,18 +96,18 @@ __global__ void ew_prep_kernel(const T* __restrict__ theta, const EwLayerMeta* _
 // The reverse sweep needs no stash: each elementary update is undone exactly (up to rounding) while its adjoint is
 // applied, the second-order term being a Hessian-vector product of the target.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int HD>
+template <typename T, int HD, bool LR>
 __device__ __forceinline__ void leapfrog_apply(const TargetParams<T>& sp, T* x, T* v, const T* eps, T sgn, int nsteps) {
   T g[HD];
 #pragma unroll
   for (int k = 0; k < HD; ++k) g[k] = 0;
-  target_logp_score<T, HD>(sp, x, g);
+  target_logp_score<T, HD, LR>(sp, x, g);
 #pragma unroll
   for (int k = 0; k < HD; ++k) v[k] += sgn * eps[k] / 2 * g[k];
   for (int it = 0; it < nsteps; ++it) {
 #pragma unroll
     for (int k = 0; k < HD; ++k) x[k] += sgn * eps[k] * v[k];
-    target_logp_score<T, HD>(sp, x, g);
+    target_logp_score<T, HD, LR>(sp, x, g);
     const T c = (it == nsteps - 1) ? sgn / 2 : sgn;
 #pragma unroll
     for (int k = 0; k < HD; ++k) v[k] += c * eps[k] * g[k];
@@ -115,7 +116,7 @@ __device__ __forceinline__ void leapfrog_apply(const TargetParams<T>& sp, T* x, 
 
 // (x, v): OUTPUT state of leapfrog_apply(sgn) on entry, its input state on exit; (gx, gv): adjoints of the output on
 // entry, of the input on exit; geps += d/d(eps) (the derivative w.r.t. the signed step is folded in through sgn).
-template <typename T, int HD>
+template <typename T, int HD, bool LR>
 __device__ __forceinline__ void leapfrog_backward(const TargetParams<T>& sp, T* x, T* v, T* gx, T* gv, const T* eps,
                                                   T sgn, int nsteps, T* geps) {
   T g[HD], w[HD], hw[HD];
@@ -124,14 +125,14 @@ __device__ __forceinline__ void leapfrog_backward(const TargetParams<T>& sp, T* 
   for (int it = nsteps - 1; it >= 0; --it) {
     // undo  v += c eps s(x)
     const T c = (it == nsteps - 1) ? sgn / 2 : sgn;
-    target_logp_score<T, HD>(sp, x, g);
+    target_logp_score<T, HD, LR>(sp, x, g);
 #pragma unroll
     for (int k = 0; k < HD; ++k) {
       v[k] -= c * eps[k] * g[k];
       geps[k] += c * gv[k] * g[k];
       w[k] = c * eps[k] * gv[k];
     }
-    target_hvp<T, HD>(sp, x, w, hw);
+    target_hvp<T, HD, LR>(sp, x, w, hw);
 #pragma unroll
     for (int k = 0; k < HD; ++k) gx[k] += hw[k];
     // undo  x += eps v
@@ -143,14 +144,14 @@ __device__ __forceinline__ void leapfrog_backward(const TargetParams<T>& sp, T* 
     }
   }
   // undo the opening half kick
-  target_logp_score<T, HD>(sp, x, g);
+  target_logp_score<T, HD, LR>(sp, x, g);
 #pragma unroll
   for (int k = 0; k < HD; ++k) {
     v[k] -= sgn * eps[k] / 2 * g[k];
     geps[k] += sgn / 2 * gv[k] * g[k];
     w[k] = sgn * eps[k] / 2 * gv[k];
   }
-  target_hvp<T, HD>(sp, x, w, hw);
+  target_hvp<T, HD, LR>(sp, x, w, hw);
 #pragma unroll
   for (int k = 0; k < HD; ++k) gx[k] += hw[k];
 }
@@ -175,7 +176,7 @@ template <typename T> struct EwArgs {
   uint64_t seed;
 };
 
-template <typename T, int DP, int S>
+template <typename T, int DP, int S, bool LR>
 __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, const int nblk) {
   using N_ = Num<T>;
   constexpr int STR = ew_stride<DP>();
@@ -295,7 +296,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
         for (int k = 0; k < HD; ++k) eps[k] = e[4 + k];
         const int nst = (int)e[0];
 #pragma unroll
-        for (int s = 0; s < S; ++s) leapfrog_apply<T, HD>(a.sp, z[s], z[s] + HD, eps, T(1), nst);
+        for (int s = 0; s < S; ++s) leapfrog_apply<T, HD, LR>(a.sp, z[s], z[s] + HD, eps, T(1), nst);
       }
     }
     // ---- outputs of a pure forward pass ----
@@ -320,13 +321,13 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
       for (int k = 0; k < DP; ++k) gy[s][k] = 0;
       T lp;
       if (a.tp.joint) {   // logp(x) + sum logN(rho; 0, 1)   (demo_hamiltonian_flow.jl:117-124); d == DP here
-        lp = target_logp_score<T, HD>(a.tp, z[s], gy[s]);
+        lp = target_logp_score<T, HD, LR>(a.tp, z[s], gy[s]);
         T q = 0;
 #pragma unroll
         for (int k = HD; k < DP; ++k) { q += z[s][k] * z[s][k]; gy[s][k] = -z[s][k]; }
         lp -= q / 2 + T(HD) * T(NF_LOG2PI / 2);
       } else {
-        lp = target_logp_score<T, DP>(a.tp, z[s], gy[s]);
+        lp = target_logp_score<T, DP, LR>(a.tp, z[s], gy[s]);
       }
       const T term = lp - lq[s] + ld[s];
       if (live[s]) {
@@ -458,7 +459,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
         const int nst = (int)e[0];
 #pragma unroll
         for (int s = 0; s < S; ++s)
-          leapfrog_backward<T, HD>(a.sp, z[s], z[s] + HD, gy[s], gy[s] + HD, eps, T(1), nst, ge);
+          leapfrog_backward<T, HD, LR>(a.sp, z[s], z[s] + HD, gy[s], gy[s] + HD, eps, T(1), nst, ge);
 #pragma unroll
         for (int k = 0; k < HD; ++k) {
           const T v = warp_sum(ge[k]);
@@ -488,9 +489,9 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
   }
 }
 
-template <typename T, int DP, int S>
+template <typename T, int DP, int S, bool LR>
 __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
-  ew_flow_body<T, DP, S>(a, (int)blockIdx.x, (int)gridDim.x);
+  ew_flow_body<T, DP, S, LR>(a, (int)blockIdx.x, (int)gridDim.x);
 }
 
 
@@ -504,7 +505,7 @@ __global__ void __launch_bounds__(128) ew_flow_kernel(EwArgs<T> a) {
 // safeguarded Newton inside the bracket [w.y - |m|, w.y + |m|].  Radial inverse: closed form (App. A.2).
 // No stash is needed: the backward sweep walks the FORWARD maps from x0 back to y.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int DP, int S>
+template <typename T, int DP, int S, bool LR>
 __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
   using N_ = Num<T>;
   constexpr int STR = ew_stride<DP>();
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
         for (int k = 0; k < HD; ++k) eps[k] = e[4 + k];
         const int nst = (int)e[0];
 #pragma unroll
-        for (int s = 0; s < S; ++s) leapfrog_apply<T, HD>(a.sp, z[s], z[s] + HD, eps, T(-1), nst);
+        for (int s = 0; s < S; ++s) leapfrog_apply<T, HD, LR>(a.sp, z[s], z[s] + HD, eps, T(-1), nst);
       }
     }
     if (a.flags & (EW_WRITE_Y | EW_WRITE_LD)) {
@@ -779,7 +780,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
         const int nst = (int)e[0];
 #pragma unroll
         for (int s = 0; s < S; ++s)
-          leapfrog_backward<T, HD>(a.sp, z[s], z[s] + HD, gz[s], gz[s] + HD, eps, T(-1), nst, ge);
+          leapfrog_backward<T, HD, LR>(a.sp, z[s], z[s] + HD, gz[s], gz[s] + HD, eps, T(-1), nst, ge);
 #pragma unroll
         for (int k = 0; k < HD; ++k) {
           const T v = warp_sum(ge[k]);
@@ -899,7 +900,7 @@ template <typename T> struct EwTrain {
   uint64_t seed0;
 };
 
-template <typename T, int DP, int S>
+template <typename T, int DP, int S, bool LR>
 __global__ void __launch_bounds__(128) ew_train_kernel(EwArgs<T> a, EwTrain<T> tr) {
   __shared__ double s_g2[4];
   const int tid = threadIdx.x, nthr = blockDim.x;
@@ -910,7 +911,7 @@ __global__ void __launch_bounds__(128) ew_train_kernel(EwArgs<T> a, EwTrain<T> t
     __syncthreads();
     EwArgs<T> ai = a;
     ai.seed = tr.seed0 + (uint64_t)it;
-    ew_flow_body<T, DP, S>(ai, 0, 1);
+    ew_flow_body<T, DP, S, LR>(ai, 0, 1);
     __syncthreads();
     for (int l = tid; l < a.L; l += nthr)
       ew_finalize_body<T, DP>(tr.theta, tr.meta, a.L, a.d, a.gpart, a.epart, 1, a.N, tr.P, 1, 0, tr.gsum, l);
@@ -943,7 +944,7 @@ __global__ void __launch_bounds__(128) ew_train_kernel(EwArgs<T> a, EwTrain<T> t
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <typename T, int DP, int S>
+template <typename T, int DP, int S, bool LR, bool INV>
 static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, const T* z0_dev, uint64_t seed,
                      int flags, T* y_out, T* ld_out, T* terms_out, double* gsum_dev, bool inverse) {
   const int L = (int)f.layers.size(), d = f.dim;
@@ -954,7 +955,9 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
     set_error("elementwise flow with %d layers needs %zu B of shared memory (limit 200 KiB)", L, smem);
     return NF_ERR_UNSUPPORTED;
   }
-  auto kern = inverse ? ew_inv_flow_kernel<T, DP, S> : ew_flow_kernel<T, DP, S>;
+  (void)inverse;
+  void (*kern)(EwArgs<T>);
+  if constexpr (INV) kern = ew_inv_flow_kernel<T, DP, S, LR>; else kern = ew_flow_kernel<T, DP, S, LR>;
   NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t group = (int64_t)threads * S;
   int max_blocks = 0;
@@ -991,9 +994,12 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
   return NF_OK;
 }
 
-template <typename T>
-int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
-           bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev, bool inverse, bool head) {
+// One direction (forward sweep / inverse sweep) per translation unit: the kernels are many large instantiations, and
+// splitting them (elementwise_{fwd,inv,train}_{f32,f64}.cu) lets the build compile them in parallel.
+template <typename T, bool INV>
+int ew_run_dir(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
+               bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev, bool head) {
+  constexpr bool inverse = INV;
   int flags = 0;
   if (tgt || (inverse && head)) flags |= EW_TARGET;
   if (want_grad) flags |= EW_GRAD;
@@ -1005,22 +1011,31 @@ int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const v
     set_error("Hamiltonian flows / joint targets need dim a power of two, got %d", d);
     return NF_ERR_UNSUPPORTED;
   }
-#define NF_EW_CASE(DPV, SV)                                                                              \
-  return ew_launch<T, DPV, SV>(f, tgt, (const T*)theta_dev, N, (const T*)z0_dev, seed, flags, (T*)y_out, \
-                               (T*)ld_out, (T*)terms_out, gsum_dev, inverse)
-  static const int s_override = getenv("NFCUDA_EW_S") ? atoi(getenv("NFCUDA_EW_S")) : 0;   // experiment knob: samples per thread
-  if (d <= 2) { if (s_override == 1) NF_EW_CASE(2, 1); if (s_override == 2) NF_EW_CASE(2, 2); if (s_override == 8) NF_EW_CASE(2, 8); NF_EW_CASE(2, 4); }
-  if (d <= 4) { if (s_override == 1) NF_EW_CASE(4, 1); NF_EW_CASE(4, 2); }
+  // the logistic-regression target (as the objective's target or as the LeapFrog score) gets its own instantiations
+  const bool lr = (tgt && tgt->kind == NF_TARGET_LOGREG) || (f.score_target && f.score_target->kind == NF_TARGET_LOGREG);
+  if (lr && d > 16) {
+    set_error("elementwise flows on the logistic-regression target support dim <= 16, got %d", d);
+    return NF_ERR_UNSUPPORTED;
+  }
+#define NF_EW_ARGS f, tgt, (const T*)theta_dev, N, (const T*)z0_dev, seed, flags, (T*)y_out, (T*)ld_out, (T*)terms_out, gsum_dev, inverse
+#define NF_EW_CASE(DPV, SV)                                                      \
+  do {                                                                           \
+    if (lr) { if constexpr (DPV <= 16) return ew_launch<T, DPV, SV, true, INV>(NF_EW_ARGS); } \
+    return ew_launch<T, DPV, SV, false, INV>(NF_EW_ARGS);                        \
+  } while (0)
+  if (d <= 2) NF_EW_CASE(2, 4);
+  if (d <= 4) NF_EW_CASE(4, 2);
   if (d <= 8) NF_EW_CASE(8, 1);
   if (d <= 16) NF_EW_CASE(16, 1);
   if (d <= 32) NF_EW_CASE(32, 1);
   if (d <= 64) NF_EW_CASE(64, 1);
 #undef NF_EW_CASE
+#undef NF_EW_ARGS
   set_error("elementwise (planar/radial) flows support dim <= 64 in this build, got %d", d);
   return NF_ERR_UNSUPPORTED;
 }
 
-template <typename T, int DP, int S>
+template <typename T, int DP, int S, bool LR>
 static int ew_train_launch(Flow& f, const Target* tgt, int64_t N, uint64_t seed, int n_iters, int t0, double eta, double b1,
                            double b2, double eps, void* m_dev, void* v_dev) {
   const int L = (int)f.layers.size(), d = f.dim;
@@ -1031,7 +1046,7 @@ static int ew_train_launch(Flow& f, const Target* tgt, int64_t N, uint64_t seed,
     set_error("elementwise flow with %d layers needs %zu B of shared memory (limit 200 KiB)", L, smem);
     return NF_ERR_UNSUPPORTED;
   }
-  auto kern = ew_train_kernel<T, DP, S>;
+  auto kern = ew_train_kernel<T, DP, S, LR>;
   NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   f.ws_reset();
   NF_TRY(f.ws_reserve((size_t)4 << 20));
@@ -1067,7 +1082,12 @@ int ew_train(Flow& f, const Target* tgt, int64_t N, uint64_t seed, int n_iters, 
     set_error("Hamiltonian flows / joint targets need dim a power of two, got %d", d);
     return NF_ERR_UNSUPPORTED;
   }
-#define NF_EWT_CASE(DPV, SV) return ew_train_launch<T, DPV, SV>(f, tgt, N, seed, n_iters, t0, eta, b1, b2, eps, m_dev, v_dev)
+  const bool lr = tgt->kind == NF_TARGET_LOGREG || (f.score_target && f.score_target->kind == NF_TARGET_LOGREG);
+#define NF_EWT_CASE(DPV, SV)                                                                                              \
+  do {                                                                                                                    \
+    if (lr) return ew_train_launch<T, DPV, SV, true>(f, tgt, N, seed, n_iters, t0, eta, b1, b2, eps, m_dev, v_dev);        \
+    return ew_train_launch<T, DPV, SV, false>(f, tgt, N, seed, n_iters, t0, eta, b1, b2, eps, m_dev, v_dev);             \
+  } while (0)
   // one sample per thread while the batch fits the CTA (a thread's S samples are a serial dependency chain)
   if (d <= 2) { if (N <= 128) NF_EWT_CASE(2, 1); NF_EWT_CASE(2, 4); }
   if (d <= 4) { if (N <= 128) NF_EWT_CASE(4, 1); NF_EWT_CASE(4, 2); }
@@ -1077,10 +1097,5 @@ int ew_train(Flow& f, const Target* tgt, int64_t N, uint64_t seed, int n_iters, 
   set_error("persistent training kernel supports dim <= 16, got %d", d);
   return NF_ERR_UNSUPPORTED;
 }
-template int ew_train<float>(Flow&, const Target*, int64_t, uint64_t, int, int, double, double, double, double, void*, void*);
-template int ew_train<double>(Flow&, const Target*, int64_t, uint64_t, int, int, double, double, double, double, void*, void*);
-
-template int ew_run<float>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool, bool);
-template int ew_run<double>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool, bool);
 
 }  // namespace nf

@@ -1,0 +1,5 @@
+// Inverse-sweep fused elementwise kernels, double instantiations (see elementwise_impl.cuh).
+#include "elementwise_impl.cuh"
+namespace nf {
+template int ew_run_dir<double, true>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool);
+}  // namespace nf

@@ -149,6 +149,7 @@ struct Flow {
 struct Target {
   int kind = 0, dim = 0;
   bool joint = false;        // dim is then 2 * (inner dim)
+  int n_data = 0;            // LogReg: observations; d_vec holds X[n][dim] then y[n]
   std::vector<double> p;
   double c0 = 0;
   void* d_vec_f32 = nullptr;
@@ -160,17 +161,28 @@ struct Target {
     tp.p1 = p.size() > 1 ? (T)p[1] : T(0);
     tp.c0 = (T)c0;
     tp.vec = (const T*)(sizeof(T) == 4 ? d_vec_f32 : d_vec_f64);
+    tp.n_data = n_data;
     tp.joint = joint ? 1 : 0;
     if (joint) tp.dim = dim / 2;
     return tp;
   }
 };
 
-// elementwise.cu
+// elementwise_{fwd,inv}_{f32,f64}.cu
+template <typename T, bool INV>
+int ew_run_dir(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
+               bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev, bool head);
+extern template int ew_run_dir<float, false>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool);
+extern template int ew_run_dir<float, true>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool);
+extern template int ew_run_dir<double, false>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool);
+extern template int ew_run_dir<double, true>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool);
 template <typename T>
-int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
-           bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev, bool inverse = false,
-           bool head = false);
+inline int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,
+                  bool want_grad, void* y_out, void* ld_out, void* terms_out, double* gsum_dev, bool inverse = false,
+                  bool head = false) {
+  return inverse ? ew_run_dir<T, true>(f, tgt, theta_dev, N, z0_dev, seed, want_grad, y_out, ld_out, terms_out, gsum_dev, head)
+                 : ew_run_dir<T, false>(f, tgt, theta_dev, N, z0_dev, seed, want_grad, y_out, ld_out, terms_out, gsum_dev, head);
+}
 
 // single-launch Adam training loop for small batches of elementwise flows (elementwise.cu: ew_train_kernel)
 template <typename T>

@@ -82,7 +82,8 @@ static int clone_target(const Target& src, Target& dst) {
   dst = src;
   dst.d_vec_f32 = dst.d_vec_f64 = nullptr;
   if (src.d_vec_f32) {
-    const int n = 2 * (src.joint ? src.dim / 2 : src.dim);
+    const int inner_dim = src.joint ? src.dim / 2 : src.dim;
+    const int n = src.kind == NF_TARGET_LOGREG ? src.n_data * inner_dim + src.n_data : 2 * inner_dim;
     NF_CUDA(cudaMalloc(&dst.d_vec_f32, n * sizeof(float)));
     NF_CUDA(cudaMalloc(&dst.d_vec_f64, n * sizeof(double)));
     NF_CUDA(cudaMemcpy(dst.d_vec_f32, src.d_vec_f32, n * sizeof(float), cudaMemcpyDeviceToDevice));
@@ -159,7 +160,7 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
           f->score_target = new Target();
           NF_TRY(clone_target(*st, *f->score_target));
         } else {
-          NF_REQUIRE(f->score_target->kind == st->kind && f->score_target->p == st->p,
+          NF_REQUIRE(f->score_target->kind == st->kind && f->score_target->p == st->p && f->score_target->n_data == st->n_data,
                      "layer %d: all leapfrog layers of a flow must share one score target", i);
         }
         L.K = ds.n_steps;
@@ -507,6 +508,23 @@ int nf_target_create(nf_target_t* out, int kind, int dim, const double* params, 
       NF_CUDA(cudaMalloc(&t->d_vec_f64, 2 * dim * sizeof(double)));
       NF_CUDA(cudaMemcpy(t->d_vec_f32, hf.data(), 2 * dim * sizeof(float), cudaMemcpyHostToDevice));
       NF_CUDA(cudaMemcpy(t->d_vec_f64, params, 2 * dim * sizeof(double), cudaMemcpyHostToDevice));
+      break;
+    }
+    case NF_TARGET_LOGREG: {
+      NF_REQUIRE(n_params >= 2 && params[0] > 0 && params[1] >= 1 && dim <= NF_LOGREG_MAX_DIM,
+                 "LogReg(dim <= %d; sigma0 > 0, n >= 1, X[n*dim], y[n])", NF_LOGREG_MAX_DIM);
+      const int n = (int)params[1];
+      NF_REQUIRE(n_params == 2 + n * dim + n, "LogReg needs 2 + n*dim + n parameters, got %d", n_params);
+      t->n_data = n;
+      t->c0 = -0.5 * dim * (NF_LOG2PI + 2.0 * std::log(params[0]));
+      const int cnt = n * dim + n;
+      std::vector<float> hf(cnt);
+      for (int k = 0; k < cnt; ++k) hf[k] = (float)params[2 + k];
+      NF_CUDA(cudaMalloc(&t->d_vec_f32, cnt * sizeof(float)));
+      NF_CUDA(cudaMalloc(&t->d_vec_f64, cnt * sizeof(double)));
+      NF_CUDA(cudaMemcpy(t->d_vec_f32, hf.data(), cnt * sizeof(float), cudaMemcpyHostToDevice));
+      NF_CUDA(cudaMemcpy(t->d_vec_f64, params + 2, cnt * sizeof(double), cudaMemcpyHostToDevice));
+      t->p.resize(1);      // p[0] = sigma0 (the data live on the device)
       break;
     }
     default:

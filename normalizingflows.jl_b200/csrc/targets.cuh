@@ -10,15 +10,19 @@ template <typename T> struct TargetParams {
   int dim;
   T p0, p1;        // scalar parameters
   T c0;            // precomputed constant part of logp
-  const T* vec;    // DiagNormal: mu[dim] then sigma[dim] (device memory)
+  const T* vec;    // DiagNormal: mu[dim] then sigma[dim]; LogReg: X[n][dim] then y[n] (device memory); p0 = sigma0, n_data = n
+  int n_data;      // LogReg: number of observations
   int joint;       // 1: logp(z) = logp_inner(z[0:dim]) + sum logN(z[dim:2dim]; 0, 1)  (demo_hamiltonian_flow.jl:117-124)
 };
 
 #define NF_LOG2PI 1.8378770664093454835606594728112
+#define NF_LOGREG_MAX_DIM 256
 
 // z, g: arrays of length >= d (registers when DP > 0 and loops unroll, else any memory).
 // Returns logp(z) and writes g = dlogp/dz.
-template <typename T, int DP>
+// LR = false compiles the (data-set walking) logistic-regression case out: the fused elementwise kernels are instantiated both
+// ways so that the common targets keep their register budget.
+template <typename T, int DP, bool LR = true>
 __device__ __forceinline__ T target_logp_score(const TargetParams<T>& tp, const T* z, T* g) {
   using N = Num<T>;
   const int d = tp.dim;
@@ -108,6 +112,45 @@ __device__ __forceinline__ T target_logp_score(const TargetParams<T>& tp, const 
       }
       return tp.c0 - q / 2;
     }
+    case NF_TARGET_LOGREG: if constexpr (LR) {  // u_i = x_i . z ;  logp = sum_i [y_i u_i - softplus(u_i)] - |z|^2 / (2 sigma0^2) + c0
+      const T is2 = 1 / (tp.p0 * tp.p0);
+      const T* X = tp.vec;
+      const T* y = tp.vec + (size_t)tp.n_data * d;
+      T lp = 0, q = 0;
+      T zz[DP > 0 ? DP : 1];   // the inputs are read before g is written (z and g may alias)
+      if (DP > 0) {
+#pragma unroll
+        for (int k = 0; k < UB; ++k) { if (k >= d) break; zz[k] = z[k]; q += z[k] * z[k]; g[k] = -z[k] * is2; }
+        for (int i = 0; i < tp.n_data; ++i) {
+          const T* xi = X + (size_t)i * d;
+          T u = 0;
+#pragma unroll
+          for (int k = 0; k < UB; ++k) { if (k >= d) break; u += xi[k] * zz[k]; }
+          const T yi = y[i];
+          lp += yi * u - softplus_stable<T>(u);
+          const T r = yi - sigmoid_stable<T>(u);
+#pragma unroll
+          for (int k = 0; k < UB; ++k) { if (k >= d) break; g[k] += r * xi[k]; }
+        }
+      } else {
+        // generic-memory variant (heads of the layered path, where z and g may be the SAME row): private copies of the input
+        // and of the score accumulator live in (L1-resident) local memory, so the data set is walked once
+        T zc[NF_LOGREG_MAX_DIM], acc[NF_LOGREG_MAX_DIM];
+        for (int k = 0; k < d; ++k) { zc[k] = z[k]; q += zc[k] * zc[k]; acc[k] = -zc[k] * is2; }
+        for (int i = 0; i < tp.n_data; ++i) {
+          const T* xi = X + (size_t)i * d;
+          T u = 0;
+          for (int k = 0; k < d; ++k) u += xi[k] * zc[k];
+          const T yi = y[i];
+          lp += yi * u - softplus_stable<T>(u);
+          const T r = yi - sigmoid_stable<T>(u);
+          for (int k = 0; k < d; ++k) acc[k] += r * xi[k];
+        }
+        for (int k = 0; k < d; ++k) g[k] = acc[k];
+      }
+      return tp.c0 + lp - q * is2 / 2;
+    }
+    break;
   }
   return 0;
 }
@@ -115,7 +158,7 @@ __device__ __forceinline__ T target_logp_score(const TargetParams<T>& tp, const 
 // out = (Hessian of logp at x) * w -- the second-order term the reverse sweep through a LeapFrog layer needs
 // (reference example/demo_hamiltonian_flow.jl:49-61 differentiates through `∇logp`).  Supported for the targets
 // whose score is smooth and closed-form: Banana, Funnel, DiagNormal.
-template <typename T, int DP>
+template <typename T, int DP, bool LR = true>
 __device__ __forceinline__ void target_hvp(const TargetParams<T>& tp, const T* x, const T* w, T* out) {
   using N = Num<T>;
   const int d = tp.dim;
@@ -158,11 +201,28 @@ __device__ __forceinline__ void target_hvp(const TargetParams<T>& tp, const T* x
       }
       return;
     }
+    case NF_TARGET_LOGREG: if constexpr (LR) {  // H w = -X^T diag(s (1 - s)) X w - w / sigma0^2,  s = sigmoid(X x)
+      const T is2 = 1 / (tp.p0 * tp.p0);
+      const T* X = tp.vec;
+#pragma unroll
+      for (int k = 0; k < UB; ++k) { if (k >= d) break; out[k] = -w[k] * is2; }
+      for (int i = 0; i < tp.n_data; ++i) {
+        const T* xi = X + (size_t)i * d;
+        T u = 0, xw = 0;
+#pragma unroll
+        for (int k = 0; k < UB; ++k) { if (k >= d) break; u += xi[k] * x[k]; xw += xi[k] * w[k]; }
+        const T sg = sigmoid_stable<T>(u);
+        const T cfac = -sg * (1 - sg) * xw;
+#pragma unroll
+        for (int k = 0; k < UB; ++k) { if (k >= d) break; out[k] += cfac * xi[k]; }
+      }
+      return;
+    }
   }
 }
 
 __host__ __device__ inline bool target_has_hvp(int kind) {
-  return kind == NF_TARGET_BANANA || kind == NF_TARGET_FUNNEL || kind == NF_TARGET_DIAG_NORMAL;
+  return kind == NF_TARGET_BANANA || kind == NF_TARGET_FUNNEL || kind == NF_TARGET_DIAG_NORMAL || kind == NF_TARGET_LOGREG;
 }
 
 }  // namespace nf

@@ -774,6 +774,8 @@ def target_score(target):
         return lambda x: _score_banana(x, target.b, target.var)
     if isinstance(target, DiagNormal):
         return lambda x: -(x - target.mu.to(x.dtype)) / target.sigma.to(x.dtype) ** 2
+    if isinstance(target, LogReg):
+        return target.score
     raise TypeError("no score function for %r" % (target,))
 
 
@@ -819,6 +821,39 @@ class DiagNormal(Target):
         mu, sg = self.mu.to(y.dtype), self.sigma.to(y.dtype)
         z = (y - mu) / sg
         return -0.5 * self.dim * LOG2PI - torch.log(sg).sum() - 0.5 * (z * z).sum(dim=1)
+
+
+class LogReg(Target):
+    """Synthetic Bayesian logistic-regression posterior (BASELINE config 5 names it; the reference itself has no such
+    target -- SURVEY section 8f rank 1):  logp(beta) = sum_i [y_i u_i - softplus(u_i)] + log N(beta; 0, sigma0^2 I),
+    u = X beta, X [n, dim], y in {0, 1}^n."""
+    kind = "logreg"
+
+    def __init__(self, X, y, sigma0=1.0):
+        self.X = torch.as_tensor(X, dtype=torch.float64)
+        self.y = torch.as_tensor(y, dtype=torch.float64)
+        self.sigma0 = float(sigma0)
+        self.dim = self.X.shape[1]
+
+    def logp(self, b):
+        X, y = self.X.to(b.dtype), self.y.to(b.dtype)
+        u = b @ X.T                                             # [N, n]
+        ll = (y * u - _softplus(u)).sum(dim=1)
+        return ll - 0.5 * (b * b).sum(dim=1) / self.sigma0 ** 2 - 0.5 * self.dim * (LOG2PI + 2 * math.log(self.sigma0))
+
+    def score(self, b):
+        X, y = self.X.to(b.dtype), self.y.to(b.dtype)
+        u = b @ X.T
+        return (y - torch.sigmoid(u)) @ X - b / self.sigma0 ** 2
+
+
+def synthetic_logreg(dim: int, n: int, seed: int = 7, sigma0: float = 1.0) -> "LogReg":
+    """Deterministic synthetic data set: X ~ N(0, 1/dim), beta* ~ N(0, 1), y ~ Bernoulli(sigmoid(X beta*))."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    X = rng.standard_normal((n, dim)) / math.sqrt(dim)
+    bstar = rng.standard_normal(dim)
+    y = (rng.uniform(size=n) < 1.0 / (1.0 + np.exp(-X @ bstar))).astype(np.float64)
+    return LogReg(X, y, sigma0)
 
 
 # ----------------------------------------------------------------------------------------------

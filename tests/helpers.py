@@ -87,6 +87,8 @@ def gpu_target(nf, ot):
         return nf.Cross(ot.mu, ot.sigma, ot.dim)
     if isinstance(ot, O.DiagNormal):
         return nf.DiagNormal(ot.mu.numpy(), ot.sigma.numpy())
+    if isinstance(ot, O.LogReg):
+        return nf.LogReg(ot.X.numpy(), ot.y.numpy(), ot.sigma0)
     if isinstance(ot, O.JointTarget):
         return nf.JointTarget(gpu_target(nf, ot.inner))
     raise TypeError(ot)

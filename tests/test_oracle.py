@@ -213,3 +213,14 @@ def test_hamiltonian_flow_theta_layout_and_gradient():
     z = xs[:3]
     ref = tgt.logp(z[:, :2]) + torch.distributions.Normal(0, 1).log_prob(z[:, 2:]).sum(dim=1)
     assert float((jt.logp(z) - ref).abs().max()) < 1e-12
+
+
+def test_logreg_target_score_and_normalisation():
+    """LogReg: closed-form score == autograd; with no data the target is exactly N(0, sigma0^2 I)."""
+    tgt = O.synthetic_logreg(5, 30, sigma0=1.5)
+    x = torch.from_numpy(np.random.default_rng(4).standard_normal((6, 5))).requires_grad_(True)
+    (g,) = torch.autograd.grad(tgt.logp(x).sum(), x)
+    assert float((g - tgt.score(x.detach())).abs().max()) < 1e-12
+    empty = O.LogReg(np.zeros((0, 5)), np.zeros(0), sigma0=1.5)
+    ref = torch.distributions.Normal(torch.tensor(0.0, dtype=torch.float64), torch.tensor(1.5, dtype=torch.float64)).log_prob(x.detach()).sum(dim=1)
+    assert float((empty.logp(x.detach()) - ref).abs().max()) < 1e-12
