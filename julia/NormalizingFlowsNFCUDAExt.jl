@@ -43,7 +43,7 @@ end
     AutoNFCUDA(; device = 0, target)
 
 `target` names a device-side log-density: `(:banana, b, var)`, `(:funnel, μ, σ)`, `(:warped_gauss, σ1, σ2)`,
-`(:cross, μ, σ)`, `(:diag_normal, μ, σ)`.  The Julia `logp` closure handed to `train_flow` is used only
+`(:cross, μ, σ)`, `(:diag_normal, μ, σ)`, `(:logreg, σ₀, n, X, y)`; `(:joint, kind, params...)` wraps any of them with N(0, I) momenta.  The Julia `logp` closure handed to `train_flow` is used only
 to recognise the example targets; an arbitrary closure cannot cross the C ABI (use `nf_forward_stash` /
 `nf_backward` with CUDA.jl evaluating logp and its score on the device buffer).
 """
@@ -109,7 +109,8 @@ mutable struct Prep
     T::DataType
 end
 
-target_kind(s::Symbol) = Dict(:banana => 1, :funnel => 2, :warped_gauss => 3, :cross => 4, :diag_normal => 5)[s]
+target_kind(s::Symbol) = Dict(:banana => 1, :funnel => 2, :warped_gauss => 3, :cross => 4, :diag_normal => 5, :logreg => 6)[s]
+# (:logreg, σ₀, n, vec(X'), y): X' is the n×dim design matrix flattened row by row, i.e. vec of the dim×n Julia matrix
 
 function make_prep(flow::Bijectors.TransformedDistribution, ad::AutoNFCUDA, ::Type{T}) where {T}
     check(ccall((:nf_init, libnfcuda), Cint, (Cint,), ad.device))
