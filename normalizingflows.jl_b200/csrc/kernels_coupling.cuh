@@ -347,46 +347,6 @@ template <typename T> struct RqsBin {
   T Sw, Sh;               // softmax denominators
 };
 
-// Locate the bin of v along `logits_search` (widths for forward, heights for inverse) and fetch the
-// matching knots of the other family plus the two derivatives.
-template <typename T, bool INV>
-__device__ __forceinline__ void rqs_locate(const T* __restrict__ tw, const T* __restrict__ th, const T* __restrict__ td,
-                                           int K, T B, T v, RqsBin<T>& b) {
-  using N = Num<T>;
-  const T* ts = INV ? th : tw;   // searched family
-  const T* to = INV ? tw : th;   // other family
-  T Ss = 0, So = 0;
-  for (int k = 0; k < K; ++k) { Ss = add_rn(Ss, N::exp(ts[k])); So = add_rn(So, N::exp(to[k])); }
-  const T twoB = 2 * B;
-  T cs = 0, prev = -B, prevc = 0;
-  int bin = K + 1;
-  T s0 = 0, s1 = 0, c0 = 0, c1 = 0;
-  if (!(prev < v)) { bin = 0; }
-  else {
-    for (int k = 1; k <= K; ++k) {
-      cs = add_rn(cs, div_rn(N::exp(ts[k - 1]), Ss));
-      const T knot = add_rn(mul_rn(twoB, cs), -B);
-      if (!(knot < v)) { bin = k; s0 = prev; s1 = knot; c0 = prevc; c1 = cs; break; }
-      prev = knot; prevc = cs;
-    }
-  }
-  b.k = bin;
-  if (bin < 1 || bin > K) return;
-  // other family's knots bin-1, bin
-  T co = 0, o0 = -B, o1 = 0, oc0 = 0, oc1 = 0;
-  for (int k = 1; k <= bin; ++k) {
-    co = add_rn(co, div_rn(N::exp(to[k - 1]), So));
-    const T knot = add_rn(mul_rn(twoB, co), -B);
-    if (k == bin - 1) { o0 = knot; oc0 = co; }
-    if (k == bin) { o1 = knot; oc1 = co; }
-  }
-  if (!INV) { b.x0 = s0; b.x1 = s1; b.cx0 = c0; b.cx1 = c1; b.y0 = o0; b.y1 = o1; b.cy0 = oc0; b.cy1 = oc1; b.Sw = Ss; b.Sh = So; }
-  else      { b.y0 = s0; b.y1 = s1; b.cy0 = c0; b.cy1 = c1; b.x0 = o0; b.x1 = o1; b.cx0 = oc0; b.cx1 = oc1; b.Sh = Ss; b.Sw = So; }
-  // derivatives: d[0] = d[K] = 1, d[j] = log(exp(td[j-1]) + 1)
-  b.d0 = (bin - 1 == 0) ? T(1) : N::log(N::exp(td[bin - 2]) + 1);
-  b.d1 = (bin == K) ? T(1) : N::log(N::exp(td[bin - 1]) + 1);
-}
-
 template <typename T>
 __device__ __forceinline__ void rqs_eval_fwd(const RqsBin<T>& b, T x, T& y, T& lj) {
   using N = Num<T>;

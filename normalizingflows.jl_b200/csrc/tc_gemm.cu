@@ -575,7 +575,8 @@ struct WgradParams {
   int terms;
   const float* x_meta;
   const float* g_meta;
-  double* gW;         // gsum + w_off, row-major [kin][nout]
+  double* gW;         // gsum + w_off (+ sub-block offset), row-major with row stride ldw
+  int ldw;            // row stride of gW = nout of the whole Dense (kin / nout above are the sizes of this sub-block)
 };
 
 template <int BN> struct WgradCfg {
@@ -682,7 +683,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           if (krow < p.kin) {
-            double* g = p.gW + (int64_t)krow * p.nout + c * 32;
+            double* g = p.gW + (int64_t)krow * p.ldw + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (c * 32 + j < p.nout) atomicAdd(&g[j], (double)(__uint_as_float(v[j]) * descale));
@@ -1030,13 +1031,17 @@ int make_map_store(TcState* st, const void* basep, int64_t rows, int64_t cols, i
 }
 
 // MN-major view for wgrad: dims {64, rows, cols/64, 2}, box {64, 32, nblocks, 1} -> smem [block][row][64]
-int make_map_mnmajor(TcState* st, const void* basep, int64_t rows, int64_t cols, int64_t plane_elems, int nblocks, CUtensorMap* out) {
-  auto key = std::make_tuple(basep, rows, cols, plane_elems, nblocks, 1);
+// `cols` = row stride of the planes in elements; `avail_cols` = columns addressable from basep (basep may point at a
+// 256-column sub-block of a wider plane).
+int make_map_mnmajor(TcState* st, const void* basep, int64_t rows, int64_t cols, int64_t plane_elems, int nblocks, CUtensorMap* out,
+                     int64_t avail_cols = 0) {
+  if (avail_cols <= 0) avail_cols = cols;
+  auto key = std::make_tuple(basep, rows, cols * 4096 + avail_cols, plane_elems, nblocks, 1);
   auto itf = st->maps.find(key);
   if (itf != st->maps.end()) { *out = itf->second; return NF_OK; }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return NF_ERR_CUDA; }
-  cuuint64_t gdim[4] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64), 2};
+  cuuint64_t gdim[4] = {64, (cuuint64_t)rows, (cuuint64_t)(avail_cols / 64), 2};
   cuuint64_t gstr[3] = {(cuuint64_t)cols * 2, 128, (cuuint64_t)plane_elems * 2};
   cuuint32_t box[4] = {64, 32, (cuuint32_t)nblocks, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -1295,19 +1300,26 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
     const float* x_meta = meta_of(st, xbuf);
     NF_REQUIRE(g_meta && x_meta, "tcgen05 path: missing tensor metadata (backward)");
     {  // weight gradient
-      NF_REQUIRE(X.ld <= 256 && Gp.ld <= 256, "tcgen05 wgrad supports layer widths up to 256 (got %d x %d)", dp.kin, dp.nout);
-      CUtensorMap mx, mg;
-      const int mt = (int)ceil_div(X.ld, 128);
-      NF_TRY(make_map_mnmajor(st, X.p, n, X.ld, X.plane_elems(), mt * 2, &mx));
-      NF_TRY(make_map_mnmajor(st, Gp.p, n, Gp.ld, Gp.plane_elems(), Gp.ld / 64, &mg));
-      WgradParams wp{};
-      wp.n = n; wp.kin = dp.kin; wp.nout = dp.nout; wp.mt = mt; wp.terms = terms; wp.gW = gsum + dp.w_off;
-      wp.x_meta = x_meta; wp.g_meta = g_meta;
-      switch (Gp.ld) {
-        case 64: NF_TRY(launch_wgrad_bn<64>(f, mx, mg, wp)); break;
-        case 128: NF_TRY(launch_wgrad_bn<128>(f, mx, mg, wp)); break;
-        case 192: NF_TRY(launch_wgrad_bn<192>(f, mx, mg, wp)); break;
-        default: NF_TRY(launch_wgrad_bn<256>(f, mx, mg, wp)); break;
+      // the kernel holds a [<=256 in] x [<=256 out] block of dW^T in TMEM; wider layers are covered block by block
+      for (int i0 = 0; i0 < X.ld; i0 += 256) {
+        for (int j0 = 0; j0 < Gp.ld; j0 += 256) {
+          const int xl = std::min(256, X.ld - i0), gl = std::min(256, Gp.ld - j0);
+          if (i0 >= dp.kin || j0 >= dp.nout) continue;
+          CUtensorMap mx, mg;
+          const int mt = (int)ceil_div(xl, 128);
+          NF_TRY(make_map_mnmajor(st, X.p + i0, n, X.ld, X.plane_elems(), mt * 2, &mx, xl));
+          NF_TRY(make_map_mnmajor(st, Gp.p + j0, n, Gp.ld, Gp.plane_elems(), gl / 64, &mg, gl));
+          WgradParams wp{};
+          wp.n = n; wp.kin = std::min(256, dp.kin - i0); wp.nout = std::min(256, dp.nout - j0); wp.mt = mt; wp.terms = terms;
+          wp.gW = gsum + dp.w_off + (int64_t)i0 * dp.nout + j0; wp.ldw = dp.nout;
+          wp.x_meta = x_meta; wp.g_meta = g_meta;
+          switch (gl) {
+            case 64: NF_TRY(launch_wgrad_bn<64>(f, mx, mg, wp)); break;
+            case 128: NF_TRY(launch_wgrad_bn<128>(f, mx, mg, wp)); break;
+            case 192: NF_TRY(launch_wgrad_bn<192>(f, mx, mg, wp)); break;
+            default: NF_TRY(launch_wgrad_bn<256>(f, mx, mg, wp)); break;
+          }
+        }
       }
     }
     if (i > 0 || G) {  // data gradient (skipped for the first Dense when nobody needs d/d(conditioner input))

@@ -1,0 +1,77 @@
+"""Unusual shapes through the C ABI vs the oracle: hidden widths that are not multiples of the 64-column plane tiles, three-layer
+and one-layer conditioners, widths above 256 (beyond the tcgen05 wgrad tile), arbitrary (non-alternating) coupling masks,
+spline bin counts across the KMAX template buckets, odd dimensions."""
+import numpy as np
+import pytest
+import torch
+
+import nf_oracle as O
+from helpers import gpu_flow, gpu_target, oracle_target, rel_err, z0
+
+pytestmark = pytest.mark.gpu
+TDT = {np.float32: torch.float32, np.float64: torch.float64}
+
+
+def _affine_flow(dim, hdims, masks, dtype, seed=1):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    layers = []
+    for m in masks:
+        c = len(m)
+        layers.append(O.AffineCoupling(dim, list(m), O.fnn(rng, dim - c, hdims, c, "tanh", TDT[dtype]),
+                                       O.fnn(rng, dim - c, hdims, c, None, TDT[dtype])))
+    return O.Flow(dim, layers, dtype=TDT[dtype])
+
+
+def _spline_flow(dim, hdims, K, B, masks, dtype, seed=2):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    layers = [O.NeuralSplineCoupling(dim, K, B, list(m), O.fnn(rng, dim - len(m), hdims, (3 * K - 1) * len(m), None, TDT[dtype]))
+              for m in masks]
+    return O.Flow(dim, layers, dtype=TDT[dtype])
+
+
+def _check(nf, of, of64, ot, N, dtype, tv, tg):
+    xs = z0(N, of.dim, dtype, seed=N + of.dim)
+    v_ref, g_ref = O.elbo_value_and_grad(of, ot, of.theta(), torch.from_numpy(xs))
+    if dtype == np.float32:   # Float32 noise floor of the CPU path itself
+        th = of.theta().clone()
+        v64, g64 = O.elbo_value_and_grad(of64, ot, th.double(), torch.from_numpy(xs).double())
+        tv, tg = max(tv, 2 * abs(v_ref - v64) / max(abs(v64), 1.0)), max(tg, 2 * rel_err(g_ref, g64))
+    v, g = nf.api._elbo_impl(gpu_flow(nf, of, dtype), gpu_target(nf, ot), xs, want_grad=True)
+    assert abs(v - v_ref) <= tv * max(abs(v_ref), 1.0), (v, v_ref)
+    assert rel_err(g, g_ref) <= tg, rel_err(g, g_ref)
+
+
+AFFINE = [
+    (7, [17], [(0, 3, 4), (1, 2, 5, 6)]),                 # one hidden layer, width 17, irregular masks
+    (6, [48, 100, 33], [(0, 1, 2), (3, 4, 5)]),           # three hidden layers, block masks
+    (9, [200, 64], [(8,), (0, 1, 2, 3, 4, 5, 6, 7)]),     # a single transformed coordinate / a single conditioner input
+    (12, [300, 40], [tuple(range(0, 12, 2)), tuple(range(1, 12, 2))]),   # width 300 > 256
+    (70, [96, 96], [tuple(range(0, 70, 2)), tuple(range(1, 70, 2))]),    # 35 conditioner inputs (K padded 35 -> 64), d > 64
+    (8, [512, 300], [(0, 1, 2, 3), (4, 5, 6, 7)]),        # 512 x 300 Dense: 2 x 2 blocks of the tcgen05 weight-gradient tile
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("dim,hdims,masks", AFFINE, ids=["w17", "w48-100-33", "c1", "w300", "d70", "w512x300"])
+def test_affine_coupling_shapes(gpu, dim, hdims, masks, dtype):
+    of = _affine_flow(dim, hdims, masks, dtype)
+    of64 = _affine_flow(dim, hdims, masks, np.float64)
+    tv, tg = (1e-5, 1e-4) if dtype == np.float32 else (1e-9, 1e-7)
+    _check(gpu, of, of64, oracle_target("diag", dim), 333, dtype, tv, tg)
+
+
+SPLINE = [
+    (5, [24], 2, 3.0, [(0, 2, 4), (1, 3)]),          # K = 2 (smallest), one hidden layer
+    (6, [40, 40], 5, 4.0, [(0, 1, 2), (3, 4, 5)]),
+    (4, [32, 32], 16, 5.0, [(0, 3), (1, 2)]),        # KMAX = 16 bucket
+    (4, [32, 32], 33, 6.0, [(1,), (0, 2, 3)]),       # KMAX = 64 bucket, 98 logits per coordinate
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("dim,hdims,K,B,masks", SPLINE, ids=["K2", "K5", "K16", "K33"])
+def test_spline_coupling_shapes(gpu, dim, hdims, K, B, masks, dtype):
+    of = _spline_flow(dim, hdims, K, B, masks, dtype)
+    of64 = _spline_flow(dim, hdims, K, B, masks, np.float64)
+    tv, tg = (2e-5, 2e-4) if dtype == np.float32 else (1e-9, 1e-7)
+    _check(gpu, of, of64, oracle_target("diag", dim), 257, dtype, tv, tg)
