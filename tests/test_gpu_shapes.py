@@ -75,3 +75,33 @@ def test_spline_coupling_shapes(gpu, dim, hdims, K, B, masks, dtype):
     of64 = _spline_flow(dim, hdims, K, B, masks, np.float64)
     tv, tg = (2e-5, 2e-4) if dtype == np.float32 else (1e-9, 1e-7)
     _check(gpu, of, of64, oracle_target("diag", dim), 257, dtype, tv, tg)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("which", ["affine-w17", "affine-w512x300", "spline-K5", "spline-K33"])
+def test_loglikelihood_unusual_shapes(gpu, which, dtype):
+    """forward-KL objective (inverse sweep + implicit-differentiation backward) on the same unusual shapes."""
+    import ctypes as C
+    nf = gpu
+    if which.startswith("affine"):
+        dim, hdims, masks = AFFINE[0] if which == "affine-w17" else AFFINE[5]
+        of = _affine_flow(dim, hdims, masks, dtype)
+    else:
+        dim, hdims, K_, B, masks = SPLINE[1] if which == "spline-K5" else SPLINE[3]
+        of = _spline_flow(dim, hdims, K_, B, masks, dtype)
+    gf = gpu_flow(nf, of, dtype)
+    rng = np.random.Generator(np.random.PCG64(11))
+    xs = (0.7 * rng.standard_normal((150, dim))).astype(dtype)
+    v_ref, g_ref = O.loglik_value_and_grad(of, of.theta(), torch.from_numpy(xs))
+    K = nf._capi
+    val = C.c_double()
+    g = np.empty(gf.theta.size, dtype=dtype)
+    K.check(K.lib().nf_loglik_value_and_grad(gf.handle(), K.ptr(gf.theta), xs.shape[0], K.ptr(xs), 1.0, C.byref(val), K.ptr(g)))
+    tv, tg = (2e-5, 3e-4) if dtype == np.float32 else (1e-9, 1e-7)
+    assert abs(val.value - v_ref) <= tv * max(abs(v_ref), 1.0), (val.value, v_ref)
+    assert rel_err(g, g_ref) <= tg, rel_err(g, g_ref)
+    y, lj = gf.with_logabsdet_jacobian(xs)
+    xr, lji = gf.inverse_with_logabsdet_jacobian(y)
+    rt = 2e-4 if dtype == np.float32 else 1e-9
+    np.testing.assert_allclose(xr, xs, rtol=rt, atol=rt)
+    np.testing.assert_allclose(lj, -lji, rtol=rt, atol=rt)
