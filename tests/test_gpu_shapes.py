@@ -105,3 +105,44 @@ def test_loglikelihood_unusual_shapes(gpu, which, dtype):
     rt = 2e-4 if dtype == np.float32 else 1e-9
     np.testing.assert_allclose(xr, xs, rtol=rt, atol=rt)
     np.testing.assert_allclose(lj, -lji, rtol=rt, atol=rt)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("kind", ["affine", "spline", "planar"])
+def test_non_standard_base_distribution(gpu, kind, dtype):
+    """q0 = MvNormal(mu, Diagonal(sigma^2)) with mu != 0, sigma != 1 (reference example/demo_planar_flow.jl:24 style) under
+    every path: host-supplied draws from q0, log q0 in the ELBO / log-likelihood heads."""
+    nf = gpu
+    dim = 6
+    rng = np.random.Generator(np.random.PCG64(21))
+    mu, sg = rng.standard_normal(dim), rng.uniform(0.5, 2.0, dim)
+    if kind == "affine":
+        of = _affine_flow(dim, [24, 24], [(0, 2, 4), (1, 3, 5)], dtype)
+    elif kind == "spline":
+        of = _spline_flow(dim, [24], 6, 4.0, [(0, 1, 2), (3, 4, 5)], dtype)
+    else:
+        of = O.planarflow(dim, 5, TDT[dtype], rng)
+    of.base_mu, of.base_sigma = torch.from_numpy(mu).to(TDT[dtype]), torch.from_numpy(sg).to(TDT[dtype])
+    ot = oracle_target("diag", dim)
+    xs = (mu + sg * z0(300, dim, np.float64, seed=3)).astype(dtype)          # draws from q0
+    v_ref, g_ref = O.elbo_value_and_grad(of, ot, of.theta(), torch.from_numpy(xs))
+    gf = gpu_flow(nf, of, dtype)
+    v, g = nf.api._elbo_impl(gf, gpu_target(nf, ot), xs, want_grad=True)
+    tv, tg = (2e-5, 2e-4) if dtype == np.float32 else (1e-9, 1e-7)
+    assert abs(v - v_ref) <= tv * max(abs(v_ref), 1.0), (v, v_ref)
+    assert rel_err(g, g_ref) <= tg, rel_err(g, g_ref)
+    ys = (0.8 * z0(200, dim, np.float64, seed=4)).astype(dtype)
+    lp = gf.logpdf(ys)
+    lp_ref = of.logpdf(torch.from_numpy(ys)).detach().numpy()
+    np.testing.assert_allclose(lp, lp_ref, rtol=2e-4 if dtype == np.float32 else 1e-9, atol=2e-4 if dtype == np.float32 else 1e-9)
+
+
+def test_wide_state_fallback_paths(gpu):
+    """d = 300 > 256: the generic coupling kernel and the untiled ELBO head (their row-oriented / shared-memory fast paths stop
+    at 256 columns)."""
+    dim = 300
+    masks = [tuple(range(0, dim, 2)), tuple(range(1, dim, 2))]
+    for dtype, tv, tg in ((np.float64, 1e-9, 1e-7), (np.float32, 2e-5, 2e-4)):
+        of = _affine_flow(dim, [64], masks, dtype)
+        of64 = _affine_flow(dim, [64], masks, np.float64)
+        _check(gpu, of, of64, oracle_target("diag", dim), 200, dtype, tv, tg)
