@@ -15,8 +15,13 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def nf():
+    """The package over libnfcuda.so.  A fresh checkout has no built library (it is git-ignored): compile it first, exactly as
+    `__graft_entry__.build()` does (nvcc cross-compiles sm_100a without a GPU; a few minutes)."""
     import nfload
-    return nfload.load()
+    mod = nfload.load()
+    if not os.path.exists(mod.LIB_PATH):
+        nfload.build()
+    return mod
 
 
 @pytest.fixture(scope="session")
