@@ -224,3 +224,18 @@ def test_logreg_target_score_and_normalisation():
     empty = O.LogReg(np.zeros((0, 5)), np.zeros(0), sigma0=1.5)
     ref = torch.distributions.Normal(torch.tensor(0.0, dtype=torch.float64), torch.tensor(1.5, dtype=torch.float64)).log_prob(x.detach()).sum(dim=1)
     assert float((empty.logp(x.detach()) - ref).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("kind,kw", [("planar", dict(nlayers=3)), ("radial", dict(nlayers=3)),
+                                     ("realnvp", dict(hdims=[8, 8], nlayers=1)),
+                                     ("nsf", dict(hdims=[8, 8], K=6, B=3.0, nlayers=1))])
+def test_logdet_equals_log_abs_det_of_autograd_jacobian(kind, kw):
+    """Independent pin of every layer family's hand-written log|det J| (Bijectors / MonotonicSplines formulas restated in the
+    oracle): it must equal log|det| of the Jacobian torch.autograd builds from the forward map alone."""
+    from helpers import oracle_flow
+    of = oracle_flow(kind, 4, np.float64, **kw)
+    xs = torch.from_numpy(np.random.default_rng(12).standard_normal((5, 4)) * 1.5)
+    _, ld = of.forward(xs)
+    for i in range(xs.shape[0]):
+        J = torch.autograd.functional.jacobian(lambda v: of.forward(v[None, :])[0][0], xs[i])
+        assert abs(float(torch.linalg.slogdet(J)[1]) - float(ld[i])) < 1e-9, (kind, i)
