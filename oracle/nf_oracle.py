@@ -14,7 +14,8 @@ only through the reference's own *property* tests, which `tests/test_oracle.py` 
   test/flow.jl:25-39,92-106,158-172,224-238   inverse consistency (rtol 1e-6 / 1e-4), odd d = 5
   test/flow.jl:42-61        finite elbo / elbo_batch at n = 64 and n = 1
   test/interface.jl:28-50   Shift∘Scale training converges to (10,10,2,2)
-plus autograd-vs-finite-difference checks.  `julia/crosscheck.jl` (shipped, unexecuted here) turns
+plus autograd-vs-finite-difference checks and an independent pin of every hand-written log|det J| (planar, radial, affine
+and spline couplings, leapfrog) against log|det| of the autograd Jacobian of the forward map.  `julia/crosscheck.jl` (shipped, unexecuted here) turns
 the UNVERIFIED switches below into pass/fail on a machine that has Julia.
 
 Layout convention: a Julia `d×N` column-major batch is a row-major `[N, d]` tensor here (each
