@@ -236,6 +236,12 @@ int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, i
                    int32_t* bins, const float* amax_in, float* amax_out) {
   const int d = f.dim, c = (int)Ld.idx1.size(), cbar = (int)Ld.idx2.size();
   const bool tc = f.mma_mode != NF_MMA_SIMT;
+  if (Ld.kind == NF_SHIFT || Ld.kind == NF_SCALE) {
+    diag_apply_kernel<T, INV><<<(unsigned)std::min<int64_t>(ceil_div(n * d, 256), 16 * kNumSMs), 256, 0, f.stream>>>(
+        Xin, theta + Ld.theta_off, Ld.kind == NF_SCALE ? 1 : 0, d, n, Xout, ld, amax_out);
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+  }
   if (tc) {
     NF_TRY(tc_gather_split(f, (const float*)Xin, d, Ld.d_idx2, cbar, n, b.act0, amax_in));
     for (size_t m = 0; m < Ld.mlps.size(); ++m) NF_TRY(tc_mlp_forward(f, Ld, (int)m, n, b.act0, b.acts[m]));
@@ -291,6 +297,13 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
   T* gA = (T*)c.ga[0];
   T* gB = (T*)c.ga[1];
   T* gC = (T*)c.ga[2];
+  if (Ld.kind == NF_SHIFT || Ld.kind == NF_SCALE) {
+    const int64_t rpb = 4096;
+    diag_bwd_kernel<T, INV><<<(unsigned)ceil_div(n, rpb), 256, 0, f.stream>>>(G, INV ? Xout : Xin, theta + Ld.theta_off, gld,
+                                                                            Ld.kind == NF_SCALE ? 1 : 0, d, n, rpb, f.d_gsum + Ld.theta_off);
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+  }
   if (Ld.kind == NF_AFFINE_COUPLING) {
     // gA <- d/d(pre-tanh s), gB <- d/dt
     float* mS = tc ? tc_alloc_meta(f) : nullptr;
@@ -340,8 +353,9 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
 template <typename T>
 int check_supported(const Flow& f) {
   for (auto& L : f.layers)
-    if (!is_coupling(L.kind)) {
-      set_error("flows mixing elementwise layers (planar/radial/shift/scale) with coupling layers are not supported in this build");
+    if (!is_coupling(L.kind) && L.kind != NF_SHIFT && L.kind != NF_SCALE) {
+      set_error("flows mixing planar / radial / Hamiltonian layers with coupling layers are not supported in this build "
+                "(Shift and Scale may be mixed with couplings)");
       return NF_ERR_UNSUPPORTED;
     }
   return NF_OK;

@@ -325,6 +325,65 @@ __global__ void affine_bwd_kernel(T* __restrict__ G, const T* __restrict__ X1src
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bijectors.Shift / Bijectors.Scale inside a layered (coupling) flow: y = x + a / y = a .* x, logdet 0 / sum log|a|
+// (e.g. a trainable `Shift ∘ Scale` pre-conditioner in front of RealNVP layers, the pattern of
+// reference example/demo_hamiltonian_flow.jl:139-142).  One thread per element; exact max |y| for the next plane scale.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool INV>
+__global__ void diag_apply_kernel(const T* __restrict__ Xin, const T* __restrict__ a, int is_scale, int d, int64_t N,
+                                  T* __restrict__ Xout, T* __restrict__ ld, float* __restrict__ amax_meta) {
+  const int64_t total = N * d;
+  float run_max = 0.f;
+  T slog = 0;
+  if (is_scale && ld)
+    for (int k = 0; k < d; ++k) slog += Num<T>::log(Num<T>::abs(a[k]));
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / d;
+    const int k = (int)(e - r * d);
+    const T x = Xin[e];
+    const T y = is_scale ? (INV ? x / a[k] : x * a[k]) : (INV ? x - a[k] : x + a[k]);
+    Xout[e] = y;
+    run_max = fmaxf(run_max, fabsf((float)y));
+    if (is_scale && ld && k == 0) ld[r] += INV ? -slog : slog;
+  }
+  if (amax_meta) amax_update(amax_meta, run_max);
+}
+
+// Backward: G (d/dXout) -> d/dXin in place; parameter gradient sums into ga (double atomics).  blockDim = 32 columns x 8 rows.
+// V = the values the scale gradient multiplies: the layer input x (forward direction) or the inverse's output x = y / a.
+template <typename T, bool INV>
+__global__ void diag_bwd_kernel(T* __restrict__ G, const T* __restrict__ V, const T* __restrict__ a, const T* __restrict__ gld,
+                                int is_scale, int d, int64_t N, int64_t rows_per_block, double* __restrict__ ga) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < N ? r0 + rows_per_block : N;
+  for (int c0 = 0; c0 < d; c0 += 32) {
+    const int c = c0 + cx;
+    double s = 0;
+    if (c < d) {
+      const T ak = a[c];
+      for (int64_t r = r0 + ry; r < r1; r += 8) {
+        const T g = G[r * d + c];
+        const T gl = gld ? gld[r] : T(1);
+        if (!is_scale) s += INV ? -(double)g : (double)g;
+        else if (!INV) { s += (double)(g * V[r * d + c] + gl / ak); G[r * d + c] = g * ak; }
+        else { s += (double)(-g * V[r * d + c] / ak - gl / ak); G[r * d + c] = g / ak; }
+      }
+    }
+    red[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && c < d) {
+      double t = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += red[q][cx];
+      atomicAdd(&ga[c], t);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Rational-quadratic spline coupling (MonotonicSplines v0.3.3 semantics)
 // theta_raw row layout per sample: coordinate i owns rows [i*(3K-1), (i+1)*(3K-1)) = K width logits,
 // K height logits, K-1 derivative logits ("block" layout; see oracle RQS_PARAM_LAYOUT).

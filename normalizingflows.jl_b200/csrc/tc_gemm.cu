@@ -708,10 +708,21 @@ __global__ void absmax_kernel(const float* __restrict__ X, int d, const int* __r
                               float* __restrict__ meta) {
   float m = 0.f;
   const int64_t total = n * n_idx;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = e / n_idx;
-    const int k = (int)(e - r * n_idx);
-    m = fmaxf(m, fabsf(idx ? X[r * d + idx[k]] : X[r * d + k]));
+  if (!idx && d == n_idx && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {   // dense: a flat array, 16-byte loads
+    const int64_t nv = total >> 2;
+    const float4* X4 = reinterpret_cast<const float4*>(X);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nv; e += (int64_t)gridDim.x * blockDim.x) {
+      const float4 v = X4[e];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (int64_t e = (nv << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+      m = fmaxf(m, fabsf(X[e]));
+  } else {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = e / n_idx;
+      const int k = (int)(e - r * n_idx);
+      m = fmaxf(m, fabsf(idx ? X[r * d + idx[k]] : X[r * d + k]));
+    }
   }
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) meta_amax(meta, m);

@@ -146,3 +146,42 @@ def test_wide_state_fallback_paths(gpu):
         of = _affine_flow(dim, [64], masks, dtype)
         of64 = _affine_flow(dim, [64], masks, np.float64)
         _check(gpu, of, of64, oracle_target("diag", dim), 200, dtype, tv, tg)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("kind", ["affine", "spline"])
+def test_shift_scale_mixed_with_couplings(gpu, kind, dtype):
+    """Trainable Shift / Scale layers composed with coupling layers (a `Shift ∘ Scale` pre-conditioner in front of the couplings,
+    one more Scale behind them): ELBO and log-likelihood value + gradient, forward / inverse round trip."""
+    import ctypes as C
+    nf = gpu
+    dim = 6
+    rng = np.random.Generator(np.random.PCG64(31))
+    td = TDT[dtype]
+    core = (_affine_flow(dim, [24, 24], [(0, 2, 4), (1, 3, 5)], dtype) if kind == "affine"
+            else _spline_flow(dim, [24], 6, 4.0, [(0, 1, 2), (3, 4, 5)], dtype)).layers
+    layers = ([O.Scale(torch.from_numpy(rng.uniform(0.6, 1.6, dim)).to(td))] + core +
+              [O.Shift(torch.from_numpy(0.3 * rng.standard_normal(dim)).to(td)),
+               O.Scale(torch.from_numpy(rng.uniform(0.7, 1.4, dim) * rng.choice([-1.0, 1.0], dim)).to(td))])
+    of = O.Flow(dim, layers, dtype=td)
+    ot = oracle_target("diag", dim)
+    xs = z0(300, dim, dtype, seed=5)
+    v_ref, g_ref = O.elbo_value_and_grad(of, ot, of.theta(), torch.from_numpy(xs))
+    gf = gpu_flow(nf, of, dtype)
+    v, g = nf.api._elbo_impl(gf, gpu_target(nf, ot), xs, want_grad=True)
+    tv, tg = (2e-5, 2e-4) if dtype == np.float32 else (1e-9, 1e-7)
+    assert abs(v - v_ref) <= tv * max(abs(v_ref), 1.0), (v, v_ref)
+    assert rel_err(g, g_ref) <= tg, rel_err(g, g_ref)
+    ys = (0.7 * z0(200, dim, np.float64, seed=6)).astype(dtype)
+    vl_ref, gl_ref = O.loglik_value_and_grad(of, of.theta(), torch.from_numpy(ys))
+    K = nf._capi
+    val = C.c_double()
+    gl = np.empty(gf.theta.size, dtype=dtype)
+    K.check(K.lib().nf_loglik_value_and_grad(gf.handle(), K.ptr(gf.theta), ys.shape[0], K.ptr(ys), 1.0, C.byref(val), K.ptr(gl)))
+    assert abs(val.value - vl_ref) <= tv * max(abs(vl_ref), 1.0), (val.value, vl_ref)
+    assert rel_err(gl, gl_ref) <= (3e-4 if dtype == np.float32 else tg), rel_err(gl, gl_ref)
+    y, lj = gf.with_logabsdet_jacobian(xs)
+    xr, lji = gf.inverse_with_logabsdet_jacobian(y)
+    rt = 2e-4 if dtype == np.float32 else 1e-9
+    np.testing.assert_allclose(xr, xs, rtol=rt, atol=rt)
+    np.testing.assert_allclose(lj, -lji, rtol=rt, atol=rt)
