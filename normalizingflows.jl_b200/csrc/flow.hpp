@@ -125,6 +125,7 @@ struct Flow {
   void* d_out = nullptr;               // dtype[P+1] scaled outputs
   void* d_adam = nullptr;              // dtype[2P]: Adam first / second moments (on-device optimiser loop)
   double* d_stats = nullptr;           // [iters][2]: loss, |g|^2
+  int64_t* d_iter = nullptr;           // device iteration counter (+ 2 uints) of the graph-replayed training loop
   int stats_cap = 0;
   void* h_pinned = nullptr;            // pinned staging (P+1 of dtype + 1 double)
   size_t h_pinned_bytes = 0;

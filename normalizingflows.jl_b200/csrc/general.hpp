@@ -15,6 +15,7 @@ struct GeneralJob {
   const void* in_dev = nullptr;
   int64_t N = 0;
   uint64_t seed = 0;
+  const int64_t* seed_iter_dev = nullptr;   // device iteration counter added to the seed (graph-replayed training loop)
   bool want_grad = false;
   void* y_out = nullptr;
   void* ld_out = nullptr;

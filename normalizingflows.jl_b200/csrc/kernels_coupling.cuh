@@ -915,10 +915,14 @@ __global__ void loglik_head_kernel(const T* __restrict__ X0, const T* __restrict
 }
 
 // K7: base draws x = mu + sigma .* randn  (reference ext/NormalizingFlowsCUDAExt.jl:43-48)
+// seed_iter (optional, device): added to the seed -- the iteration counter of a CUDA-graph-replayed training loop, so that one
+// captured launch draws a fresh batch at every replay.
 template <typename T>
-__global__ void base_sample_kernel(T* __restrict__ Z, const T* __restrict__ base, int d, int64_t N, uint64_t seed, int64_t row0) {
+__global__ void base_sample_kernel(T* __restrict__ Z, const T* __restrict__ base, int d, int64_t N, uint64_t seed, int64_t row0,
+                                   const int64_t* __restrict__ seed_iter = nullptr) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N * d) return;
+  if (seed_iter) seed += (uint64_t)*seed_iter;
   const int k = (int)(e % d);
   T z = philox_randn<T>(seed, (uint64_t)(row0 * d + e));
   if (base) z = z * base[d + k] + base[k];

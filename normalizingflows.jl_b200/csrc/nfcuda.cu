@@ -66,6 +66,37 @@ __global__ void adam_step_kernel(const double* __restrict__ gsum, int64_t P, dou
   if (i == 0) stat[0] = -gsum[P] * inv_n;
 }
 
+// Same step for the CUDA-graph-replayed loop: the iteration index lives on the device (one captured launch serves every replay);
+// the last thread block to finish advances it.
+template <typename T>
+__global__ void adam_step_graph_kernel(const double* __restrict__ gsum, int64_t P, double inv_n, double b1d, double b2d, int t0, T eta,
+                                       T eps, T* __restrict__ theta, T* __restrict__ m, T* __restrict__ v, double* __restrict__ stats,
+                                       int64_t* __restrict__ iter, unsigned int* __restrict__ done) {
+  const int64_t it = *iter;
+  const int step = t0 + (int)it + 1;
+  const T b1 = (T)b1d, b2 = (T)b2d;
+  const T omb1t = (T)(1.0 - pow(b1d, (double)step)), omb2t = (T)(1.0 - pow(b2d, (double)step));
+  double* stat = stats + 2 * it;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double g2 = 0;
+  if (i < P) {
+    const T g = (T)(-gsum[i] * inv_n);
+    const T mi = b1 * m[i] + (T(1) - b1) * g;
+    const T vi = b2 * v[i] + (T(1) - b2) * g * g;
+    m[i] = mi; v[i] = vi;
+    theta[i] -= mi / omb1t / (Num<T>::sqrt(vi / omb2t) + eps) * eta;
+    g2 = (double)g * (double)g;
+  }
+  g2 = warp_sum(g2);
+  if ((threadIdx.x & 31) == 0 && g2 != 0) atomicAdd(&stat[1], g2);
+  if (i == 0) stat[0] = -gsum[P] * inv_n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1u) == gridDim.x - 1) { *done = 0; *iter = it + 1; }   // every block has read `it` before this point
+  }
+}
+
 static int check_device() {
   int dev = 0;
   NF_CUDA(cudaGetDevice(&dev));
@@ -250,7 +281,7 @@ static void flow_destroy(Flow* f) {
   for (auto& L : f->layers) { cudaFree(L.d_idx1); cudaFree(L.d_idx2); cudaFree(L.d_pos); }
   cudaFree(f->d_base); cudaFree(f->d_ew_meta); cudaFree(f->d_ew_kinds);
   cudaFree(f->d_theta); cudaFree(f->d_gsum); cudaFree(f->d_out); cudaFreeHost(f->h_pinned);
-  cudaFree(f->d_adam); cudaFree(f->d_stats);
+  cudaFree(f->d_adam); cudaFree(f->d_stats); cudaFree(f->d_iter);
   cudaFree(f->ws.base);
   if (f->score_target) { cudaFree(f->score_target->d_vec_f32); cudaFree(f->score_target->d_vec_f64); delete f->score_target; }
   if (f->ev0) cudaEventDestroy(f->ev0);
@@ -267,6 +298,7 @@ struct Job {
   const void* in_dev = nullptr;       // z0 / x / y; nullptr -> device Philox draws (OP_ELBO / OP_FORWARD)
   int64_t N = 0;
   uint64_t seed = 0;
+  const int64_t* seed_iter_dev = nullptr;
   bool want_grad = false;
   void* y_out = nullptr;              // [N, d]
   void* ld_out = nullptr;             // [N]
@@ -287,7 +319,7 @@ static int run_job(Flow& f, const Job& j) {
     return ew_run<double>(f, j.tgt, j.theta_dev, j.N, j.in_dev, j.seed, j.want_grad, j.y_out, j.ld_out, j.terms_out, gs, inv, head);
   }
   GeneralJob g;
-  g.op = j.op; g.tgt = j.tgt; g.theta_dev = j.theta_dev; g.in_dev = j.in_dev; g.N = j.N; g.seed = j.seed;
+  g.op = j.op; g.tgt = j.tgt; g.theta_dev = j.theta_dev; g.in_dev = j.in_dev; g.N = j.N; g.seed = j.seed; g.seed_iter_dev = j.seed_iter_dev;
   g.want_grad = j.want_grad; g.y_out = j.y_out; g.ld_out = j.ld_out; g.terms_out = j.terms_out; g.bins_out = j.bins_out;
   return general_run(f, g);
 }
@@ -638,6 +670,62 @@ int nf_loglik_value_and_grad_dev(nf_flow_t flow, const void* theta_dev, int64_t 
   return value_and_grad_dev(f, OP_LOGLIK, nullptr, theta_dev, N, xs_dev, 0, scale, value_out, grad_dev_out);
 }
 
+static int train_graph(Flow& f, const Target* t, int64_t N, uint64_t seed, int n_iters, int t0, double eta, double beta1, double beta2,
+                       double eps, char* dm, char* dv) {
+  const int64_t P = f.P;
+  if (!f.d_iter) {
+    NF_CUDA(cudaMalloc((void**)&f.d_iter, sizeof(int64_t) + sizeof(unsigned int) * 2));
+  }
+  NF_CUDA(cudaMemsetAsync(f.d_iter, 0, sizeof(int64_t) + sizeof(unsigned int) * 2, f.stream));
+  unsigned int* d_done = reinterpret_cast<unsigned int*>(f.d_iter + 1);
+  // one untimed warm-up enqueue outside capture: sizes the workspace, builds tensor maps, sets function attributes
+  f.ws_reset();
+  NF_TRY(general_plan_workspace(f, OP_ELBO, N, 0));
+  Job j;
+  j.op = OP_ELBO; j.tgt = t; j.theta_dev = f.d_theta; j.in_dev = nullptr; j.N = N; j.seed = seed; j.seed_iter_dev = f.d_iter; j.want_grad = true;
+  auto enqueue_iteration = [&]() -> int {
+    f.ws_reset();
+    NF_TRY(general_plan_workspace(f, OP_ELBO, N, 0));
+    NF_TRY(run_job(f, j));
+    const int threads = 256;
+    const int blocks = (int)ceil_div(P, threads);
+    if (f.dtype == NF_F32)
+      adam_step_graph_kernel<float><<<blocks, threads, 0, f.stream>>>(f.d_gsum, P, 1.0 / (double)N, beta1, beta2, t0, (float)eta, (float)eps,
+                                                                     (float*)f.d_theta, (float*)dm, (float*)dv, f.d_stats, f.d_iter, d_done);
+    else
+      adam_step_graph_kernel<double><<<blocks, threads, 0, f.stream>>>(f.d_gsum, P, 1.0 / (double)N, beta1, beta2, t0, eta, eps,
+                                                                      (double*)f.d_theta, (double*)dm, (double*)dv, f.d_stats, f.d_iter, d_done);
+    NF_LAUNCH_CHECK();
+    return NF_OK;
+  };
+  NF_TRY(enqueue_iteration());                       // iteration 0, eagerly (also the warm-up)
+  const void* ws_base = f.ws.base;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  NF_CUDA(cudaStreamBeginCapture(f.stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_iteration();
+  const cudaError_t ce = cudaStreamEndCapture(f.stream, &graph);
+  if (rc != NF_OK || ce != cudaSuccess || !graph || f.ws.base != ws_base) {
+    if (graph) cudaGraphDestroy(graph);
+    set_error("CUDA graph capture of the training iteration failed");
+    // iteration 0 has already been applied eagerly: finish the remaining iterations eagerly too
+    for (int it = 1; it < n_iters; ++it) NF_TRY(enqueue_iteration());
+    return NF_OK;
+  }
+  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    cudaGraphDestroy(graph);
+    for (int it = 1; it < n_iters; ++it) NF_TRY(enqueue_iteration());
+    return NF_OK;
+  }
+  for (int it = 1; it < n_iters; ++it) {
+    if (cudaGraphLaunch(exec, f.stream) != cudaSuccess) { cudaGraphExecDestroy(exec); cudaGraphDestroy(graph); set_error("cudaGraphLaunch failed"); return NF_ERR_CUDA; }
+  }
+  NF_CUDA(cudaStreamSynchronize(f.stream));
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  return NF_OK;
+}
+
 int nf_train_elbo_adam(nf_flow_t flow, nf_target_t target, void* theta_host_inout, int64_t N, uint64_t seed, int n_iters,
                        int t0, double eta, double beta1, double beta2, double eps, void* m_host_inout, void* v_host_inout,
                        double* stats_out) {
@@ -675,7 +763,16 @@ int nf_train_elbo_adam(nf_flow_t flow, nf_target_t target, void* theta_host_inou
     if (f.dtype == NF_F32) NF_TRY(ew_train<float>(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv));
     else NF_TRY(ew_train<double>(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv));
   }
-  for (int it = 0; it < n_iters && !persistent; ++it) {
+  // coupling flows with small batches are launch bound (~100 launches per iteration): capture ONE iteration (value + gradient +
+  // Adam, the iteration index and the Philox seed offset read from a device counter) in a CUDA graph and replay it
+  // (NFCUDA_TRAIN_GRAPH=0 disables; a capture problem makes train_graph finish with eager launches)
+  bool graphed = false;
+  if (!persistent && !f.all_elementwise && n_iters >= 4 && N <= ((int64_t)1 << 16) &&
+      !(getenv("NFCUDA_TRAIN_GRAPH") && atoi(getenv("NFCUDA_TRAIN_GRAPH")) == 0)) {
+    NF_TRY(train_graph(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv));   // falls back to eager launches inside
+    graphed = true;
+  }
+  for (int it = 0; it < n_iters && !persistent && !graphed; ++it) {
     f.ws_reset();
     NF_TRY(general_plan_workspace(f, OP_ELBO, N, 0));
     Job j;

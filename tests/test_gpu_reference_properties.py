@@ -110,14 +110,21 @@ def test_device_sampling_statistics(gpu):
 
 
 @pytest.mark.parametrize("T", [np.float32, np.float64], ids=["f32", "f64"])
-def test_on_device_adam_matches_host_loop(gpu, T):
+@pytest.mark.parametrize("kind", ["planar", "realnvp", "nsf"])
+def test_on_device_adam_matches_host_loop(gpu, T, kind):
     """nf_train_elbo_adam == the reference loop body (value_and_gradient + Optimisers.Adam update) run from the host
-    with the same per-iteration Philox seeds."""
+    with the same per-iteration Philox seeds.  planar: the persistent single-launch loop; realnvp / nsf: one iteration captured
+    in a CUDA graph and replayed (iteration index and seed offset read from a device counter)."""
     import ctypes as C
     nf = gpu
     K = nf._capi
     nf.seed(11)
-    flow = nf.planarflow(nf.MvNormal(np.zeros(2)), 5, T)
+    if kind == "planar":
+        flow = nf.planarflow(nf.MvNormal(np.zeros(2)), 5, T)
+    elif kind == "realnvp":
+        flow = nf.realnvp(nf.MvNormal(np.zeros(2)), [16, 16], 2, T)
+    else:
+        flow = nf.nsf(nf.MvNormal(np.zeros(2)), [16, 16], 6, 4.0, 1, T)
     target = nf.Banana(2, 1.0, 10.0)
     n, iters, seed0 = 256, 25, 1234
     # host loop
@@ -136,7 +143,7 @@ def test_on_device_adam_matches_host_loop(gpu, T):
     stats = np.empty((iters, 2))
     K.check(K.lib().nf_train_elbo_adam(flow.handle(), target.handle(), K.ptr(theta_d), n, seed0, iters, 0, 1e-2, 0.9, 0.999, 1e-8,
                                        K.ptr(m), K.ptr(v), stats.ctypes.data_as(C.POINTER(C.c_double))))
-    tol = 2e-4 if T == np.float32 else 1e-9
+    tol = (2e-4 if kind == "planar" else 2e-3) if T == np.float32 else 1e-9   # 25 chained Float32 Adam steps through tensor-core MLPs
     assert np.allclose(theta_d, theta, rtol=tol, atol=tol)
     assert np.allclose(stats[:, 0], np.array(losses, dtype=np.float64), rtol=tol, atol=tol)
     assert np.allclose(m, st["m"], rtol=10 * tol, atol=tol)
