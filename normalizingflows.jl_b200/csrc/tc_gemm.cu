@@ -424,12 +424,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           } else {
             const uint32_t mbits = row_ok ? p.mask_bits[row * p.mask_ld + (col0 >> 5)] : 0u;
             float cs[32];
+            const float dpos = row_ok ? ds_out : 0.f, dneg = 0.01f * dpos;   // rows past M contribute exact zeros
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const bool pa = (mbits >> j) & 1u;          // leakyrelu'(h): 1 where the stashed activation was > 0, else 0.01
               const bool pb = (mbits >> (j + 1)) & 1u;
-              const float a = row_ok ? v[j] * (pa ? ds_out : 0.01f * ds_out) : 0.f;      // scaled values
-              const float b = row_ok ? v[j + 1] * (pb ? ds_out : 0.01f * ds_out) : 0.f;
+              const float a = v[j] * (pa ? dpos : dneg);                       // scaled values
+              const float b = v[j + 1] * (pb ? dpos : dneg);
               run_max = fmaxf(run_max, fmaxf(fabsf(a), fabsf(b)));
               split_pair(a, b, hi[j >> 1], lo[j >> 1]);
               cs[j] = a; cs[j + 1] = b;
