@@ -208,6 +208,7 @@ struct GemmParams {
   int64_t mask_ld;             // words per row
   uint32_t* out_bits;          // EPI_PLANES_ACT: packed sign bits written next to the planes
   int64_t out_bits_ld;
+  int f32_tma;             // EPI_F32_ACT: leave through a TMA store of the staged 32 x 16 fp32 sub-tiles (tmapO is then the fp32 map)
   float* G;                // EPI_SCATTER_ADD
   int ldg;
   const int* idx;
@@ -497,6 +498,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 o4[u] = a;
               }
               *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            }
+            if (p.epi == EPI_F32_ACT && p.f32_tma) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) tma_store_3d(&tmapO, smem_u32(stg), cc0, (int)row_base, 0);   // clipped at M rows / n_store columns
+              continue;
             }
             __syncwarp();
             const int cq = cc0 + (lane & 3) * 4;
@@ -1042,6 +1049,26 @@ int make_map_store(TcState* st, const void* basep, int64_t rows, int64_t cols, i
   return NF_OK;
 }
 
+// fp32 row-major output [rows, cols] with row stride ld: box {16 columns, 32 rows} = the per-warp staging sub-tile (64-byte rows)
+int make_map_store_f32(TcState* st, const void* basep, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
+  auto key = std::make_tuple(basep, rows, cols * 65536 + ld, (int64_t)0, 16, 3);
+  auto itf = st->maps.find(key);
+  if (itf != st->maps.end()) { *out = itf->second; return NF_OK; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return NF_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 1};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(basep), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp32 store) failed: %d (rows %lld cols %lld ld %lld)", (int)r, (long long)rows, (long long)cols, (long long)ld); return NF_ERR_CUDA; }
+  if (st->maps.size() > 4096) st->maps.clear();
+  st->maps[key] = *out;
+  return NF_OK;
+}
+
 // MN-major view for wgrad: dims {64, rows, cols/64, 2}, box {64, 32, nblocks, 1} -> smem [block][row][64]
 // `cols` = row stride of the planes in elements; `avail_cols` = columns addressable from basep (basep may point at a
 // 256-column sub-block of a wider plane).
@@ -1283,6 +1310,11 @@ int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, s
     } else {
       p.epi = EPI_F32_ACT; p.act = md.out_act ? ACT_TANH : ACT_NONE; p.n_store = dp.nout;
       p.out_f32 = (float*)acts[i]; p.out_f32_ld = dp.nout;
+      static const bool f32_tma_ok = !(getenv("NFCUDA_F32_TMA_STORE") && atoi(getenv("NFCUDA_F32_TMA_STORE")) == 0);
+      if (f32_tma_ok && (dp.nout & 3) == 0 && (reinterpret_cast<uintptr_t>(acts[i]) & 15) == 0) {
+        NF_TRY(make_map_store_f32(st, acts[i], n, dp.nout, dp.nout, &mo));
+        p.f32_tma = 1;
+      }
     }
     NF_TRY(launch_gemm(f, bn, ma, mb, mo, p, n_tiles_n));
   }
