@@ -409,16 +409,25 @@ class Flow:
         K.check(K.lib().nf_inverse(self.handle(), K.ptr(self.theta), ys.shape[0], K.ptr(ys), K.ptr(xs), K.ptr(ld)))
         return xs, ld
 
-    def logpdf(self, ys):
-        """logpdf(flow, ys) -- one value per sample."""
+    def logpdf(self, ys, out=None):
+        """logpdf(flow, ys) -- one value per sample.  `out`: optional preallocated (ideally page-locked) result array."""
         ys = self._x(ys)
-        out = np.empty(ys.shape[0], dtype=self.paramtype)
+        if out is None:
+            out = np.empty(ys.shape[0], dtype=self.paramtype)
+        elif out.shape != (ys.shape[0],) or out.dtype != self.paramtype or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous %s array of shape (%d,)" % (np.dtype(self.paramtype).name, ys.shape[0]))
         K.check(K.lib().nf_logpdf(self.handle(), K.ptr(self.theta), ys.shape[0], K.ptr(ys), K.ptr(out)))
         return out
 
-    def rand(self, n: int, seed: int = 0):
-        """rand(flow, n): device Philox base draws pushed through the flow in one batched pass."""
-        ys = np.empty((n, self.dim), dtype=self.paramtype)
+    def rand(self, n: int, seed: int = 0, out=None):
+        """rand(flow, n): device Philox base draws pushed through the flow in one batched pass.  `out`: optional preallocated
+        [n, dim] array (a fresh pageable array per call costs more in page faults than the flow itself at n = 2^20)."""
+        if out is None:
+            ys = np.empty((n, self.dim), dtype=self.paramtype)
+        elif out.shape != (n, self.dim) or out.dtype != self.paramtype or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous %s array of shape (%d, %d)" % (np.dtype(self.paramtype).name, n, self.dim))
+        else:
+            ys = out
         K.check(K.lib().nf_sample(self.handle(), K.ptr(self.theta), n, seed, K.ptr(ys)))
         return ys
 
