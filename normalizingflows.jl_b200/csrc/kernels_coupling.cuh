@@ -517,11 +517,10 @@ constexpr int kMaxStages = 4;
 }  // namespace rq
 
 template <typename T, int KMAX, bool INV>
-__device__ __forceinline__ void rqs_apply_row(T* __restrict__ row, int64_t e, const T* __restrict__ Xin, const int* __restrict__ idx1,
+__device__ __forceinline__ void rqs_apply_row(T* __restrict__ row, int64_t r, int i, const T* __restrict__ Xin, const int* __restrict__ idx1,
                                               int c, int d, int K, T B, T* __restrict__ Xout, int32_t* __restrict__ bins,
                                               float& run_max, T& lj_out, int64_t& r_out, int& i_out) {
-  const int64_t r = e / c;
-  const int i = (int)(e - r * c);
+  const int64_t e = r * c + i;
   const int j = idx1[i];
   const T v = Xin[r * d + j];
   RqsBin<T> b;
@@ -570,6 +569,8 @@ __global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict_
     }
   }
   const bool pow2 = (c & (c - 1)) == 0 && c <= 32 && (blockDim.x % c) == 0;
+  const bool whole_rows = (blockDim.x % c) == 0;          // a tile is whole samples: (row, coordinate) of a thread is loop-invariant
+  const int rows_per_tile = blockDim.x / c, t_row = threadIdx.x / c, t_col = threadIdx.x % c;
   for (int64_t it = 0; it < n_my; ++it) {
     const int buf = (int)(it % stages);
     const int64_t blk = blockIdx.x + it * gridDim.x;
@@ -584,8 +585,10 @@ __global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict_
     }
     rq::wait(rq::s32(&full_bar[buf]), (uint32_t)((it / stages) & 1));
     T lj_out = 0; int64_t r_out = 0; int i_out = -1;
-    const int64_t e = blk * blockDim.x + threadIdx.x;
-    rqs_apply_row<T, KMAX, INV>(tiles + (size_t)buf * tile_elems + threadIdx.x * P3, e, Xin, idx1, c, d, K, B, Xout, bins, run_max,
+    int64_t r; int i;
+    if (whole_rows) { r = blk * rows_per_tile + t_row; i = t_col; }      // no 64-bit division on the hot path
+    else { const int64_t e = blk * blockDim.x + threadIdx.x; r = e / c; i = (int)(e - r * c); }
+    rqs_apply_row<T, KMAX, INV>(tiles + (size_t)buf * tile_elems + threadIdx.x * P3, r, i, Xin, idx1, c, d, K, B, Xout, bins, run_max,
                                 lj_out, r_out, i_out);
     if (ld) {
       if (pow2) {          // the c coordinates of a sample sit in c adjacent lanes: segmented butterfly, one add per sample
@@ -605,7 +608,8 @@ __global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict_
     __syncthreads();
     if ((int)threadIdx.x < rem) {
       T lj_out = 0; int64_t r_out = 0; int i_out = -1;
-      rqs_apply_row<T, KMAX, INV>(tiles + threadIdx.x * P3, e0 + threadIdx.x, Xin, idx1, c, d, K, B, Xout, bins, run_max, lj_out, r_out, i_out);
+      const int64_t e = e0 + threadIdx.x;
+      rqs_apply_row<T, KMAX, INV>(tiles + threadIdx.x * P3, e / c, (int)(e % c), Xin, idx1, c, d, K, B, Xout, bins, run_max, lj_out, r_out, i_out);
       if (ld && lj_out != T(0)) atomicAdd(&ld[r_out], lj_out);
     }
   }
@@ -614,13 +618,11 @@ __global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict_
 
 // One row of the backward: turns the thread's private row of logits into its row of gradients in place.
 template <typename T, int KMAX, bool INV>
-__device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t e, T* __restrict__ G, const T* __restrict__ Vsrc,
+__device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int i, T* __restrict__ G, const T* __restrict__ Vsrc,
                                             const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int K, T B,
                                             float& run_max) {
   using Nm = Num<T>;
   const int P3 = 3 * K - 1;
-  const int64_t r = e / c;
-  const int i = (int)(e - r * c);
   const int j = idx1[i];
   const T v = Vsrc[r * d + j];
   const T go = G[r * d + j];
@@ -734,12 +736,19 @@ __global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, co
     for (int q = 0; q < stages - 1 && q < n_my; ++q)
       rq::load_tile(rq::s32(tiles + (size_t)q * tile_elems), raw + (blockIdx.x + (int64_t)q * gridDim.x) * tile_elems, tile_bytes,
                     rq::s32(&full_bar[q]));
+  const bool whole_rows = (blockDim.x % c) == 0;
+  const int rows_per_tile = blockDim.x / c, t_row = threadIdx.x / c, t_col = threadIdx.x % c;
   for (int64_t it = 0; it < n_my; ++it) {
     const int buf = (int)(it % stages);
     const int64_t blk = blockIdx.x + it * gridDim.x;
     T* tile = tiles + (size_t)buf * tile_elems;
     rq::wait(rq::s32(&full_bar[buf]), (uint32_t)((it / stages) & 1));
-    rqs_bwd_row<T, KMAX, INV>(tile + threadIdx.x * P3, blk * blockDim.x + threadIdx.x, G, Vsrc, gld, idx1, c, d, K, B, run_max);
+    {
+      int64_t r; int i;
+      if (whole_rows) { r = blk * rows_per_tile + t_row; i = t_col; }    // no 64-bit division on the hot path
+      else { const int64_t e = blk * blockDim.x + threadIdx.x; r = e / c; i = (int)(e - r * c); }
+      rqs_bwd_row<T, KMAX, INV>(tile + threadIdx.x * P3, r, i, G, Vsrc, gld, idx1, c, d, K, B, run_max);
+    }
     rq::fence_async();       // generic-proxy writes of the rows -> visible to the bulk store
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -774,7 +783,10 @@ __global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, co
     const int64_t e0 = nfull * blockDim.x;
     for (int i = threadIdx.x; i < rem * P3; i += blockDim.x) tiles[i] = raw[e0 * P3 + i];
     __syncthreads();
-    if ((int)threadIdx.x < rem) rqs_bwd_row<T, KMAX, INV>(tiles + threadIdx.x * P3, e0 + threadIdx.x, G, Vsrc, gld, idx1, c, d, K, B, run_max);
+    if ((int)threadIdx.x < rem) {
+      const int64_t e = e0 + threadIdx.x;
+      rqs_bwd_row<T, KMAX, INV>(tiles + threadIdx.x * P3, e / c, (int)(e % c), G, Vsrc, gld, idx1, c, d, K, B, run_max);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < rem * P3; i += blockDim.x) graw[e0 * P3 + i] = tiles[i];
     if (colsum) {
