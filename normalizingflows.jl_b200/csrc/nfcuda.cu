@@ -767,7 +767,7 @@ int nf_train_elbo_adam(nf_flow_t flow, nf_target_t target, void* theta_host_inou
   // Adam, the iteration index and the Philox seed offset read from a device counter) in a CUDA graph and replay it
   // (NFCUDA_TRAIN_GRAPH=0 disables; a capture problem makes train_graph finish with eager launches)
   bool graphed = false;
-  if (!persistent && !f.all_elementwise && n_iters >= 4 && N <= ((int64_t)1 << 16) &&
+  if (!persistent && !f.all_elementwise && !f.prof.on && n_iters >= 4 && N <= ((int64_t)1 << 16) &&
       !(getenv("NFCUDA_TRAIN_GRAPH") && atoi(getenv("NFCUDA_TRAIN_GRAPH")) == 0)) {
     NF_TRY(train_graph(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv));   // falls back to eager launches inside
     graphed = true;
