@@ -210,6 +210,10 @@ NF_API int nf_rqs_bin_search(int dtype, const void* knots_host, const void* v_ho
 NF_API int nf_tc_gemm_test(int64_t n, int K, int N, const float* X, const float* Wt, const float* b, int terms, float* Y);
 /* Number of kernels launched by this thread's library calls since the last reset (bench.py `gpu_launches`). */
 NF_API int64_t nf_launch_count(int reset);
+/* Process-wide execution options (diagnostics / A-B measurements; results are parity grade either way).
+ *   "fused_coupling"  1 (default): AffineCoupling layers that qualify run the fused conditioner kernels; 0: layer by layer
+ * Returns NF_ERR_INVALID for an unknown name. */
+NF_API int nf_set_option(const char* name, int value);
 /* Duration (ms, CUDA events on the flow's stream) of the device work of the last value_and_grad call. */
 NF_API double  nf_last_device_ms(nf_flow_t flow);
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "nf_rqs_bin_search": (_i, [_i, _vp, _vp, _i64, _i, C.POINTER(C.c_int32)]),
     "nf_tc_gemm_test": (_i, [_i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "nf_launch_count": (_i64, [_i]),
+    "nf_set_option": (_i, [C.c_char_p, _i]),
     "nf_last_device_ms": (_d, [_vp]),
     "nf_profile_enable": (_i, [_vp, _i]),
     "nf_profile_keys": (_i, [_vp, C.c_char_p, _i]),

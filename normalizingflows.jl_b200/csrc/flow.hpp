@@ -132,7 +132,10 @@ struct Flow {
 
   Workspace ws;
   Profiler prof;
-  void ws_reset() { ws.off = 0; }
+  int64_t stash_N = 0;                 // samples of the forward pass kept by nf_forward_stash for nf_backward (0: none)
+  // every entry point that recycles the workspace also drops a stashed forward pass (its pointers live in the workspace),
+  // so a later nf_backward fails with 'needs a preceding nf_forward_stash' instead of reading recycled memory
+  void ws_reset() { ws.off = 0; stash_N = 0; }
   void* ws_alloc(size_t bytes);        // bump allocation, 256 B aligned; nullptr (+error) when exhausted
   int ws_reserve(size_t bytes);        // make sure capacity >= bytes (reallocates; invalidates pointers)
 
@@ -140,9 +143,6 @@ struct Flow {
   int64_t chunk_N = 0;
   void* gen_state = nullptr;
   void* tc_state = nullptr;            // tcgen05 path: prepared weight planes, tensor-map cache
-
-  // state kept by nf_forward_stash for nf_backward
-  int64_t stash_N = 0;
 
   size_t esize() const { return dtype == NF_F64 ? 8 : 4; }
 };

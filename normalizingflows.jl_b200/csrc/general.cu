@@ -242,6 +242,10 @@ int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, i
     NF_LAUNCH_CHECK();
     return NF_OK;
   }
+  if (tc && amax_in && tc_fused_affine_ok(f, Ld)) {
+    // both conditioners, all Dense layers and the coupling arithmetic in one launch (fused_coupling.cuh)
+    return tc_affine_forward_fused(f, Ld, n, (const float*)Xin, (float*)Xout, (float*)ld, b.act0, b.acts, amax_in, amax_out, INV);
+  }
   if (tc) {
     NF_TRY(tc_gather_split(f, (const float*)Xin, d, Ld.d_idx2, cbar, n, b.act0, amax_in));
     for (size_t m = 0; m < Ld.mlps.size(); ++m) NF_TRY(tc_mlp_forward(f, Ld, (int)m, n, b.act0, b.acts[m]));

@@ -10,6 +10,7 @@ namespace nf {
 
 static thread_local std::string g_last_error;
 thread_local int64_t g_launch_count = 0;
+int g_opt_fused_coupling = !(getenv("NFCUDA_FUSED") && atoi(getenv("NFCUDA_FUSED")) == 0);
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -161,12 +162,15 @@ static int upload_base(Flow& f) {
   return NF_OK;
 }
 
+static void flow_destroy(Flow* f);
+
 static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers, int dim, int dtype) {
   NF_REQUIRE(out && descs, "null argument");
   NF_REQUIRE(n_layers > 0 && dim > 0, "need at least one layer and dim > 0");
   NF_REQUIRE(dtype == NF_F32 || dtype == NF_F64, "dtype must be NF_F32 or NF_F64");
   NF_TRY(check_device());
-  std::unique_ptr<Flow> f(new Flow());
+  // flow_destroy (not plain delete) on every failure path: it also frees the device buffers, stream and events created so far
+  std::unique_ptr<Flow, void (*)(Flow*)> f(new Flow(), flow_destroy);
   f->dim = dim; f->dtype = dtype;
   NF_CUDA(cudaGetDevice(&f->device));
   int64_t off = 0;
@@ -221,16 +225,6 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
           L.mlps.resize(1);
           NF_TRY(build_mlp(L.mlps[0], cbar, ds.hdims, ds.n_hidden, (3 * ds.K - 1) * c, 0, off));  // neuralspline.jl:55-56
         }
-        NF_CUDA(cudaMalloc((void**)&L.d_idx1, c * sizeof(int)));
-        NF_CUDA(cudaMalloc((void**)&L.d_idx2, cbar * sizeof(int)));
-        NF_CUDA(cudaMemcpy(L.d_idx1, L.idx1.data(), c * sizeof(int), cudaMemcpyHostToDevice));
-        NF_CUDA(cudaMemcpy(L.d_idx2, L.idx2.data(), cbar * sizeof(int), cudaMemcpyHostToDevice));
-        {
-          std::vector<int> pos(dim, -1);
-          for (int k = 0; k < c; ++k) pos[L.idx1[k]] = k;
-          NF_CUDA(cudaMalloc((void**)&L.d_pos, dim * sizeof(int)));
-          NF_CUDA(cudaMemcpy(L.d_pos, pos.data(), dim * sizeof(int), cudaMemcpyHostToDevice));
-        }
         break;
       }
       default:
@@ -239,6 +233,19 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
     }
     L.n_params = off - L.theta_off;
     f->layers.push_back(std::move(L));
+    if (ds.kind == NF_AFFINE_COUPLING || ds.kind == NF_SPLINE_COUPLING) {
+      // device copies of the masks are created on the layer the flow already owns, so a failure below frees them
+      LayerDesc& Lo = f->layers.back();
+      const int c = (int)Lo.idx1.size(), cbar = (int)Lo.idx2.size();
+      NF_CUDA(cudaMalloc((void**)&Lo.d_idx1, c * sizeof(int)));
+      NF_CUDA(cudaMalloc((void**)&Lo.d_idx2, cbar * sizeof(int)));
+      NF_CUDA(cudaMemcpy(Lo.d_idx1, Lo.idx1.data(), c * sizeof(int), cudaMemcpyHostToDevice));
+      NF_CUDA(cudaMemcpy(Lo.d_idx2, Lo.idx2.data(), cbar * sizeof(int), cudaMemcpyHostToDevice));
+      std::vector<int> pos(dim, -1);
+      for (int k = 0; k < c; ++k) pos[Lo.idx1[k]] = k;
+      NF_CUDA(cudaMalloc((void**)&Lo.d_pos, dim * sizeof(int)));
+      NF_CUDA(cudaMemcpy(Lo.d_pos, pos.data(), dim * sizeof(int), cudaMemcpyHostToDevice));
+    }
   }
   f->P = off;
   f->mma_mode = (dtype == NF_F32) ? NF_MMA_F16X3 : NF_MMA_SIMT;
@@ -758,10 +765,14 @@ int nf_train_elbo_adam(nf_flow_t flow, nf_target_t target, void* theta_host_inou
   NF_CUDA(cudaEventRecord(f.ev0, f.stream));
   // small batches of elementwise flows: every iteration inside one persistent single-CTA launch (NFCUDA_TRAIN_PERSISTENT=0 disables)
   const bool persistent_ok = !(getenv("NFCUDA_TRAIN_PERSISTENT") && atoi(getenv("NFCUDA_TRAIN_PERSISTENT")) == 0);
-  const bool persistent = persistent_ok && f.all_elementwise && f.dim <= 16 && N <= 2048;
+  bool persistent = persistent_ok && f.all_elementwise && f.dim <= 16 && N <= 2048;
   if (persistent) {
-    if (f.dtype == NF_F32) NF_TRY(ew_train<float>(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv));
-    else NF_TRY(ew_train<double>(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv));
+    // NF_ERR_UNSUPPORTED = "does not qualify" (e.g. the layer tables of a very deep flow exceed the shared memory of one
+    // CTA): fall through to the multi-launch loop below instead of failing the call
+    const int s = f.dtype == NF_F32 ? ew_train<float>(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv)
+                                    : ew_train<double>(f, t, N, seed, n_iters, t0, eta, beta1, beta2, eps, dm, dv);
+    if (s == NF_ERR_UNSUPPORTED) persistent = false;
+    else NF_TRY(s);
   }
   // coupling flows with small batches are launch bound (~100 launches per iteration): capture ONE iteration (value + gradient +
   // Adam, the iteration index and the Philox seed offset read from a device counter) in a CUDA graph and replay it
@@ -900,6 +911,12 @@ int64_t nf_launch_count(int reset) {
   const int64_t c = g_launch_count;
   if (reset) g_launch_count = 0;
   return c;
+}
+
+int nf_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "fused_coupling")) { g_opt_fused_coupling = value; return NF_OK; }
+  set_error("nf_set_option: unknown option '%s'", name ? name : "(null)");
+  return NF_ERR_INVALID;
 }
 
 double nf_last_device_ms(nf_flow_t flow) { return flow ? NF_FLOW(flow).last_ms : -1.0; }

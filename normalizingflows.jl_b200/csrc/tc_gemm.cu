@@ -952,6 +952,7 @@ struct TcState {
   std::map<const void*, int> slot_of;
   int64_t pool_elems = 0, bias_elems = 0;
   std::map<std::tuple<const void*, int64_t, int64_t, int64_t, int, int>, CUtensorMap> maps;
+  std::map<int, int*> pos2;                 // fused path: [dim] position of a column inside idx2 (or -1), per layer
 };
 
 inline int pick_bn(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
@@ -1218,6 +1219,8 @@ int split_into_planes(Flow& f, TcState* st, const float* X, int d, const int* d_
   return NF_OK;
 }
 
+#include "fused_coupling.cuh"
+
 }  // namespace
 
 size_t tc_act_bytes(int64_t n, int width) {
@@ -1230,6 +1233,7 @@ void tc_release(Flow& f) {
   TcState* st = get_state(f);
   if (!st) return;
   cudaFree(st->pool); cudaFree(st->bias_pool); cudaFree(st->d_preps); cudaFree(st->d_scalars); cudaFree(st->meta_pool);
+  for (auto& kv : st->pos2) cudaFree(kv.second);
   delete st;
   f.tc_state = nullptr;
 }
@@ -1398,6 +1402,83 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
   return NF_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fused AffineCoupling forward (fused_coupling.cuh)
+// ---------------------------------------------------------------------------------------------
+bool tc_fused_affine_ok(const Flow& f, const LayerDesc& Ld) {
+  if (!g_opt_fused_coupling || f.dtype != NF_F32 || f.mma_mode == NF_MMA_SIMT) return false;
+  if (Ld.kind != NF_AFFINE_COUPLING || Ld.mlps.size() != 2) return false;
+  const int d = f.dim, c = (int)Ld.idx1.size(), cbar = (int)Ld.idx2.size();
+  if ((d & 3) || d > 64 || c < 1 || c > 32 || cbar < 1 || cbar > 64) return false;
+  for (const MLPDesc& md : Ld.mlps) {
+    if (md.n_dense() != 3 || md.dims[0] != cbar || md.dims[3] != c) return false;
+    if (md.dims[1] != md.dims[2] || pad64(md.dims[1]) > 256) return false;
+  }
+  return Ld.mlps[0].dims[1] == Ld.mlps[1].dims[1];
+}
+
+int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float* Xin, float* Xout, float* ld, void* act0,
+                            std::vector<std::vector<void*>>& acts, const float* x_meta, float* y_meta, bool inv) {
+  TcState* st = get_state(f);
+  NF_REQUIRE(st && x_meta, "fused coupling: missing state / input bound");
+  const int li = (int)(&Ld - f.layers.data());
+  const int d = f.dim, c = (int)Ld.idx1.size(), cbar = (int)Ld.idx2.size();
+  const int H = Ld.mlps[0].dims[1], h_ld = pad64(H);
+  int*& d_pos2 = st->pos2[li];
+  if (!d_pos2) {
+    std::vector<int> pos2(d, -1);
+    for (int k = 0; k < cbar; ++k) pos2[Ld.idx2[k]] = k;
+    NF_CUDA(cudaMalloc((void**)&d_pos2, d * sizeof(int)));
+    NF_CUDA(cudaMemcpy(d_pos2, pos2.data(), d * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  FusedFwdMaps maps;
+  FusedFwdParams p{};
+  p.n = n; p.d = d; p.c = c; p.cbar = cbar; p.nch = h_ld / 64; p.kk1 = (cbar + 15) / 16; p.inv = inv ? 1 : 0;
+  p.terms = f.mma_mode == NF_MMA_F16X1 ? 1 : 3;
+  p.Xin = Xin; p.Xout = Xout; p.ld = ld; p.pos = Ld.d_pos; p.pos2 = d_pos2; p.x_meta = x_meta; p.y_meta = y_meta;
+  p.h_ld = h_ld; p.h_plane_elems = round_up(n, 128) * h_ld;
+  Planes A0 = planes_of(act0, n, cbar);
+  NF_REQUIRE(A0.ld == 64, "fused coupling: conditioner input wider than 64");
+  NF_TRY(make_map_kmajor(st, A0.p, n, A0.ld, A0.plane_elems(), 128, &maps.x2));
+  p.x2_meta = new_meta(st, act0);
+  NF_REQUIRE(p.x2_meta, "tcgen05 path: out of tensor metadata slots");
+  for (int m = 0; m < 2; ++m) {
+    FusedNet& N = p.net[m];
+    for (int i = 0; i < 3; ++i) {
+      const int pi = st->index[li][m][i];
+      const DensePrep& dp = st->preps[pi];
+      N.w_sc[i] = st->d_scalars + 4 * pi;
+      N.bias[i] = st->bias_pool + dp.bias_off;
+      NF_REQUIRE(dp.kin_p == (i == 0 ? 64 : h_ld) && dp.nf_rows >= (i == 2 ? 32 : h_ld), "fused coupling: unexpected weight plane shape");
+      NF_TRY(make_map_kmajor(st, st->pool + dp.wf_off, dp.nf_rows, dp.kin_p, (int64_t)dp.nf_rows * dp.kin_p, i == 2 ? 32 : 64, &maps.w[m][i]));
+      if (i < 2) {
+        Planes O = planes_of(acts[m][i], n, H);
+        N.h_planes[i] = O.p;
+        N.h_bits[i] = reinterpret_cast<uint16_t*>(O.bits());
+        N.h_meta[i] = new_meta(st, acts[m][i]);
+        NF_REQUIRE(N.h_meta[i], "tcgen05 path: out of tensor metadata slots");
+      }
+    }
+    N.out = (float*)acts[m][2];
+  }
+  p.dbg_flags = getenv("NFCUDA_DBG_FLAGS") ? atoi(getenv("NFCUDA_DBG_FLAGS")) : 0;
+  p.rz[0] = rz_compensation(cbar, 1, 1);
+  p.rz[1] = rz_compensation(H, h_ld / 64, 1);
+  p.rz[2] = rz_compensation(H, h_ld / 64, 1);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NF_CUDA(cudaFuncSetAttribute(fused_affine_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM));
+    attr_set = true;
+  }
+  const int64_t tiles = ceil_div(n, 128);
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, kNumSMs);
+  f.prof.begin("fused_affine_fwd", f.stream);
+  fused_affine_fwd_kernel<<<grid, FusedCfg::THREADS, FusedCfg::SMEM, f.stream>>>(maps, p);
+  f.prof.end(f.stream);
+  NF_LAUNCH_CHECK();
+  return NF_OK;
+}
 
 // Test hook: Y[n, N] = X[n, K] * Wt[K, N] + b through the tcgen05 forward GEMM (one Dense, no activation).
 int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* Wt_host, const float* b_host, int terms,
