@@ -1050,6 +1050,27 @@ int make_map_store(TcState* st, const void* basep, int64_t rows, int64_t cols, i
   return NF_OK;
 }
 
+// Store view of split planes for the fused coupling kernel: dims {cols, rows, 2}, box {16, 32, 1}, SWIZZLE_32B
+// (one warp's piece of a hidden-activation chunk: 32 rows x 32 bytes)
+int make_map_store32(TcState* st, const void* basep, int64_t rows, int64_t cols, int64_t plane_elems, CUtensorMap* out) {
+  auto key = std::make_tuple(basep, rows, cols, plane_elems, 16, 4);
+  auto itf = st->maps.find(key);
+  if (itf != st->maps.end()) { *out = itf->second; return NF_OK; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return NF_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  cuuint64_t gstr[2] = {(cuuint64_t)cols * 2, (cuuint64_t)plane_elems * 2};
+  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(basep), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (store32) failed: %d (rows %lld cols %lld)", (int)r, (long long)rows, (long long)cols); return NF_ERR_CUDA; }
+  if (st->maps.size() > 4096) st->maps.clear();
+  st->maps[key] = *out;
+  return NF_OK;
+}
+
 // fp32 row-major output [rows, cols] with row stride ld: box {16 columns, 32 rows} = the per-warp staging sub-tile (64-byte rows)
 int make_map_store_f32(TcState* st, const void* basep, int64_t rows, int64_t cols, int64_t ld, CUtensorMap* out) {
   auto key = std::make_tuple(basep, rows, cols * 65536 + ld, (int64_t)0, 16, 3);
@@ -1455,6 +1476,7 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
       if (i < 2) {
         Planes O = planes_of(acts[m][i], n, H);
         N.h_planes[i] = O.p;
+        NF_TRY(make_map_store32(st, O.p, n, O.ld, O.plane_elems(), &maps.h[m][i]));
         N.h_bits[i] = reinterpret_cast<uint16_t*>(O.bits());
         N.h_meta[i] = new_meta(st, acts[m][i]);
         NF_REQUIRE(N.h_meta[i], "tcgen05 path: out of tensor metadata slots");
@@ -1473,10 +1495,31 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
   }
   const int64_t tiles = ceil_div(n, 128);
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, kNumSMs);
+  long long* d_dbg = nullptr;
+  static int dbg_seen = 0;
+  if (getenv("NFCUDA_DBG") && !strcmp(getenv("NFCUDA_DBG"), "fused_fwd") && dbg_seen++ == (getenv("NFCUDA_DBG_SKIP") ? atoi(getenv("NFCUDA_DBG_SKIP")) : 0)) {
+    NF_CUDA(cudaMalloc((void**)&d_dbg, 3 * 512 * sizeof(long long)));
+    NF_CUDA(cudaMemset(d_dbg, 0, 3 * 512 * sizeof(long long)));
+    p.dbg = d_dbg;
+  }
   f.prof.begin("fused_affine_fwd", f.stream);
   fused_affine_fwd_kernel<<<grid, FusedCfg::THREADS, FusedCfg::SMEM, f.stream>>>(maps, p);
   f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
+  if (d_dbg) {
+    std::vector<long long> h(3 * 512);
+    NF_CUDA(cudaStreamSynchronize(f.stream));
+    NF_CUDA(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_dbg);
+    long long t0 = 0;
+    for (auto v : h) if (v && (!t0 || v < t0)) t0 = v;
+    fprintf(stderr, "[nfcuda dbg] fused_fwd grid %u tiles %lld: clock64 relative to the first event (CTA 0)\n", grid, (long long)tiles);
+    for (int r = 0; r < 3; ++r) {
+      fprintf(stderr, "  role %d:", r);
+      for (int i = 0; i < 512; ++i) { if (i % 4 == 0) fprintf(stderr, " |"); fprintf(stderr, " %lld", h[r * 512 + i] ? h[r * 512 + i] - t0 : -1); }
+      fprintf(stderr, "\n");
+    }
+  }
   return NF_OK;
 }
 

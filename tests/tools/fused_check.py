@@ -79,6 +79,9 @@ def timing(N):
 
 
 if __name__ == "__main__":
+    if "--n17" in sys.argv:
+        timing(1 << 17)
+        sys.exit(0)
     if "--time" in sys.argv:
         timing(1 << 17)
         timing(1 << 20)
