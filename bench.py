@@ -247,7 +247,9 @@ def run_side_config(args):
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement oracle (kind 'port') on all host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU arithmetic for this path, restated (oracle port, kind 'port'), on all host
+    cores, a bounded sample of the workload per step.  The Julia reference itself is not installable here (no Julia, no
+    network; Bijectors / MonotonicSplines / Flux / Zygote are not vendored), so `julia_threads` is null."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -255,7 +257,7 @@ def run_reference(args):
     import nf_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_s = 1 << 13
+    n_s = 1 << 14
     rng = np.random.Generator(np.random.PCG64(123))
     of = O.realnvp(DIM, HDIMS, NLAYERS, torch.float32, rng)
     ot = O.Funnel(DIM)
@@ -268,13 +270,16 @@ def run_reference(args):
         O.elbo_value_and_grad(of, ot, th, xs)
     dt = time.perf_counter() - t0
     val = n_s * args.steps / dt
-    sample = "one ELBO value+gradient per step over %d of the 2^20 base draws (torch CPU autograd oracle, %d threads)" % (n_s, cores)
+    sample = "one ELBO value+gradient per step over 2^14 = %d of the 2^20 base draws (torch CPU autograd oracle, %d threads)" % (n_s, cores)
     print(json.dumps({
         "impl": "reference", "metric": "ELBO+grad samples/sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": n_s, "note": "CPU restatement oracle, not the Julia reference (Julia unavailable)"},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "batch_per_step": n_s,
+                   "note": "CPU restatement oracle, not the Julia reference; samples/s is per-sample work, so the 2^14-draw step "
+                           "is a bounded sample of the 2^20-draw workload"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
+                         "julia_threads": None, "julia_threads_reason": "Julia is not installed in this image or on the GPU box"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -297,9 +302,83 @@ def cpu_baseline():
         O.elbo_value_and_grad(of, ot, th, xs)
         reps += 1
     dt = time.perf_counter() - t0
-    return {"value": n_s * reps / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+    return {"value": n_s * reps / dt, "unit": "samples/s", "cores": cores, "kind": "port", "julia_threads": None,
+            "julia_threads_reason": "Julia is not installed in this image or on the GPU box",
             "sample": "%d x ELBO value+gradient over %d of the 2^20 base draws (torch CPU autograd oracle; "
                       "CPU restatement, not the Julia reference)" % (reps, n_s)}
+
+
+def collect_profile(K, lib, h):
+    kbuf = C.create_string_buffer(4096)
+    K.check(lib.nf_profile_keys(h, kbuf, 4096))
+    prof = {}
+    for key in [k for k in kbuf.value.decode().split(",") if k]:
+        cnt, ms = C.c_int64(), C.c_double()
+        K.check(lib.nf_profile_collect(h, key.encode(), C.byref(cnt), C.byref(ms)))
+        prof[key] = {"launches": cnt.value, "total_ms": ms.value}
+    return prof
+
+
+def measured_traffic(kernel_key, n_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this build (profiles/r2_traffic.json: bytes per sample at the captured N, scaled to this N); None when the
+    capture does not cover the kernel -- never a guess."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        e = d[kernel_key]
+        return {"bytes_per_launch": e["dram_bytes_per_sample"] * n_local, "source": e["source"]}
+    except Exception:
+        return None
+
+
+def side_c4(nf, K, lib, torch, steps=5):
+    """BASELINE config 4 (NSF d=16, K=10, B=5, [32,32], 8 couplings, Cross x 8, N = 2^20) measured in the same run so that the
+    driver's record carries it: resident inputs, CUDA-event device time, dominant-kernel roofline."""
+    nf.seed(123)
+    n, d = 1 << 20, 16
+    flow = nf.nsf(nf.MvNormal(np.zeros(d)), [32, 32], 10, 5.0, 4, np.float32)
+    tgt = nf.Cross(2.0, 0.15, d)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    theta_dev = torch.from_numpy(flow.theta).to(dev)
+    z0 = torch.randn((n, d), device=dev, dtype=torch.float32)
+    grad = torch.empty(flow.num_params, device=dev, dtype=torch.float32)
+    val = C.c_double()
+    torch.cuda.synchronize()
+    h, th = flow.handle(), tgt.handle()
+
+    def step():
+        K.check(lib.nf_elbo_value_and_grad_dev(h, th, theta_dev.data_ptr(), n, z0.data_ptr(), 0, -1.0, C.byref(val), grad.data_ptr()))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(steps):
+        step()
+        dev_ms += lib.nf_last_device_ms(h)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    K.check(lib.nf_profile_enable(h, 1))
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    K.check(lib.nf_profile_enable(h, 0))
+    prof = collect_profile(K, lib, h)
+    _, _, hbm, src = peaks()
+    roof = None
+    if prof.get("rqs_bwd", {}).get("launches"):
+        c, P3 = d // 2, 3 * 10 - 1
+        bytes_per_launch = n * c * (2 * P3 * 4 + 12) + n * 4
+        avg_ms = prof["rqs_bwd"]["total_ms"] / prof["rqs_bwd"]["launches"]
+        ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "rqs_bwd_kernel<float,10>", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "avg_launch_ms": avg_ms, "peak_source": src + " copy bandwidth", "traffic": None,
+                "note": "bytes = the kernel's own unfused traffic (logits in, gradients out); algorithmic bytes of the step are 64 B/sample"}
+    return {"workload": "nsf_d16_K10_B5_mlp32x32_8xNeuralSplineCoupling_cross8_reverseKL_elbo+grad", "batch": n, "value": n * steps / dt,
+            "unit": "samples/s", "ms_per_step": 1e3 * dt / steps, "device_ms_per_step": dev_ms / steps, "steps": steps, "loss": val.value,
+            "roofline": roof, "kernel_classes": prof}
 
 
 def main():
@@ -310,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="base draws per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the side blocks (C4, strong scaling)")
     ap.add_argument("--config", default="c3", help="c3 (headline) | c1 | c2 | c2p | c3b | c3x1 | c4 | c4b | c4ll | c5 | c5f64")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -324,15 +404,26 @@ def main():
     nf = nfload.load()
     K = nf._capi
     lib = K.lib()
+    lib.nf_last_device_ms.restype = C.c_double
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     K.check(lib.nf_init(local))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    # torch.distributed carries only the launcher's plumbing (the 128-byte NCCL id, barriers, max-over-ranks of the timings);
+    # the gradient all-reduce of the data plane is the ncclAllReduce inside libnfcuda (nf_elbo_value_and_grad_multi*)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        uid = torch.zeros(K.NF_UNIQUE_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(nf.dp.Comm.unique_id()), dtype=torch.uint8).clone()
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        comm = nf.dp.Comm.init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()), local)
+    else:
+        comm = nf.dp.Comm.init_all([local])
 
     n_local = args.batch
     flow = make_theta(nf)
@@ -343,21 +434,21 @@ def main():
     theta_dev = torch.from_numpy(flow.theta).to(dev)
     g = torch.Generator(device=dev); g.manual_seed(2024 + rank)
     z0_dev = torch.randn((n_local, DIM), device=dev, dtype=torch.float32, generator=g)   # resident synthetic base draws
-    sums = torch.zeros(P + 1, device=dev, dtype=torch.float32)
     grad_dev = torch.empty(P, device=dev, dtype=torch.float32)
     val = C.c_double()
     n_total = n_local * world
     torch.cuda.synchronize()          # inputs were produced on torch's stream; the library runs on its own
+    vp = C.c_void_p
+    flows_a, tgts_a = (vp * 1)(h), (vp * 1)(th)
 
-    def step_resident():
-        if world == 1:
-            K.check(lib.nf_elbo_value_and_grad_dev(h, th, theta_dev.data_ptr(), n_local, z0_dev.data_ptr(), 0, -1.0,
-                                                   C.byref(val), grad_dev.data_ptr()))
+    def make_resident(n_tot, z_dev):
+        th_a, z_a, g_a = (vp * 1)(theta_dev.data_ptr()), (vp * 1)(z_dev.data_ptr()), (vp * 1)(grad_dev.data_ptr())
+
+        def step():
+            K.check(lib.nf_elbo_value_and_grad_multi_dev(comm._h, flows_a, tgts_a, th_a, n_tot, z_a, 0, -1.0, C.byref(val), g_a))
             return val.value
-        K.check(lib.nf_elbo_sums_dev(h, th, theta_dev.data_ptr(), n_local, z0_dev.data_ptr(), 0, sums.data_ptr()))
-        dist.all_reduce(sums)                       # the one collective of the path: P+1 floats
-        sums.mul_(-1.0 / n_total)
-        return float(sums[P].item())                # loss; sums[:P] is the gradient handed to the optimiser
+        return step
+    step_resident = make_resident(n_total, z0_dev)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -365,109 +456,120 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(step, steps):
+        sync_all()
+        t0 = time.perf_counter()
+        dms = 0.0
+        for _ in range(steps):
+            step()
+            dms += lib.nf_last_device_ms(h)      # CUDA events on the library stream around this step's kernels (no host time)
+        sync_all()
+        t1 = time.perf_counter()
+        tm = torch.tensor([t1 - t0, dms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm[0].item()), float(tm[1].item()), t0, t1
+
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()          # started before the warm-up so that nvidia-smi's own start-up is outside the timed region
+        sampler.start()          # started before the warm-up so that its own start-up is outside the timed region
     for _ in range(args.warmup):
         loss = step_resident()
     lib.nf_launch_count(1)
-    sync_all()
-    lib.nf_last_device_ms.restype = C.c_double
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        loss = step_resident()
-        dev_ms += lib.nf_last_device_ms(h)      # CUDA events on the library stream around this step's kernels (no host time)
-    sync_all()
-    t1 = time.perf_counter()
-    dt = t1 - t0
+    dt, dev_ms, t0, t1 = timed(step_resident, args.steps)
+    loss = val.value
     launches = lib.nf_launch_count(0)
-    # second pass over the same K steps with a CUDA-event pair around every GEMM launch (per-kernel-class device time
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    value = n_total * args.steps / dt
+    # second pass over the same K steps with a CUDA-event pair around every profiled launch (per-kernel-class device time
     # for the roofline); kept out of the headline region because the extra event records perturb launch overlap
     K.check(lib.nf_profile_enable(h, 1))
-    sync_all()
-    t0p = time.perf_counter()
-    for _ in range(args.steps):
-        step_resident()
-    sync_all()
-    dt_prof = time.perf_counter() - t0p
+    dt_prof, _, _, _ = timed(step_resident, args.steps)
     K.check(lib.nf_profile_enable(h, 0))
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-    tmax = torch.tensor([dt, dev_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dt, dev_ms = float(tmax[0].item()), float(tmax[1].item())
-    value = n_total * args.steps / dt
-
-    # ---- per-kernel-class device time (CUDA events on the library stream, recorded in the timed region) ----
-    kbuf = C.create_string_buffer(4096)
-    K.check(lib.nf_profile_keys(h, kbuf, 4096))
-    prof = {}
-    for key in [k for k in kbuf.value.decode().split(",") if k]:
-        cnt, ms = C.c_int64(), C.c_double()
-        K.check(lib.nf_profile_collect(h, key.encode(), C.byref(cnt), C.byref(ms)))
-        prof[key] = {"launches": cnt.value, "total_ms": ms.value}
+    prof = collect_profile(K, lib, h)
     sustained, burst, hbm, peak_src = peaks()
-    dom = "tc_gemm_n256_k256"
+
+    # ---- roofline of the dominant kernel class (largest share of the profiled step) ----
     roofline = None
-    if dom in prof and prof[dom]["launches"]:
+    timed_classes = {k: v for k, v in prof.items() if v["launches"]}
+    if timed_classes:
+        dom = max(timed_classes, key=lambda k: timed_classes[k]["total_ms"])
         avg_ms = prof[dom]["total_ms"] / prof[dom]["launches"]
-        flops = 2.0 * n_local * 256 * 256
-        ach = flops / (avg_ms * 1e-3) / 1e12
-        # the same launches seen from the memory side: the fp16 hi/lo planes make this kernel move 2 x 2 B per operand element in
-        # and out, so its HBM floor (2.15 GB / 6.46 TB/s = 0.33 ms) is ABOVE its tensor floor (3 x 137 GFLOP / 1442 TF/s = 0.29 ms)
-        plane_bytes = n_local * 256 * 2 * 2 * 2.0           # A planes in + output planes out (sign bits / weights are < 1 %)
-        hbm_ach = plane_bytes / (avg_ms * 1e-3) / 1e9
-        roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<256> (256x256 Dense fwd/dgrad, fp16x3 split = 3 MMAs per useful MAC)",
-                    "achieved": ach, "peak": sustained, "unit": "TFLOP/s", "frac": ach / sustained,
-                    "frac_issued_mma": 3 * ach / sustained, "avg_launch_ms": avg_ms, "launches_per_step": prof[dom]["launches"] / args.steps,
-                    "share_of_step": prof[dom]["total_ms"] / (1e3 * dt_prof), "profiled_ms_per_step": 1e3 * dt_prof / args.steps,
-                    "peak_source": peak_src + " bf16 dense, sustained",
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at N = 2^20 (profiles/r1_tc_gemm_full.txt, K=256 launch)
-                    "traffic": 2.150e9 * n_local / (1 << 20),
-                    "hbm_view": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm, "unit": "GB/s", "frac": hbm_ach / hbm,
-                                 "algorithmic_bytes_per_launch": plane_bytes,
-                                 "note": "split-plane operands: in + out planes per launch; this is the binding roof of the kernel as built"}}
-    step_roof = {"achieved_tflops": value / world * FLOP_PER_SAMPLE / 1e12, "frac_of_bf16_sustained": value / world * FLOP_PER_SAMPLE / 1e12 / sustained,
+        if dom == "fused_affine_fwd":
+            # one launch = both conditioner networks of one coupling, forward: 2 x 81 920 MACs per sample
+            flops = 2.0 * n_local * 2 * 81920
+            kname = "fused_affine_fwd_kernel (both conditioners of a coupling, 3 Dense layers each, + coupling arithmetic; fp16x3 split)"
+        elif dom.startswith("tc_gemm_n256_k256"):
+            flops = 2.0 * n_local * 256 * 256
+            kname = "tc_gemm_kernel<256> (256x256 Dense dgrad, fp16x3 split = 3 MMAs per useful MAC)"
+        elif dom.startswith("tc_wgrad_m256_n256"):
+            flops = 2.0 * n_local * 256 * 256
+            kname = "tc_wgrad_kernel<256> (256x256 weight gradient, contraction over samples)"
+        else:
+            flops, kname = None, dom
+        if flops is not None:
+            ach = flops / (avg_ms * 1e-3) / 1e12
+            tr = measured_traffic(dom, n_local)
+            roofline = {"bound": "tensor", "kernel": kname, "class": dom, "achieved": ach, "peak": sustained, "unit": "TFLOP/s",
+                        "frac": ach / sustained, "frac_issued_mma": 3 * ach / sustained, "avg_launch_ms": avg_ms,
+                        "launches_per_step": prof[dom]["launches"] / args.steps,
+                        "share_of_step": prof[dom]["total_ms"] / (1e3 * dt_prof), "profiled_ms_per_step": 1e3 * dt_prof / args.steps,
+                        "peak_source": peak_src + " bf16 dense, sustained",
+                        "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None}
+    step_roof = {"achieved_tflops": value / world * FLOP_PER_SAMPLE / 1e12,
+                 "frac_of_bf16_sustained": value / world * FLOP_PER_SAMPLE / 1e12 / sustained,
+                 "frac_issued_mma": 3 * value / world * FLOP_PER_SAMPLE / 1e12 / sustained,
                  "achieved_hbm_algorithmic_gbs": value / world * 4 * DIM / 1e9}
 
-    # ---- e2e: host-buffer C-ABI call (what the Julia ccall does), pinned host memory ----
+    # ---- e2e: the host-buffer C-ABI call a Julia `ccall` makes (theta + this rank's Z0 rows host->device from pinned memory,
+    #      all-reduced gradient + value device->host), and the training form (z0 = NULL: device Philox draws) ----
     z0_host_t = torch.empty((n_local, DIM), dtype=torch.float32).pin_memory()
     z0_host_t.copy_(z0_dev.cpu())
     z0_host = z0_host_t.numpy()
     theta_host = flow.theta
-    grad_host_t = torch.empty(P, dtype=torch.float32).pin_memory()
-    grad_host = grad_host_t.numpy()
-    sums_host_t = torch.empty(P + 1, dtype=torch.float32).pin_memory()
-    z0_stage = torch.empty((n_local, DIM), device=dev, dtype=torch.float32)
+    grad_host = torch.empty(P, dtype=torch.float32).pin_memory().numpy()
 
     def step_e2e():
-        if world == 1:
-            K.check(lib.nf_elbo_value_and_grad(h, th, K.ptr(theta_host), n_local, K.ptr(z0_host), 0, -1.0, C.byref(val), K.ptr(grad_host)))
-            return val.value
-        theta_dev.copy_(torch.from_numpy(theta_host), non_blocking=True)
-        z0_stage.copy_(z0_host_t, non_blocking=True)
-        torch.cuda.synchronize()
-        K.check(lib.nf_elbo_sums_dev(h, th, theta_dev.data_ptr(), n_local, z0_stage.data_ptr(), 0, sums.data_ptr()))
-        dist.all_reduce(sums)
-        sums.mul_(-1.0 / n_total)
-        sums_host_t.copy_(sums, non_blocking=False)
-        return float(sums_host_t[P])
+        K.check(lib.nf_elbo_value_and_grad_multi(comm._h, flows_a, tgts_a, K.ptr(theta_host), n_total, K.ptr(z0_host), 0, -1.0,
+                                                 C.byref(val), K.ptr(grad_host)))
+
+    it_seed = [1000]
+
+    def step_e2e_train():
+        it_seed[0] += 1
+        K.check(lib.nf_elbo_value_and_grad_multi(comm._h, flows_a, tgts_a, K.ptr(theta_host), n_total, None, it_seed[0], -1.0,
+                                                 C.byref(val), K.ptr(grad_host)))
 
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    sync_all()
-    dt2 = time.perf_counter() - t0
-    t2 = torch.tensor([dt2], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_val = n_total * e2e_steps / float(t2.item())
-    e2e = {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": int(world * (n_local * DIM * 4 + P * 4)),
-           "d2h_bytes_per_step": int(world * (P * 4 + 8)), "steps": e2e_steps}
+    dt2, _, _, _ = timed(step_e2e, e2e_steps)
+    e2e = {"value": n_total * e2e_steps / dt2, "unit": "samples/s", "h2d_bytes_per_step": int(world * (n_local * DIM * 4 + P * 4)),
+           "d2h_bytes_per_step": int(P * 4 + 8), "steps": e2e_steps,
+           "call": "nf_elbo_value_and_grad_multi(theta_host, z0_host) -- host-supplied Z0, the parity form"}
+    step_e2e_train()
+    dt3, _, _, _ = timed(step_e2e_train, e2e_steps)
+    e2e_train = {"value": n_total * e2e_steps / dt3, "unit": "samples/s", "h2d_bytes_per_step": int(world * P * 4),
+                 "d2h_bytes_per_step": int(P * 4 + 8), "steps": e2e_steps,
+                 "call": "nf_elbo_value_and_grad_multi(theta_host, z0 = NULL, seed) -- device Philox draws, the call "
+                         "train_flow(elbo_batch, flow, logp, n) makes"}
+
+    side = {}
+    if not args.no_side:
+        if world > 1 and BATCH_PER_GPU % world == 0:
+            # strong scaling: ONE global batch of 2^20 split over the ranks (the all-reduce and launch latency now weigh
+            # against 1/N of the compute)
+            n_strong = BATCH_PER_GPU
+            step_strong = make_resident(n_strong, z0_dev[: n_strong // world])
+            for _ in range(3):
+                step_strong()
+            dts, dms, _, _ = timed(step_strong, args.steps)
+            side["strong_scaling"] = {"global_batch": n_strong, "n_gpus": world, "value": n_strong * args.steps / dts, "unit": "samples/s",
+                                      "ms_per_step": 1e3 * dts / args.steps, "device_ms_per_step": dms / args.steps, "steps": args.steps}
+        if world == 1:
+            try:
+                side["c4"] = side_c4(nf, K, lib, torch)
+            except Exception as e:   # noqa: a side block must not take the headline line down
+                side["c4"] = {"error": str(e)}
 
     if rank == 0:
         out = {
@@ -475,15 +577,17 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "device_ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": n_local, "global_batch": n_total, "params": int(P),
-                       "parallelism": "dp%d (samples sharded, theta replicated, one all-reduce of P+1 floats)" % world,
+                       "parallelism": "dp%d (samples sharded, theta replicated, one ncclAllReduce of P+1 doubles inside libnfcuda)" % world,
+                       "entry_point": "nf_elbo_value_and_grad_multi_dev (value) / nf_elbo_value_and_grad_multi (e2e)",
                        "mma_mode": "tcgen05 kind::f16, fp16 hi/lo split x3, fp32 accumulate (parity mode)",
                        "l2_policy": "inputs larger than L2: Z0 268 MB and ~40 GB of stashed activations stream through HBM every step"},
-            "loss": loss, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "step_roofline": step_roof, "kernel_classes": prof,
+            "loss": loss, "e2e": e2e, "e2e_train": e2e_train, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "step_roofline": step_roof, "kernel_classes": prof, "side": side,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
+    comm.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -210,6 +210,43 @@ NF_API int nf_rqs_bin_search(int dtype, const void* knots_host, const void* v_ho
 NF_API int nf_tc_gemm_test(int64_t n, int K, int N, const float* X, const float* Wt, const float* b, int terms, float* Y);
 /* Number of kernels launched by this thread's library calls since the last reset (bench.py `gpu_launches`). */
 NF_API int64_t nf_launch_count(int reset);
+/* ---- multi-GPU data parallelism (the call that replaces reference src/optimize.jl:86 on G devices) ----------
+ * Samples shard across devices in contiguous blocks (rank r owns rows [r*N/R, (r+1)*N/R), the remainder spread over the
+ * first ranks), theta is replicated, and the only exchange is ONE ncclAllReduce(sum) of the P+1 double accumulators
+ * (parameter-gradient sums + objective sum) on each device's compute stream, before the 1/N_total scaling.  NCCL is
+ * resolved at run time (libnccl.so.2); nothing else in the library needs it.
+ *   nf_comm_init_all : ONE process drives n_dev GPUs (the Julia host): ncclCommInitAll over dev_ids (NULL: 0..n_dev-1)
+ *   nf_comm_unique_id / nf_comm_init_rank : one process per GPU (torchrun, MPI): rank 0 makes the id, the launcher hands
+ *                      its NF_UNIQUE_ID_BYTES bytes to every rank, each rank joins with its own device                    */
+typedef struct nf_comm_s* nf_comm_t;
+#define NF_UNIQUE_ID_BYTES 128
+NF_API int nf_comm_init_all(nf_comm_t* out, int n_dev, const int* dev_ids);
+NF_API int nf_comm_unique_id(void* id_out);
+NF_API int nf_comm_init_rank(nf_comm_t* out, int n_ranks, int rank, const void* id, int device);
+NF_API int nf_comm_size(nf_comm_t comm);          /* ranks in the job                       */
+NF_API int nf_comm_local_size(nf_comm_t comm);    /* devices driven by this process         */
+NF_API int nf_comm_local_device(nf_comm_t comm, int i);
+NF_API int nf_comm_local_rank(nf_comm_t comm, int i);
+NF_API void nf_comm_destroy(nf_comm_t comm);
+/* flows[i] / targets[i]: one replica per LOCAL device i, created while that device was current (nf_init(device)).
+ * theta_host: P values.  N_total: samples over the whole job.  z0_host: the rows owned by THIS process (all of them with
+ * nf_comm_init_all; the rank's own shard with one process per GPU), or NULL for device Philox draws -- rank r then draws
+ * rows [begin_r, end_r) of the one global draw matrix of (seed), so the result equals the single-device result up to
+ * summation order.  value_out / grad_host_out: the job-wide ELBO and gradient (identical on every process).            */
+NF_API int nf_elbo_value_and_grad_multi(nf_comm_t comm, const nf_flow_t* flows, const nf_target_t* targets, const void* theta_host,
+                                        int64_t N_total, const void* z0_host, uint64_t seed, double scale, double* value_out,
+                                        void* grad_host_out);
+/* forward-KL twin (reference src/objectives/loglikelihood.jl:26-33): xs_host = this process's rows of the data batch */
+NF_API int nf_loglik_value_and_grad_multi(nf_comm_t comm, const nf_flow_t* flows, const void* theta_host, int64_t N_total,
+                                          const void* xs_host, double scale, double* value_out, void* grad_host_out);
+/* Same with everything resident: theta_dev[i] (P values), in_dev[i] (device i's shard, or NULL / null entries for Philox
+ * draws), grad_dev_out[i] (P values, may be NULL) per local device; nothing crosses PCIe except the objective value.   */
+NF_API int nf_elbo_value_and_grad_multi_dev(nf_comm_t comm, const nf_flow_t* flows, const nf_target_t* targets,
+                                            const void* const* theta_dev, int64_t N_total, const void* const* z0_dev, uint64_t seed,
+                                            double scale, double* value_out, void* const* grad_dev_out);
+/* rows [begin, end) of a batch of N_total owned by `rank` of `n_ranks` (the partition the calls above use) */
+NF_API void nf_shard_range(int64_t N_total, int n_ranks, int rank, int64_t* begin, int64_t* end);
+
 /* Process-wide execution options (diagnostics / A-B measurements; results are parity grade either way).
  *   "fused_coupling"  1 (default): AffineCoupling layers that qualify run the fused conditioner kernels; 0: layer by layer
  * Returns NF_ERR_INVALID for an unknown name. */

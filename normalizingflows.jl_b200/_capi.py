@@ -15,6 +15,7 @@ NF_MOMENTUM_AFFINE, NF_LEAPFROG = 7, 8
 NF_TARGET_BANANA, NF_TARGET_FUNNEL, NF_TARGET_WARPED_GAUSS, NF_TARGET_CROSS, NF_TARGET_DIAG_NORMAL = 1, 2, 3, 4, 5
 NF_TARGET_LOGREG = 6
 NF_MMA_SIMT, NF_MMA_F16X3, NF_MMA_F16X1 = 0, 1, 2
+NF_UNIQUE_ID_BYTES = 128
 
 
 class LayerDesc(C.Structure):
@@ -65,6 +66,19 @@ SIGNATURES = {
     "nf_tc_gemm_test": (_i, [_i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "nf_launch_count": (_i64, [_i]),
     "nf_set_option": (_i, [C.c_char_p, _i]),
+    "nf_comm_init_all": (_i, [C.POINTER(_vp), _i, C.POINTER(_i)]),
+    "nf_comm_unique_id": (_i, [_vp]),
+    "nf_comm_init_rank": (_i, [C.POINTER(_vp), _i, _i, _vp, _i]),
+    "nf_comm_size": (_i, [_vp]),
+    "nf_comm_local_size": (_i, [_vp]),
+    "nf_comm_local_device": (_i, [_vp, _i]),
+    "nf_comm_local_rank": (_i, [_vp, _i]),
+    "nf_comm_destroy": (None, [_vp]),
+    "nf_elbo_value_and_grad_multi": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _vp, _u64, _d, C.POINTER(_d), _vp]),
+    "nf_loglik_value_and_grad_multi": (_i, [_vp, C.POINTER(_vp), _vp, _i64, _vp, _d, C.POINTER(_d), _vp]),
+    "nf_elbo_value_and_grad_multi_dev": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i64, C.POINTER(_vp), _u64, _d,
+                                              C.POINTER(_d), C.POINTER(_vp)]),
+    "nf_shard_range": (None, [_i64, _i, _i, C.POINTER(_i64), C.POINTER(_i64)]),
     "nf_last_device_ms": (_d, [_vp]),
     "nf_profile_enable": (_i, [_vp, _i]),
     "nf_profile_keys": (_i, [_vp, C.c_char_p, _i]),

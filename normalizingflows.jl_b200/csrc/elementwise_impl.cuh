@@ -174,6 +174,7 @@ template <typename T> struct EwArgs {
   int64_t N;
   int L, d, flags;
   uint64_t seed;
+  int64_t row0;         // global row of sample 0 (Philox draws of a data-parallel shard)
 };
 
 template <typename T, int DP, int S, bool LR>
@@ -215,7 +216,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
       } else {
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
-          if (k < d) z[s][k] = (a.flags & EW_GEN_Z0) ? philox_randn<T>(a.seed, (uint64_t)jj * d + k) : a.z0[jj * d + k];
+          if (k < d) z[s][k] = (a.flags & EW_GEN_Z0) ? philox_randn<T>(a.seed, (uint64_t)(a.row0 + jj) * d + k) : a.z0[jj * d + k];
           else z[s][k] = 0;
         }
       }
@@ -982,6 +983,7 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
   a.gpart = gpart; a.epart = epart; a.N = N; a.L = L; a.d = d;
   a.flags = flags | (z0_dev ? 0 : EW_GEN_Z0);
   a.seed = seed;
+  a.row0 = f.draw_row_offset;
   f.prof.begin("ew_flow", f.stream);
   kern<<<grid, threads, smem, f.stream>>>(a);
   f.prof.end(f.stream);

@@ -141,6 +141,9 @@ struct Flow {
 
   // layered path: chunk size chosen by general_plan_workspace, opaque per-flow state
   int64_t chunk_N = 0;
+  // device Philox draws: row of the global batch this flow's first draw corresponds to (data-parallel shards draw the
+  // rows [offset, offset + N) of ONE global draw matrix, so G devices reproduce the single-device batch)
+  int64_t draw_row_offset = 0;
   void* gen_state = nullptr;
   void* tc_state = nullptr;            // tcgen05 path: prepared weight planes, tensor-map cache
 

@@ -500,7 +500,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const FusedFw
         // ---- first Dense epilogue: chunk j of h1 -> TMEM operand planes + stash ----
         for (int j = 0; j < nch; ++j, ++sl) {
           const uint32_t acc = sl & 1;
-          if (lane == 0) mbar_wait_relaxed(tfull(acc), (sl >> 1) & 1);
+          if (lane == 0 || (p.dbg_flags & 4)) mbar_wait_relaxed(tfull(acc), (sl >> 1) & 1);
           __syncwarp();
           tc_fence_after();
           uint32_t v[16];
@@ -540,7 +540,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const FusedFw
             const int j = (e >> 2) & 3, k = e & 3;
             const uint32_t acc = sl & 1;
             if (t == 0) NF_FDBG(1, 4 * sl);
-            if (lane == 0) mbar_wait_relaxed(tfull(acc), (sl >> 1) & 1);
+            if (lane == 0 || (p.dbg_flags & 4)) mbar_wait_relaxed(tfull(acc), (sl >> 1) & 1);
             __syncwarp();
             if (t == 0) NF_FDBG(1, 4 * sl + 1);
             tc_fence_after();
@@ -588,7 +588,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const FusedFw
             }
           } else {
             const uint32_t acc = sl3 & 1;
-            if (lane == 0) mbar_wait_relaxed(tfull3(acc), (sl3 >> 1) & 1);
+            if (lane == 0 || (p.dbg_flags & 4)) mbar_wait_relaxed(tfull3(acc), (sl3 >> 1) & 1);
             __syncwarp();
             tc_fence_after();
             uint32_t v[8];
@@ -628,7 +628,8 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const FusedFw
       }
       epi_bar_sync(1, 512);
       // the next tile's conditioner input first: its first-Dense MMAs then run while this tile's coupling arithmetic is done
-      if (tile + gridDim.x < num_tiles) scatter_x2(tile + gridDim.x, tcount + 1);
+      const bool early_scatter = !(p.dbg_flags & 2);
+      if (early_scatter && tile + gridDim.x < num_tiles) scatter_x2(tile + gridDim.x, tcount + 1);
       // ---- coupling arithmetic: coalesced pass over the X tile ----
       for (int idx = t; idx < 128 * dh; idx += 512) {
         const int r = idx / dh, jp = idx - r * dh;
@@ -662,6 +663,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const FusedFw
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(x_empty(xs));
+      if (!early_scatter && tile + gridDim.x < num_tiles) scatter_x2(tile + gridDim.x, tcount + 1);
     }
     if (p.y_meta) {
       run_max = warp_max(run_max);

@@ -455,7 +455,7 @@ int run_typed(Flow& f, const GeneralJob& job) {
     const T* in = job.in_dev ? (const T*)job.in_dev + c0 * d : nullptr;
     NF_TRY(alloc_chunk(f, c, n, stash, in));
     if (!in) {
-      base_sample_kernel<T><<<(unsigned)ceil_div(n * d, 256), 256, 0, f.stream>>>((T*)c.X[0], base, d, n, job.seed, c0, job.seed_iter_dev);
+      base_sample_kernel<T><<<(unsigned)ceil_div(n * d, 256), 256, 0, f.stream>>>((T*)c.X[0], base, d, n, job.seed, c0 + f.draw_row_offset, job.seed_iter_dev);
       NF_LAUNCH_CHECK();
     }
     const int last = stash ? L : 1 + ((L - 1) & 1);

@@ -5,6 +5,8 @@
 #include <chrono>
 #include <cstring>
 #include <mutex>
+#include <dlfcn.h>
+#include <nccl.h>
 
 namespace nf {
 
@@ -442,6 +444,7 @@ static int transform_host(Flow& f, int op, const Target* tgt, const void* theta_
 using namespace nf;
 
 #define NF_FLOW(h) (*reinterpret_cast<nf::Flow*>(h))
+#define NF_FLOW_REF(h) (*reinterpret_cast<nf::Flow*>(h))
 #define NF_CHECK_HANDLE(h)                                  \
   do {                                                      \
     if (!(h)) { nf::set_error("null handle"); return NF_ERR_INVALID; } \
@@ -943,6 +946,296 @@ int nf_profile_collect(nf_flow_t flow, const char* key, int64_t* launches, doubl
   NF_CUDA(cudaStreamSynchronize(f.stream));
   f.prof.collect(key, launches, total_ms);
   return NF_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU data parallelism: sample shards, replicated theta, ONE all-reduce of the P+1 accumulators
+// (SURVEY 8e).  NCCL is bound at run time so that nothing else in the library depends on it.
+// ---------------------------------------------------------------------------------------------
+namespace nf {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.lib) return NF_OK;
+  // a process that already carries an NCCL (e.g. the one bundled with PyTorch) is joined to it; else the system library
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { set_error("NCCL is not available: %s", dlerror()); return NF_ERR_UNSUPPORTED; }
+#define NF_NCCL_SYM(field, name)                                                     \
+  do {                                                                               \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                                       \
+    if (!g_nccl.field) { set_error("NCCL symbol %s is missing", name); return NF_ERR_UNSUPPORTED; } \
+  } while (0)
+  NF_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+  NF_NCCL_SYM(CommInitAll, "ncclCommInitAll");
+  NF_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+  NF_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  NF_NCCL_SYM(AllReduce, "ncclAllReduce");
+  NF_NCCL_SYM(GroupStart, "ncclGroupStart");
+  NF_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+  NF_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NF_NCCL_SYM
+  g_nccl.lib = h;
+  return NF_OK;
+}
+#define NF_NCCL(expr)                                                                          \
+  do {                                                                                         \
+    ncclResult_t _r = (expr);                                                                  \
+    if (_r != ncclSuccess) {                                                                   \
+      nf::set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(_r)); \
+      return NF_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+struct Comm {
+  int n_ranks = 1;
+  std::vector<int> devices;        // local devices, in rank order
+  std::vector<int> ranks;          // global rank of each local device
+  std::vector<ncclComm_t> comms;   // one per local device (empty for a single-rank job: nothing to reduce)
+};
+
+static void shard_range(int64_t N, int R, int r, int64_t* b, int64_t* e) {
+  const int64_t q = N / R, rem = N % R;
+  *b = r * q + std::min<int64_t>(r, rem);
+  *e = *b + q + (r < rem ? 1 : 0);
+}
+
+// theta / inputs per local device are already resident (theta_dev[i], in_dev[i] or null); leaves the scaled gradient in
+// each flow's d_out (and in grad_dev_out[i] when given) and the job-wide objective in *value_out.
+static int multi_core(Comm& c, Flow* const* fl, const Target* const* tg, int op, const void* const* theta_dev, int64_t N_total,
+                      const void* const* in_dev, uint64_t seed, double scale, double* value_out, void* const* grad_dev_out) {
+  const int G = (int)c.devices.size();
+  std::vector<int64_t> nloc(G);
+  for (int i = 0; i < G; ++i) {
+    Flow& f = *fl[i];
+    int64_t b, e;
+    shard_range(N_total, c.n_ranks, c.ranks[i], &b, &e);
+    nloc[i] = e - b;
+    NF_REQUIRE(nloc[i] > 0, "N_total = %lld leaves rank %d without samples", (long long)N_total, c.ranks[i]);
+    NF_CUDA(cudaSetDevice(f.device));
+    Job j;
+    j.op = op; j.tgt = tg ? tg[i] : nullptr; j.theta_dev = theta_dev[i]; j.in_dev = in_dev ? in_dev[i] : nullptr; j.N = nloc[i]; j.seed = seed;
+    j.want_grad = true;
+    f.draw_row_offset = j.in_dev ? 0 : b;
+    NF_CUDA(cudaEventRecord(f.ev0, f.stream));
+    const int s = run_job(f, j);            // asynchronous: kernels queue on the device's stream, the host moves on to the next device
+    f.draw_row_offset = 0;
+    NF_TRY(s);
+  }
+  if (!c.comms.empty()) {
+    NF_NCCL(g_nccl.GroupStart());
+    for (int i = 0; i < G; ++i)
+      NF_NCCL(g_nccl.AllReduce(fl[i]->d_gsum, fl[i]->d_gsum, (size_t)(fl[i]->P + 1), ncclDouble, ncclSum, c.comms[i], fl[i]->stream));
+    NF_NCCL(g_nccl.GroupEnd());
+  }
+  const double factor = scale / (double)N_total;
+  for (int i = 0; i < G; ++i) {
+    Flow& f = *fl[i];
+    NF_CUDA(cudaSetDevice(f.device));
+    NF_TRY(scale_outputs(f, factor, grad_dev_out && grad_dev_out[i] ? grad_dev_out[i] : f.d_out, f.P));
+    NF_CUDA(cudaEventRecord(f.ev1, f.stream));
+  }
+  Flow& f0 = *fl[0];
+  NF_CUDA(cudaSetDevice(f0.device));
+  double* vsum = reinterpret_cast<double*>((char*)f0.h_pinned + f0.h_pinned_bytes - 16);
+  NF_CUDA(cudaMemcpyAsync(vsum, f0.d_gsum + f0.P, sizeof(double), cudaMemcpyDeviceToHost, f0.stream));
+  for (int i = 0; i < G; ++i) {
+    NF_CUDA(cudaSetDevice(fl[i]->device));
+    NF_CUDA(cudaStreamSynchronize(fl[i]->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, fl[i]->ev0, fl[i]->ev1);
+    fl[i]->last_ms = ms;
+  }
+  if (value_out) *value_out = *vsum * factor;
+  return NF_OK;
+}
+
+static int multi_host(Comm& c, const nf_flow_t* flows, const nf_target_t* targets, int op, const void* theta_host, int64_t N_total,
+                      const void* in_host, uint64_t seed, double scale, double* value_out, void* grad_host_out) {
+  const int G = (int)c.devices.size();
+  NF_REQUIRE(flows && theta_host && N_total > 0, "null argument / N_total must be positive");
+  std::vector<Flow*> fl(G);
+  std::vector<const Target*> tg(G, nullptr);
+  std::vector<const void*> th(G), in(G, nullptr);
+  int64_t first_row = 0, dummy = 0;
+  shard_range(N_total, c.n_ranks, c.ranks[0], &first_row, &dummy);
+  for (int i = 0; i < G; ++i) {
+    NF_REQUIRE(flows[i], "null flow handle for local device %d", i);
+    Flow& f = NF_FLOW_REF(flows[i]);
+    fl[i] = &f;
+    NF_REQUIRE(f.device == c.devices[i], "flows[%d] lives on device %d, the communicator expects device %d", i, f.device, c.devices[i]);
+    NF_REQUIRE(f.P == fl[0]->P && f.dtype == fl[0]->dtype && f.dim == fl[0]->dim, "flows[%d] is not a replica of flows[0]", i);
+    if (op == OP_ELBO) {
+      NF_REQUIRE(targets && targets[i], "null target handle for local device %d", i);
+      tg[i] = reinterpret_cast<const Target*>(targets[i]);
+      NF_TRY(check_target(f, tg[i]));
+    }
+    int64_t b, e;
+    shard_range(N_total, c.n_ranks, c.ranks[i], &b, &e);
+    const size_t es = f.esize();
+    NF_CUDA(cudaSetDevice(f.device));
+    f.ws_reset();
+    const size_t in_bytes = in_host ? (size_t)(e - b) * f.dim * es : 0;
+    NF_TRY(general_plan_workspace(f, op, e - b, in_bytes));
+    NF_CUDA(cudaMemcpyAsync(f.d_theta, theta_host, f.P * es, cudaMemcpyHostToDevice, f.stream));
+    th[i] = f.d_theta;
+    if (in_host) {
+      void* d = f.ws_alloc(in_bytes);
+      if (!d) return NF_ERR_OOM;
+      NF_CUDA(cudaMemcpyAsync(d, (const char*)in_host + (size_t)(b - first_row) * f.dim * es, in_bytes, cudaMemcpyHostToDevice, f.stream));
+      in[i] = d;
+    }
+  }
+  NF_TRY(multi_core(c, fl.data(), op == OP_ELBO ? tg.data() : nullptr, op, th.data(), N_total, in_host ? in.data() : nullptr, seed, scale,
+                    value_out, nullptr));
+  if (grad_host_out) {
+    Flow& f0 = *fl[0];
+    const size_t es = f0.esize();
+    NF_CUDA(cudaSetDevice(f0.device));
+    NF_CUDA(cudaMemcpyAsync(f0.h_pinned, f0.d_out, f0.P * es, cudaMemcpyDeviceToHost, f0.stream));
+    NF_CUDA(cudaStreamSynchronize(f0.stream));
+    memcpy(grad_host_out, f0.h_pinned, f0.P * es);
+  }
+  return NF_OK;
+}
+}  // namespace nf
+
+extern "C" {
+
+void nf_shard_range(int64_t N_total, int n_ranks, int rank, int64_t* begin, int64_t* end) {
+  int64_t b = 0, e = 0;
+  if (n_ranks > 0 && rank >= 0 && rank < n_ranks) nf::shard_range(N_total, n_ranks, rank, &b, &e);
+  if (begin) *begin = b;
+  if (end) *end = e;
+}
+
+int nf_comm_init_all(nf_comm_t* out, int n_dev, const int* dev_ids) {
+  NF_REQUIRE(out && n_dev >= 1, "nf_comm_init_all: need an output handle and n_dev >= 1");
+  int count = 0;
+  NF_CUDA(cudaGetDeviceCount(&count));
+  std::unique_ptr<nf::Comm> c(new nf::Comm());
+  c->n_ranks = n_dev;
+  for (int i = 0; i < n_dev; ++i) {
+    const int dev = dev_ids ? dev_ids[i] : i;
+    NF_REQUIRE(dev >= 0 && dev < count, "nf_comm_init_all: device %d is not present (%d devices)", dev, count);
+    c->devices.push_back(dev);
+    c->ranks.push_back(i);
+  }
+  if (n_dev > 1) {
+    NF_TRY(nf::nccl_load());
+    c->comms.resize(n_dev);
+    NF_NCCL(nf::g_nccl.CommInitAll(c->comms.data(), n_dev, c->devices.data()));
+  }
+  *out = reinterpret_cast<nf_comm_t>(c.release());
+  return NF_OK;
+}
+
+int nf_comm_unique_id(void* id_out) {
+  NF_REQUIRE(id_out, "null argument");
+  static_assert(sizeof(ncclUniqueId) <= NF_UNIQUE_ID_BYTES, "NF_UNIQUE_ID_BYTES too small");
+  NF_TRY(nf::nccl_load());
+  ncclUniqueId id;
+  NF_NCCL(nf::g_nccl.GetUniqueId(&id));
+  memset(id_out, 0, NF_UNIQUE_ID_BYTES);
+  memcpy(id_out, &id, sizeof(id));
+  return NF_OK;
+}
+
+int nf_comm_init_rank(nf_comm_t* out, int n_ranks, int rank, const void* id, int device) {
+  NF_REQUIRE(out && n_ranks >= 1 && rank >= 0 && rank < n_ranks, "nf_comm_init_rank: bad rank %d of %d", rank, n_ranks);
+  int count = 0;
+  NF_CUDA(cudaGetDeviceCount(&count));
+  NF_REQUIRE(device >= 0 && device < count, "nf_comm_init_rank: device %d is not present (%d devices)", device, count);
+  std::unique_ptr<nf::Comm> c(new nf::Comm());
+  c->n_ranks = n_ranks;
+  c->devices.push_back(device);
+  c->ranks.push_back(rank);
+  if (n_ranks > 1) {
+    NF_REQUIRE(id, "nf_comm_init_rank: null unique id");
+    NF_TRY(nf::nccl_load());
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    NF_CUDA(cudaSetDevice(device));
+    c->comms.resize(1);
+    NF_NCCL(nf::g_nccl.CommInitRank(&c->comms[0], n_ranks, uid, rank));
+  }
+  *out = reinterpret_cast<nf_comm_t>(c.release());
+  return NF_OK;
+}
+
+int nf_comm_size(nf_comm_t comm) { return comm ? reinterpret_cast<nf::Comm*>(comm)->n_ranks : -1; }
+int nf_comm_local_size(nf_comm_t comm) { return comm ? (int)reinterpret_cast<nf::Comm*>(comm)->devices.size() : -1; }
+int nf_comm_local_device(nf_comm_t comm, int i) {
+  if (!comm) return -1;
+  auto* c = reinterpret_cast<nf::Comm*>(comm);
+  return (i >= 0 && i < (int)c->devices.size()) ? c->devices[i] : -1;
+}
+int nf_comm_local_rank(nf_comm_t comm, int i) {
+  if (!comm) return -1;
+  auto* c = reinterpret_cast<nf::Comm*>(comm);
+  return (i >= 0 && i < (int)c->ranks.size()) ? c->ranks[i] : -1;
+}
+
+void nf_comm_destroy(nf_comm_t comm) {
+  if (!comm) return;
+  auto* c = reinterpret_cast<nf::Comm*>(comm);
+  for (size_t i = 0; i < c->comms.size(); ++i) {
+    cudaSetDevice(c->devices[i]);
+    if (nf::g_nccl.CommDestroy) nf::g_nccl.CommDestroy(c->comms[i]);
+  }
+  delete c;
+}
+
+int nf_elbo_value_and_grad_multi(nf_comm_t comm, const nf_flow_t* flows, const nf_target_t* targets, const void* theta_host,
+                                 int64_t N_total, const void* z0_host, uint64_t seed, double scale, double* value_out,
+                                 void* grad_host_out) {
+  NF_REQUIRE(comm, "null communicator");
+  return nf::multi_host(*reinterpret_cast<nf::Comm*>(comm), flows, targets, OP_ELBO, theta_host, N_total, z0_host, seed, scale, value_out,
+                        grad_host_out);
+}
+
+int nf_loglik_value_and_grad_multi(nf_comm_t comm, const nf_flow_t* flows, const void* theta_host, int64_t N_total,
+                                   const void* xs_host, double scale, double* value_out, void* grad_host_out) {
+  NF_REQUIRE(comm, "null communicator");
+  NF_REQUIRE(xs_host, "loglikelihood needs data");
+  return nf::multi_host(*reinterpret_cast<nf::Comm*>(comm), flows, nullptr, OP_LOGLIK, theta_host, N_total, xs_host, 0, scale, value_out,
+                        grad_host_out);
+}
+
+int nf_elbo_value_and_grad_multi_dev(nf_comm_t comm, const nf_flow_t* flows, const nf_target_t* targets, const void* const* theta_dev,
+                                     int64_t N_total, const void* const* z0_dev, uint64_t seed, double scale, double* value_out,
+                                     void* const* grad_dev_out) {
+  NF_REQUIRE(comm && flows && targets && theta_dev && N_total > 0, "null argument / N_total must be positive");
+  nf::Comm& c = *reinterpret_cast<nf::Comm*>(comm);
+  const int G = (int)c.devices.size();
+  std::vector<nf::Flow*> fl(G);
+  std::vector<const nf::Target*> tg(G);
+  for (int i = 0; i < G; ++i) {
+    NF_REQUIRE(flows[i] && targets[i] && theta_dev[i], "null handle / theta for local device %d", i);
+    nf::Flow& f = NF_FLOW_REF(flows[i]);
+    fl[i] = &f;
+    tg[i] = reinterpret_cast<const nf::Target*>(targets[i]);
+    NF_REQUIRE(f.device == c.devices[i], "flows[%d] lives on device %d, the communicator expects device %d", i, f.device, c.devices[i]);
+    NF_TRY(check_target(f, tg[i]));
+    int64_t b, e;
+    nf::shard_range(N_total, c.n_ranks, c.ranks[i], &b, &e);
+    NF_CUDA(cudaSetDevice(f.device));
+    f.ws_reset();
+    NF_TRY(general_plan_workspace(f, OP_ELBO, e - b, 0));
+  }
+  return nf::multi_core(c, fl.data(), tg.data(), OP_ELBO, theta_dev, N_total, z0_dev, seed, scale, value_out, grad_dev_out);
 }
 
 }  // extern "C"

@@ -1119,10 +1119,10 @@ template <int BN>
 int launch_gemm_bn(Flow& f, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmParams& p, int n_tiles_n) {
   using Cfg = GemmCfg<BN>;
   auto kern = tc_gemm_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};            // per device: function attributes belong to the context
+  if (!attr_set[f.device & 63]) {
     NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr_set = true;
+    attr_set[f.device & 63] = true;
   }
   const int64_t tiles = ceil_div(p.M, 128);
   dim3 grid((unsigned)std::min<int64_t>(tiles, std::max(1, kNumSMs / n_tiles_n)), (unsigned)n_tiles_n);
@@ -1181,10 +1181,10 @@ template <int BN>
 int launch_wgrad_bn(Flow& f, const CUtensorMap& mx, const CUtensorMap& mg, const WgradParams& p) {
   using Cfg = WgradCfg<BN>;
   auto kern = tc_wgrad_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};            // per device: function attributes belong to the context
+  if (!attr_set[f.device & 63]) {
     NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr_set = true;
+    attr_set[f.device & 63] = true;
   }
   const int64_t chunks = ceil_div(p.n, Cfg::KS);
   // at least 8 chunks (256 samples) per CTA so the atomic flush is amortised
@@ -1488,10 +1488,10 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
   p.rz[0] = rz_compensation(cbar, 1, 1);
   p.rz[1] = rz_compensation(H, h_ld / 64, 1);
   p.rz[2] = rz_compensation(H, h_ld / 64, 1);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (!attr_set[f.device & 63]) {
     NF_CUDA(cudaFuncSetAttribute(fused_affine_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM));
-    attr_set = true;
+    attr_set[f.device & 63] = true;
   }
   const int64_t tiles = ceil_div(n, 128);
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, kNumSMs);

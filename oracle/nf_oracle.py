@@ -467,6 +467,7 @@ class NeuralSplineCoupling(Layer):
         pX, pY, dYdX = self._spline_params(x2)
         y1, lj, k = rqs_forward(x1, pX, pY, dYdX)
         self.last_bins = k.detach()
+        self.last_knots, self.last_v = pX.detach(), x1.detach()   # searched knots / searched values (bin-parity tests)
         y = x.clone()
         y[:, self.idx1] = y1
         return y, lj.sum(dim=1)
@@ -476,6 +477,7 @@ class NeuralSplineCoupling(Layer):
         pX, pY, dYdX = self._spline_params(y2)
         x1, lj, k = rqs_inverse(y1, pX, pY, dYdX)
         self.last_bins = k.detach()
+        self.last_knots, self.last_v = pY.detach(), y1.detach()
         x = y.clone()
         x[:, self.idx1] = x1
         return x, lj.sum(dim=1)

@@ -77,6 +77,16 @@ def test_cuda_matches_golden(gpu, path):
     terms = nf.batched_elbos(gf, gt, xs)
     assert rel_err(terms, d["terms"]) <= 1e-5
     if "bins" in d.files:
-        got = np.stack(nf.spline_bins(gf, xs))
-        # bins are integers: exact except for inputs sitting within float32 rounding of a knot
-        assert (got != d["bins"]).mean() <= 2e-3
+        got = nf.spline_bins(gf, xs)
+        # bins are integers: exact, except where the searched value sits within float32 rounding of the knot that separates
+        # the two answers.  The fixture's bins come from the float64 oracle; the explanation is checked against the float32
+        # oracle (same theta), whose knots and searched values carry the same rounding the device arithmetic has.
+        from test_gpu_parity import bin_mismatch_ulps
+        of32 = oracle_flow(meta["kind"], meta["dim"], np.float32, **meta["kw"])
+        of32.set_theta(torch.from_numpy(theta32))
+        of32.forward(torch.from_numpy(xs.astype(np.float32)))
+        ulps = bin_mismatch_ulps(of32, got)
+        assert all(u <= 32 for u in ulps), ulps
+        g64 = np.stack(got) != d["bins"]
+        assert g64.mean() <= 5e-4, g64.mean()
+        assert np.abs(np.stack(got).astype(np.int64) - d["bins"])[g64].max(initial=1) == 1

@@ -45,19 +45,33 @@ def _set_mode(nf, gf, mode):
     return gf
 
 
-def _f32_noise_floor(kind, dim, tname, N, kw, of32, ot, xs, v32, g32):
-    """Rounding noise of the reference's own Float32 path: distance of the fp32 oracle from the fp64 oracle
-    at the same (fp32-rounded) theta.  The Float32 tolerance is max(north_star tolerance, 2 x this floor): a
-    GPU result cannot be asked to sit closer to the fp32 CPU result than that result sits to the truth."""
+def _f64_truth(kind, dim, kw, of32, ot, xs):
+    """The float64 oracle at the same (float32-rounded) theta and draws: the value the reference's arithmetic converges to."""
     of64 = oracle_flow(kind, dim, np.float64, **kw)
     of64.set_theta(of32.theta().double())
-    v64, g64 = O.elbo_value_and_grad(of64, ot, of64.theta(), torch.from_numpy(xs).double())
-    return abs(v32 - v64) / max(abs(v64), 1.0), rel_err(g32, g64), v64, g64
+    return O.elbo_value_and_grad(of64, ot, of64.theta(), torch.from_numpy(xs).double())
+
+
+_TABLE = []
+
+
+def _record(row):
+    """Achieved errors per configuration -> gpurun_out/parity_r2.json (copied to profiles/parity_r2.json)."""
+    import json, os
+    _TABLE.append({k: (float(v) if isinstance(v, (float, np.floating)) else v) for k, v in row.items()})
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_r2.json"), "w") as fh:
+        json.dump(_TABLE, fh, indent=1)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
 @pytest.mark.parametrize("kind,dim,tname,N,kw", CASES, ids=[f"{c[0]}-d{c[1]}-{c[2]}-N{c[3]}" for c in CASES])
 def test_elbo_value_and_grad(gpu, kind, dim, tname, N, kw, dtype):
+    """Float32: the CUDA result must sit within the north_star tolerance of the TRUTH (float64 oracle, same theta and draws)
+    -- no widening.  Against the reference's own Float32 CPU arithmetic (float32 oracle) the bound is the tolerance plus that
+    path's own measured distance from the truth (triangle inequality; e.g. the Float32 CPU gradient of NSF d = 16 sits
+    9e-5 from the truth while the CUDA gradient sits 2e-6 from it)."""
     nf = gpu
     of = oracle_flow(kind, dim, dtype, **kw)
     ot = oracle_target(tname, dim)
@@ -65,15 +79,25 @@ def test_elbo_value_and_grad(gpu, kind, dim, tname, N, kw, dtype):
     v_ref, g_ref = O.elbo_value_and_grad(of, ot, of.theta(), torch.from_numpy(xs))
     tv, tg = TOL[dtype]
     if dtype == np.float32:
-        fv, fg, _, _ = _f32_noise_floor(kind, dim, tname, N, kw, of, ot, xs, v_ref, g_ref)
-        tv, tg = max(tv, 2 * fv), max(tg, 2 * fg)
+        v64, g64 = _f64_truth(kind, dim, kw, of, ot, xs)
+        fv, fg = abs(v_ref - v64) / max(abs(v64), 1.0), rel_err(g_ref, g64)
     gt = gpu_target(nf, ot)
     for mode in _modes(kind, dtype):
         gf = _set_mode(nf, gpu_flow(nf, of, dtype), mode)
         v, g = nf.api._elbo_impl(gf, gt, xs, want_grad=True)
         assert np.isfinite(v), mode
-        assert abs(v - v_ref) <= tv * max(abs(v_ref), 1.0), (mode, v, v_ref)
-        assert rel_err(g, g_ref) <= tg, (mode, rel_err(g, g_ref))
+        if dtype == np.float32:
+            ev64, eg64 = abs(v - v64) / max(abs(v64), 1.0), rel_err(g, g64)
+            _record(dict(config=f"{kind}-d{dim}-{tname}-N{N}", mode=mode, elbo_rel_gpu_vs_f64=ev64, grad_rel_gpu_vs_f64=eg64,
+                         elbo_rel_f32oracle_vs_f64=fv, grad_rel_f32oracle_vs_f64=fg,
+                         elbo_rel_gpu_vs_f32oracle=abs(v - v_ref) / max(abs(v_ref), 1.0), grad_rel_gpu_vs_f32oracle=rel_err(g, g_ref)))
+            assert ev64 <= tv, (mode, "elbo vs float64 oracle", ev64)
+            assert eg64 <= tg, (mode, "gradient vs float64 oracle", eg64)
+            assert abs(v - v_ref) <= (tv + fv) * max(abs(v_ref), 1.0), (mode, v, v_ref)
+            assert rel_err(g, g_ref) <= tg + fg, (mode, rel_err(g, g_ref))
+        else:
+            assert abs(v - v_ref) <= tv * max(abs(v_ref), 1.0), (mode, v, v_ref)
+            assert rel_err(g, g_ref) <= tg, (mode, rel_err(g, g_ref))
     # per-sample terms (elbo.jl:65-70) and value-only path agree with the value+grad path
     terms = nf.batched_elbos(gf, gt, xs)
     ref_terms = O.batched_elbos(of, ot, torch.from_numpy(xs)).detach().numpy()
@@ -145,19 +169,39 @@ def test_spline_bins_bit_exact(gpu):
         assert np.array_equal(got, ref.astype(np.int32))
 
 
+def bin_mismatch_ulps(of, got):
+    """Distance, in float spacings at the knot, of every searched value whose bin differs from the oracle's to the oracle
+    knot that separates the two bins (inf when the bins differ by more than one)."""
+    out = []
+    for l, g in zip(reversed(of.layers), got):
+        ref = l.last_bins.numpy()
+        kn, v = l.last_knots.numpy(), l.last_v.numpy()
+        for (n, c) in np.argwhere(g != ref):
+            lo = min(int(g[n, c]), int(ref[n, c]))
+            if abs(int(g[n, c]) - int(ref[n, c])) != 1 or lo < 0 or lo >= kn.shape[-1]:
+                out.append(float("inf"))
+                continue
+            knot = kn[n, c, lo]
+            out.append(float(abs(np.float64(v[n, c]) - np.float64(knot)) / np.spacing(np.abs(knot))))
+    return out
+
+
 def test_spline_bins_end_to_end(gpu):
-    """Bins produced inside the flow match the oracle except for inputs within 1e-5 of a knot."""
+    """Bins produced inside the flow (knots from the tcgen05 conditioner, a differently rounded GEMM than the CPU's) equal the
+    oracle's except where the searched value sits within a few float32 spacings of the knot separating the two answers:
+    every mismatch is explained that way (measured on B200: 1 of 64 000 at 8 spacings), none is tolerated otherwise."""
     nf = gpu
     dtype = np.float32
-    of = oracle_flow("nsf", 16, dtype, hdims=[32, 32], K=10, B=5.0, nlayers=2)
-    gf = gpu_flow(nf, of, dtype)
-    xs = z0(2000, 16, dtype)
-    got = nf.spline_bins(gf, xs)
-    of.forward(torch.from_numpy(xs))
-    ref = [l.last_bins.numpy() for l in reversed(of.layers)]
-    mism = sum(int((a != b).sum()) for a, b in zip(got, ref))
-    total = sum(a.size for a in got)
-    assert mism <= 1e-4 * total, (mism, total)
+    for (kw, n) in ((dict(hdims=[32, 32], K=10, B=5.0, nlayers=2), 2000), (dict(hdims=[32, 32], K=10, B=5.0, nlayers=4), 1000)):
+        of = oracle_flow("nsf", 16, dtype, **kw)
+        gf = gpu_flow(nf, of, dtype)
+        xs = z0(n, 16, dtype)
+        got = nf.spline_bins(gf, xs)
+        of.forward(torch.from_numpy(xs))
+        ulps = bin_mismatch_ulps(of, got)
+        total = sum(a.size for a in got)
+        assert len(ulps) <= 1e-4 * total, (len(ulps), total)
+        assert all(u <= 32 for u in ulps), ulps
 
 
 def test_tc_gemm_accuracy(gpu):
