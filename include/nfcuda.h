@@ -123,6 +123,13 @@ NF_API int64_t nf_flow_num_params(nf_flow_t flow);
 NF_API int     nf_flow_dim(nf_flow_t flow);
 /* Base distribution q0 = MvNormal(mu, Diagonal(sigma.^2)); NULL -> zeros / ones.  double arrays of length dim. */
 NF_API int     nf_flow_set_base(nf_flow_t flow, const double* mu, const double* sigma);
+/* Full-covariance base q0 = MvNormal(mu, Sigma), Sigma = L L^T (what reference ext/NormalizingFlowsCUDAExt.jl:43-47 samples
+ * with `unwhiten!`; logpdf per Distributions).  L: dim x dim ROW-major lower-triangular Cholesky factor with
+ * a positive diagonal (Julia: `permutedims(cholesky(Sigma).L)` of the column-major array, or pass `cholesky(Sigma).U`'s
+ * memory as is); entries above the diagonal are ignored.  mu may be NULL (zeros).  Sampling, ELBO, log-likelihood, logpdf
+ * and rand use it on every flow family, except log-likelihood / logpdf / inverse of purely planar / radial flows
+ * (NF_ERR_UNSUPPORTED).  nf_flow_set_base switches back to the diagonal form. */
+NF_API int     nf_flow_set_base_chol(nf_flow_t flow, const double* mu, const double* L);
 /* nf_mma_mode for the coupling MLPs; default NF_MMA_F16X3 for NF_F32 flows, NF_MMA_SIMT for NF_F64. */
 NF_API int     nf_flow_set_mma_mode(nf_flow_t flow, int mode);
 /* Cap (bytes) on the activation workspace; batches larger than fits are processed in sample chunks. */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "nf_flow_num_params": (_i64, [_vp]),
     "nf_flow_dim": (_i, [_vp]),
     "nf_flow_set_base": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
+    "nf_flow_set_base_chol": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "nf_flow_set_mma_mode": (_i, [_vp, _i]),
     "nf_flow_set_workspace_limit": (_i, [_vp, _sz]),
     "nf_flow_param_offset": (_i64, [_vp, _i]),

@@ -50,7 +50,16 @@ class MvNormal:
 
     def __init__(self, mu, sigma=None):
         self.mu = np.asarray(mu, dtype=np.float64).reshape(-1)
-        self.sigma = np.ones_like(self.mu) if sigma is None else np.asarray(sigma, dtype=np.float64).reshape(-1)
+        self.chol = None
+        sg = None if sigma is None else np.asarray(sigma, dtype=np.float64)
+        if sg is not None and sg.ndim == 2:
+            # MvNormal(mu, Sigma) with a full covariance matrix (reference test/ext/CUDA/cuda.jl:33-37): keep its Cholesky factor
+            if sg.shape != (self.mu.size, self.mu.size) or not np.allclose(sg, sg.T):
+                raise ValueError("Sigma must be a symmetric dim x dim matrix")
+            self.chol = np.ascontiguousarray(np.linalg.cholesky(sg))
+            self.sigma = np.sqrt(np.diag(sg))
+            return
+        self.sigma = np.ones_like(self.mu) if sg is None else sg.reshape(-1)
         if self.sigma.shape != self.mu.shape or np.any(self.sigma <= 0):
             raise ValueError("sigma must be positive with the shape of mu")
 
@@ -366,7 +375,11 @@ class Flow:
             if P != self.theta.size:
                 raise K.NFCudaError("parameter count mismatch: library %d vs host %d" % (P, self.theta.size))
             mu = np.ascontiguousarray(self.dist.mu); sg = np.ascontiguousarray(self.dist.sigma)
-            K.check(K.lib().nf_flow_set_base(h, mu.ctypes.data_as(C.POINTER(C.c_double)), sg.ctypes.data_as(C.POINTER(C.c_double))))
+            if getattr(self.dist, "chol", None) is not None:
+                Lc = np.ascontiguousarray(self.dist.chol, dtype=np.float64)
+                K.check(K.lib().nf_flow_set_base_chol(h, mu.ctypes.data_as(C.POINTER(C.c_double)), Lc.ctypes.data_as(C.POINTER(C.c_double))))
+            else:
+                K.check(K.lib().nf_flow_set_base(h, mu.ctypes.data_as(C.POINTER(C.c_double)), sg.ctypes.data_as(C.POINTER(C.c_double))))
         return self._h
 
     def __del__(self):

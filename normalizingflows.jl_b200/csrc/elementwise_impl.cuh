@@ -15,6 +15,7 @@
 #pragma once
 #include "flow.hpp"
 #include "targets.cuh"
+#include "base_dense.cuh"
 
 namespace nf {
 
@@ -175,6 +176,7 @@ template <typename T> struct EwArgs {
   int L, d, flags;
   uint64_t seed;
   int64_t row0;         // global row of sample 0 (Philox draws of a data-parallel shard)
+  const T* lq0;         // optional per-sample log q0(x0) (full-covariance base: computed by base_dense_kernel; base == nullptr then)
 };
 
 template <typename T, int DP, int S, bool LR>
@@ -231,7 +233,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
 #pragma unroll
         for (int k = 0; k < DP; ++k) q += z[s][k] * z[s][k];
       }
-      lq[s] = a.base_c0 - q / 2;
+      lq[s] = a.lq0 ? a.lq0[jj] : a.base_c0 - q / 2;
       ld[s] = 0;
     }
     {   // a warp without a single live sample (ragged last group, tiny batches) has nothing to add to any sum
@@ -977,6 +979,27 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
   a.z0 = z0_dev; a.table = table; a.kinds = f.d_ew_kinds;
   a.base = f.base_is_standard ? nullptr : (const T*)f.d_base;
   a.base_c0 = (T)f.base_c0;
+  if (f.base_dense) {
+    // q0 = MvNormal(mu, L L^T): the draws (or the caller's x0) and their log-density come from base_dense_kernel; the fused
+    // kernel then sees ready-made x0 and a per-sample log q0
+    if (inverse) {
+      set_error("full-covariance base: log-likelihood / inverse of purely elementwise (planar / radial) flows is not implemented");
+      return NF_ERR_UNSUPPORTED;
+    }
+    T* lq0 = (T*)f.ws_alloc((size_t)N * sizeof(T));
+    if (!lq0) return NF_ERR_OOM;
+    if (!z0_dev) {
+      T* x0 = (T*)f.ws_alloc((size_t)N * d * sizeof(T));
+      if (!x0) return NF_ERR_OOM;
+      base_sample_kernel<T><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>(x0, nullptr, d, N, seed, f.draw_row_offset);
+      NF_LAUNCH_CHECK();
+      NF_TRY(base_dense_launch<T>(f, x0, N, 0, lq0, nullptr));
+      z0_dev = x0;
+    } else {
+      NF_TRY(base_dense_launch<T>(f, const_cast<T*>(z0_dev), N, 1, lq0, nullptr));
+    }
+    a.z0 = z0_dev; a.base = nullptr; a.lq0 = lq0;
+  }
   if (tgt) a.tp = tgt->params<T>();
   if (f.score_target) a.sp = f.score_target->params<T>();
   a.y_out = y_out; a.ld_out = ld_out; a.terms_out = terms_out;

@@ -114,6 +114,9 @@ struct Flow {
   std::vector<double> base_mu, base_sigma;
   void* d_base = nullptr;              // dtype[2*dim]: mu then sigma
   double base_c0 = 0;
+  // full covariance: q0 = MvNormal(mu, L L^T) (nf_flow_set_base_chol); d_base_L = dtype[dim*dim + dim]: L (row major, lower) then mu
+  bool base_dense = false;
+  void* d_base_L = nullptr;
 
   // elementwise-path metadata
   EwLayerMeta* d_ew_meta = nullptr;

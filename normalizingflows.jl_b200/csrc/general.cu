@@ -8,6 +8,7 @@
 #include "general.hpp"
 #include "kernels_coupling.cuh"
 #include "tc_gemm.hpp"
+#include "base_dense.cuh"
 
 namespace nf {
 
@@ -59,7 +60,7 @@ size_t per_sample_bytes(const Flow& f, bool stash) {
   const int L = (int)f.layers.size();
   size_t b = 0;
   b += (size_t)(stash ? L + 1 : 3) * f.dim * es;   // X
-  b += 2 * es;                                      // ld, gld
+  b += 3 * es;                                      // ld, gld, lq0 (full-covariance base)
   b += (size_t)f.dim * es;                          // G
   size_t layer_max = 0, layer_sum = 0;
   for (auto& Ld : f.layers) {
@@ -445,7 +446,7 @@ int run_typed(Flow& f, const GeneralJob& job) {
   if (job.op == OP_FORWARD_STASH) NF_REQUIRE(Nc >= N, "nf_forward_stash: batch of %lld does not fit the workspace limit", (long long)N);
   if (job.op == OP_ELBO || job.op == OP_LOGLIK) NF_CUDA(cudaMemsetAsync(f.d_gsum, 0, (f.P + 1) * sizeof(double), f.stream));
   if (f.mma_mode != NF_MMA_SIMT) NF_TRY(tc_prepare_weights(f, (const float*)theta));
-  const T* base = f.base_is_standard ? nullptr : (const T*)f.d_base;
+  const T* base = (f.base_is_standard || f.base_dense) ? nullptr : (const T*)f.d_base;
   const size_t ws_mark = f.ws.off;
   for (int64_t c0 = 0; c0 < N; c0 += Nc) {
     const int64_t n = std::min(Nc, N - c0);
@@ -454,9 +455,17 @@ int run_typed(Flow& f, const GeneralJob& job) {
     Chunk c;
     const T* in = job.in_dev ? (const T*)job.in_dev + c0 * d : nullptr;
     NF_TRY(alloc_chunk(f, c, n, stash, in));
+    T* lq0 = nullptr;           // full-covariance base: per-sample log q0(x0) (and, for the log-likelihood, its gradient) from base_dense_kernel
+    if (f.base_dense && (job.op == OP_ELBO || job.op == OP_LOGLIK)) {
+      lq0 = (T*)f.ws_alloc((size_t)n * sizeof(T));
+      if (!lq0) return NF_ERR_OOM;
+    }
     if (!in) {
       base_sample_kernel<T><<<(unsigned)ceil_div(n * d, 256), 256, 0, f.stream>>>((T*)c.X[0], base, d, n, job.seed, c0 + f.draw_row_offset, job.seed_iter_dev);
       NF_LAUNCH_CHECK();
+      if (f.base_dense) NF_TRY(base_dense_launch<T>(f, (T*)c.X[0], n, 0, lq0, nullptr));    // eps -> mu + L eps, lq0 from eps
+    } else if (f.base_dense && job.op == OP_ELBO) {
+      NF_TRY(base_dense_launch<T>(f, (T*)c.X[0], n, 1, lq0, nullptr));                      // lq0 = log q0(x0); x0 untouched
     }
     const int last = stash ? L : 1 + ((L - 1) & 1);
     if (f.mma_mode != NF_MMA_SIMT) {
@@ -480,11 +489,11 @@ int run_typed(Flow& f, const GeneralJob& job) {
             if (sm > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             kern<<<(unsigned)ceil_div(n, 128), 128, sm, f.stream>>>((const T*)c.X[last], (const T*)c.X[0], (const T*)c.ld,
                                                                     job.tgt->params<T>(), base, (T)f.base_c0, d, n, (T*)c.G, terms,
-                                                                    f.d_gsum + f.P);
+                                                                    f.d_gsum + f.P, lq0);
           } else {
             elbo_head_kernel<T><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
                 (const T*)c.X[last], (const T*)c.X[0], (const T*)c.ld, job.tgt->params<T>(), base, (T)f.base_c0, d, n,
-                (T*)c.G, terms, f.d_gsum + f.P);
+                (T*)c.G, terms, f.d_gsum + f.P, lq0);
           }
         }
         NF_LAUNCH_CHECK();
@@ -497,8 +506,10 @@ int run_typed(Flow& f, const GeneralJob& job) {
       case OP_LOGLIK: {
         NF_TRY(sweep_inverse<T>(f, c, theta));
         T* terms = job.terms_out ? (T*)job.terms_out + c0 : nullptr;
+        if (f.base_dense) NF_TRY(base_dense_launch<T>(f, (T*)c.X[last], n, 1, lq0, grad ? (T*)c.G : nullptr));
         loglik_head_kernel<T><<<(unsigned)ceil_div(n, 128), 128, 0, f.stream>>>(
-            (const T*)c.X[last], (const T*)c.ld, base, (T)f.base_c0, d, n, grad ? (T*)c.G : nullptr, terms, f.d_gsum + f.P);
+            (const T*)c.X[last], (const T*)c.ld, base, (T)f.base_c0, d, n, (grad && !f.base_dense) ? (T*)c.G : nullptr, terms, f.d_gsum + f.P,
+            lq0);
         NF_LAUNCH_CHECK();
         if (grad) {
           NF_TRY(alloc_backward_tmps(f, c));
@@ -608,11 +619,16 @@ void general_release(Flow& f) {
 
 int base_sample_dev(Flow& f, int64_t N, uint64_t seed, void* z_dev) {
   const int d = f.dim;
+  const bool plain = f.base_is_standard || f.base_dense;
   if (f.dtype == NF_F32)
-    base_sample_kernel<float><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>((float*)z_dev, f.base_is_standard ? nullptr : (const float*)f.d_base, d, N, seed, 0);
+    base_sample_kernel<float><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>((float*)z_dev, plain ? nullptr : (const float*)f.d_base, d, N, seed, 0);
   else
-    base_sample_kernel<double><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>((double*)z_dev, f.base_is_standard ? nullptr : (const double*)f.d_base, d, N, seed, 0);
+    base_sample_kernel<double><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>((double*)z_dev, plain ? nullptr : (const double*)f.d_base, d, N, seed, 0);
   NF_LAUNCH_CHECK();
+  if (f.base_dense) {       // unwhiten!(Sigma, x) .+ mu of reference ext/NormalizingFlowsCUDAExt.jl:43-47
+    if (f.dtype == NF_F32) NF_TRY(base_dense_launch<float>(f, (float*)z_dev, N, 0, nullptr, nullptr));
+    else NF_TRY(base_dense_launch<double>(f, (double*)z_dev, N, 0, nullptr, nullptr));
+  }
   return NF_OK;
 }
 

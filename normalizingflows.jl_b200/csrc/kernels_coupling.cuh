@@ -827,29 +827,32 @@ __global__ void rqs_bin_search_kernel(const T* __restrict__ knots, const T* __re
 template <typename T>
 __global__ void elbo_head_tiled_kernel(const T* __restrict__ Y, const T* __restrict__ X0, const T* __restrict__ ld,
                                        TargetParams<T> tp, const T* __restrict__ base, T base_c0, int d, int64_t N,
-                                       T* __restrict__ G, T* __restrict__ terms, double* __restrict__ sum_out) {
+                                       T* __restrict__ G, T* __restrict__ terms, double* __restrict__ sum_out,
+                                       const T* __restrict__ lq0 = nullptr) {
   extern __shared__ __align__(16) unsigned char head_smem[];
   T* sm = reinterpret_cast<T*>(head_smem);
   const int nthr = blockDim.x, tid = threadIdx.x, pitch = d + 1;
   const int64_t r0 = (int64_t)blockIdx.x * nthr;
   const int nrows = (int)((N - r0) < nthr ? (N - r0) : nthr);
   const int cnt = nrows * d;
-  for (int i = tid; i < cnt; i += nthr) sm[(i / d) * pitch + (i % d)] = X0[r0 * d + i];
-  __syncthreads();
   T q = 0;
-  if (tid < nrows)
-    for (int k = 0; k < d; ++k) {
-      const T x = sm[tid * pitch + k];
-      const T u = base ? (x - base[k]) / base[d + k] : x;
-      q += u * u;
-    }
-  __syncthreads();
+  if (!lq0) {          // lq0: per-sample log q0(x0) computed elsewhere (full-covariance base)
+    for (int i = tid; i < cnt; i += nthr) sm[(i / d) * pitch + (i % d)] = X0[r0 * d + i];
+    __syncthreads();
+    if (tid < nrows)
+      for (int k = 0; k < d; ++k) {
+        const T x = sm[tid * pitch + k];
+        const T u = base ? (x - base[k]) / base[d + k] : x;
+        q += u * u;
+      }
+    __syncthreads();
+  }
   for (int i = tid; i < cnt; i += nthr) sm[(i / d) * pitch + (i % d)] = Y[r0 * d + i];
   __syncthreads();
   double term = 0;
   if (tid < nrows) {
     const T lp = target_logp_score<T, 0>(tp, sm + tid * pitch, sm + tid * pitch);
-    const T t = lp - (base_c0 - q / 2) + ld[r0 + tid];
+    const T t = lp - (lq0 ? lq0[r0 + tid] : (base_c0 - q / 2)) + ld[r0 + tid];
     if (terms) terms[r0 + tid] = t;
     term = (double)t;
   }
@@ -870,17 +873,19 @@ __global__ void elbo_head_tiled_kernel(const T* __restrict__ Y, const T* __restr
 template <typename T>
 __global__ void elbo_head_kernel(const T* __restrict__ Y, const T* __restrict__ X0, const T* __restrict__ ld,
                                  TargetParams<T> tp, const T* __restrict__ base, T base_c0, int d, int64_t N,
-                                 T* __restrict__ G, T* __restrict__ terms, double* __restrict__ sum_out) {
+                                 T* __restrict__ G, T* __restrict__ terms, double* __restrict__ sum_out,
+                                 const T* __restrict__ lq0 = nullptr) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double term = 0;
   if (r < N) {
     const T lp = target_logp_score<T, 0>(tp, Y + r * d, G + r * d);
     T q = 0;
-    for (int k = 0; k < d; ++k) {
-      const T u = base ? (X0[r * d + k] - base[k]) / base[d + k] : X0[r * d + k];
-      q += u * u;
-    }
-    const T t = lp - (base_c0 - q / 2) + ld[r];
+    if (!lq0)
+      for (int k = 0; k < d; ++k) {
+        const T u = base ? (X0[r * d + k] - base[k]) / base[d + k] : X0[r * d + k];
+        q += u * u;
+      }
+    const T t = lp - (lq0 ? lq0[r] : (base_c0 - q / 2)) + ld[r];
     if (terms) terms[r] = t;
     term = (double)t;
   }
@@ -900,18 +905,19 @@ __global__ void elbo_head_kernel(const T* __restrict__ Y, const T* __restrict__ 
 template <typename T>
 __global__ void loglik_head_kernel(const T* __restrict__ X0, const T* __restrict__ ld, const T* __restrict__ base,
                                    T base_c0, int d, int64_t N, T* __restrict__ G, T* __restrict__ terms,
-                                   double* __restrict__ sum_out) {
+                                   double* __restrict__ sum_out, const T* __restrict__ lq0 = nullptr) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double term = 0;
   if (r < N) {
     T q = 0;
+    if (!lq0)      // lq0 (+ G already written): full-covariance base handled by base_dense_kernel
     for (int k = 0; k < d; ++k) {
       const T is = base ? 1 / base[d + k] : T(1);
       const T u = base ? (X0[r * d + k] - base[k]) * is : X0[r * d + k];
       q += u * u;
       if (G) G[r * d + k] = -u * is;
     }
-    const T t = (base_c0 - q / 2) + ld[r];
+    const T t = (lq0 ? lq0[r] : (base_c0 - q / 2)) + ld[r];
     if (terms) terms[r] = t;
     term = (double)t;
   }
@@ -924,21 +930,6 @@ __global__ void loglik_head_kernel(const T* __restrict__ X0, const T* __restrict
     for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) s += sh[w];
     atomicAdd(sum_out, s);
   }
-}
-
-// K7: base draws x = mu + sigma .* randn  (reference ext/NormalizingFlowsCUDAExt.jl:43-48)
-// seed_iter (optional, device): added to the seed -- the iteration counter of a CUDA-graph-replayed training loop, so that one
-// captured launch draws a fresh batch at every replay.
-template <typename T>
-__global__ void base_sample_kernel(T* __restrict__ Z, const T* __restrict__ base, int d, int64_t N, uint64_t seed, int64_t row0,
-                                   const int64_t* __restrict__ seed_iter = nullptr) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= N * d) return;
-  if (seed_iter) seed += (uint64_t)*seed_iter;
-  const int k = (int)(e % d);
-  T z = philox_randn<T>(seed, (uint64_t)(row0 * d + e));
-  if (base) z = z * base[d + k] + base[k];
-  Z[e] = z;
 }
 
 }  // namespace nf

@@ -288,7 +288,7 @@ static void flow_destroy(Flow* f) {
   if (f->stream) cudaStreamSynchronize(f->stream);
   general_release(*f);
   for (auto& L : f->layers) { cudaFree(L.d_idx1); cudaFree(L.d_idx2); cudaFree(L.d_pos); }
-  cudaFree(f->d_base); cudaFree(f->d_ew_meta); cudaFree(f->d_ew_kinds);
+  cudaFree(f->d_base); cudaFree(f->d_base_L); cudaFree(f->d_ew_meta); cudaFree(f->d_ew_kinds);
   cudaFree(f->d_theta); cudaFree(f->d_gsum); cudaFree(f->d_out); cudaFreeHost(f->h_pinned);
   cudaFree(f->d_adam); cudaFree(f->d_stats); cudaFree(f->d_iter);
   cudaFree(f->ws.base);
@@ -494,7 +494,38 @@ int nf_flow_set_base(nf_flow_t flow, const double* mu, const double* sigma) {
     f.base_sigma[k] = sigma ? sigma[k] : 1.0;
     NF_REQUIRE(f.base_sigma[k] > 0, "base sigma must be positive");
   }
+  f.base_dense = false;
   return upload_base(f);
+}
+
+int nf_flow_set_base_chol(nf_flow_t flow, const double* mu, const double* L) {
+  NF_CHECK_HANDLE(flow);
+  Flow& f = NF_FLOW(flow);
+  NF_REQUIRE(L, "nf_flow_set_base_chol: L is null");
+  NF_CUDA(cudaSetDevice(f.device));
+  const int d = f.dim;
+  double c0 = -0.5 * d * NF_LOG2PI;
+  for (int i = 0; i < d; ++i) {
+    NF_REQUIRE(L[i * d + i] > 0, "nf_flow_set_base_chol: the Cholesky factor needs a positive diagonal (L[%d][%d] = %g)", i, i, L[i * d + i]);
+    c0 -= std::log(L[i * d + i]);
+  }
+  const size_t n = (size_t)d * d + d;
+  if (!f.d_base_L) NF_CUDA(cudaMalloc(&f.d_base_L, n * sizeof(double)));
+  std::vector<double> h(n, 0.0);
+  for (int i = 0; i < d; ++i)
+    for (int k = 0; k <= i; ++k) h[(size_t)i * d + k] = L[i * d + k];     // strictly upper part is ignored
+  for (int i = 0; i < d; ++i) { h[(size_t)d * d + i] = mu ? mu[i] : 0.0; f.base_mu[i] = h[(size_t)d * d + i]; }
+  if (f.dtype == NF_F32) {
+    std::vector<float> hf(h.begin(), h.end());
+    NF_CUDA(cudaMemcpy(f.d_base_L, hf.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  } else {
+    NF_CUDA(cudaMemcpy(f.d_base_L, h.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  f.base_dense = true;
+  f.base_is_standard = false;
+  f.base_c0 = c0;
+  f.plan_valid = false;
+  return NF_OK;
 }
 
 int nf_flow_set_mma_mode(nf_flow_t flow, int mode) {

@@ -494,6 +494,7 @@ class Flow:
     layers: List[Layer]
     base_mu: Optional[torch.Tensor] = None
     base_sigma: Optional[torch.Tensor] = None
+    base_chol: Optional[torch.Tensor] = None            # full covariance Sigma = L L^T (lower L); overrides base_sigma
     dtype: torch.dtype = torch.float64
 
     def params(self) -> List[torch.Tensor]:
@@ -522,6 +523,11 @@ class Flow:
 
     def base_logpdf(self, x):                           # App. A.8
         mu = self.base_mu if self.base_mu is not None else torch.zeros(self.dim, dtype=x.dtype)
+        if self.base_chol is not None:
+            # Distributions.logpdf(MvNormal(mu, Sigma)): -(d log 2pi + logdet Sigma)/2 - |L^-1 (x - mu)|^2 / 2
+            L = self.base_chol.to(x.dtype)
+            z = torch.linalg.solve_triangular(L, (x - mu).T, upper=False).T
+            return -0.5 * self.dim * LOG2PI - torch.log(torch.diagonal(L)).sum() - 0.5 * (z * z).sum(dim=1)
         sg = self.base_sigma if self.base_sigma is not None else torch.ones(self.dim, dtype=x.dtype)
         z = (x - mu) / sg
         return -0.5 * self.dim * LOG2PI - torch.log(sg).sum() - 0.5 * (z * z).sum(dim=1)
@@ -529,6 +535,8 @@ class Flow:
     def base_sample(self, z_std):
         """MvNormal sampling as ext/NormalizingFlowsCUDAExt.jl:43-48: randn -> unwhiten -> + mu."""
         mu = self.base_mu if self.base_mu is not None else torch.zeros(self.dim, dtype=z_std.dtype)
+        if self.base_chol is not None:                  # unwhiten!(Sigma, x) .+ mu (ext/NormalizingFlowsCUDAExt.jl:45-46)
+            return z_std @ self.base_chol.to(z_std.dtype).T + mu
         sg = self.base_sigma if self.base_sigma is not None else torch.ones(self.dim, dtype=z_std.dtype)
         return z_std * sg + mu
 

@@ -54,6 +54,9 @@ def gpu_flow(nf, of, dtype, base=None):
             raise TypeError(l)
     mu = np.zeros(of.dim) if of.base_mu is None else of.base_mu.numpy()
     sg = np.ones(of.dim) if of.base_sigma is None else of.base_sigma.numpy()
+    if getattr(of, "base_chol", None) is not None:
+        Lc = of.base_chol.double().numpy()
+        sg = Lc @ Lc.T                                  # MvNormal(mu, Sigma): full covariance
     f = nf.Flow(layers, nf.MvNormal(mu, sg), dtype)
     f.theta = of.theta().numpy().astype(dtype)
     return f
