@@ -157,7 +157,9 @@ __device__ __forceinline__ void leapfrog_backward(const TargetParams<T>& sp, T* 
   for (int k = 0; k < HD; ++k) gx[k] += hw[k];
 }
 
-enum : int { EW_GRAD = 1, EW_TARGET = 2, EW_WRITE_Y = 4, EW_WRITE_LD = 8, EW_WRITE_TERMS = 16, EW_GEN_Z0 = 32 };
+// EW_EXT_GRAD: a run of elementwise layers INSIDE a layered (coupling) flow -- no target; the backward sweep starts from the
+// caller's d/dy (g_in) and per-sample d/dlogdet (gld, nullptr = 1) and leaves d/dx in g_out.  EW_ADD_LD: ld_out[j] += logdet.
+enum : int { EW_GRAD = 1, EW_TARGET = 2, EW_WRITE_Y = 4, EW_WRITE_LD = 8, EW_WRITE_TERMS = 16, EW_GEN_Z0 = 32, EW_EXT_GRAD = 64, EW_ADD_LD = 128 };
 
 template <typename T> struct EwArgs {
   const T* z0;          // [N, d] (ignored with EW_GEN_Z0)
@@ -177,6 +179,9 @@ template <typename T> struct EwArgs {
   uint64_t seed;
   int64_t row0;         // global row of sample 0 (Philox draws of a data-parallel shard)
   const T* lq0;         // optional per-sample log q0(x0) (full-covariance base: computed by base_dense_kernel; base == nullptr then)
+  const T* g_in;        // EW_EXT_GRAD: [N, d] d/dy
+  T* g_out;             // EW_EXT_GRAD: [N, d] d/dx (may alias g_in)
+  const T* gld;         // EW_EXT_GRAD: [N] d/dlogdet or nullptr (= 1)
 };
 
 template <typename T, int DP, int S, bool LR>
@@ -205,6 +210,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
   for (int64_t gi = bid; gi < ngroups; gi += nblk) {
     T z[S][DP], ld[S], lq[S];
     bool live[S];
+    T wl[S];              // d(objective)/d(logdet) of the sample: 1 for the ELBO, the caller's weight in EW_EXT_GRAD mode, 0 if not live
     // ---- load base draws, base log-density (a15) ----
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -235,6 +241,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
       }
       lq[s] = a.lq0 ? a.lq0[jj] : a.base_c0 - q / 2;
       ld[s] = 0;
+      wl[s] = live[s] ? (((a.flags & EW_EXT_GRAD) && a.gld) ? a.gld[jj] : T(1)) : T(0);
     }
     {   // a warp without a single live sample (ragged last group, tiny batches) has nothing to add to any sum
       bool any_live = false;
@@ -315,9 +322,24 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
         if (a.flags & EW_WRITE_LD) a.ld_out[j] = ld[s];
       }
     }
-    if (!(a.flags & EW_TARGET)) continue;
+    if (a.flags & EW_ADD_LD) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int64_t j = gi * group + (int64_t)s * nthr + tid;
+        if (live[s]) a.ld_out[j] += ld[s];
+      }
+    }
+    if (!(a.flags & (EW_TARGET | EW_EXT_GRAD))) continue;
     // ---- target log-density + score (a16), ELBO term ----
     T gy[S][DP];
+    if (a.flags & EW_EXT_GRAD) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int64_t j = gi * group + (int64_t)s * nthr + tid;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) gy[s][k] = (live[s] && k < d) ? a.g_in[j * d + k] : T(0);
+      }
+    } else
 #pragma unroll
     for (int s = 0; s < S; ++s) {
 #pragma unroll
@@ -355,7 +377,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           const T t = s_stash[((size_t)l * S + s) * nthr + tid];
-          const T w8 = live[s] ? T(1) : T(0);
+          const T w8 = wl[s];
           const T psi = 1 - t * t, den = 1 + m * psi;
           T ug = 0;
 #pragma unroll
@@ -388,7 +410,7 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           const T r = s_stash[((size_t)l * S + s) * nthr + tid];
-          const T w8 = live[s] ? T(1) : T(0);
+          const T w8 = wl[s];
           const T h = 1 / (alpha + r), g = bh * h;
           const T ifac = 1 / (1 + g);
           T df[DP], gd = 0;
@@ -468,6 +490,16 @@ __device__ __forceinline__ void ew_flow_body(const EwArgs<T>& a, const int bid, 
           const T v = warp_sum(ge[k]);
           if (lane == 0) acc[k] += v;
         }
+      }
+    }
+    if (a.flags & EW_EXT_GRAD) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int64_t j = gi * group + (int64_t)s * nthr + tid;
+        if (!live[s]) continue;
+#pragma unroll
+        for (int k = 0; k < DP; ++k)
+          if (k < d) a.g_out[j * d + k] = gy[s][k];
       }
     }
   }
@@ -817,9 +849,10 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
 template <typename T, int DP>
 __device__ __forceinline__ void ew_finalize_body(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
                                                  const T* __restrict__ gpart, const double* __restrict__ epart, int nblocks,
-                                                 int64_t N, int64_t P, int want_grad, int inverse, double* __restrict__ gsum, int l) {
+                                                 int64_t N, int64_t P, int want_grad, int inverse, double* __restrict__ gsum, int l,
+                                                 int accumulate = 0) {
   constexpr int NACC = ew_nacc<DP>();
-  if (l == 0) {
+  if (l == 0 && epart) {
     double e = 0;
     for (int b = 0; b < nblocks; ++b) e += epart[b];
     gsum[P] = e;
@@ -830,7 +863,9 @@ __device__ __forceinline__ void ew_finalize_body(const T* __restrict__ theta, co
   for (int b = 0; b < nblocks; ++b)
     for (int i = 0; i < NACC; ++i) G[i] += (double)gpart[((size_t)b * L + l) * NACC + i];
   const T* p = theta + meta[l].theta_off;
-  double* g = gsum + meta[l].theta_off;
+  double* gdst = gsum + meta[l].theta_off;
+  double gtmp[2 * DP + 2];
+  double* g = accumulate ? gtmp : gdst;        // a segment of a layered flow adds into sums other chunks may already hold
   switch (meta[l].kind) {
     case NF_PLANAR: {  // App. A.1 hand backward through u_hat(u, w)
       const T* w = p; const T* u = p + d;
@@ -875,13 +910,25 @@ __device__ __forceinline__ void ew_finalize_body(const T* __restrict__ theta, co
       break;
     }
   }
+  if (accumulate) {
+    int np = 0;
+    switch (meta[l].kind) {
+      case NF_PLANAR: np = 2 * d + 1; break;
+      case NF_RADIAL: np = d + 2; break;
+      case NF_SHIFT: case NF_SCALE: np = d; break;
+      case NF_MOMENTUM_AFFINE: np = d; break;
+      case NF_LEAPFROG: np = d / 2; break;
+    }
+    for (int k = 0; k < np; ++k) gdst[k] += gtmp[k];
+  }
 }
 
 template <typename T, int DP>
 __global__ void ew_finalize_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
                                    const T* __restrict__ gpart, const double* __restrict__ epart, int nblocks,
-                                   int64_t N, int64_t P, int want_grad, int inverse, double* __restrict__ gsum) {
-  ew_finalize_body<T, DP>(theta, meta, L, d, gpart, epart, nblocks, N, P, want_grad, inverse, gsum, (int)(blockIdx.x * blockDim.x + threadIdx.x));
+                                   int64_t N, int64_t P, int want_grad, int inverse, double* __restrict__ gsum, int accumulate = 0) {
+  ew_finalize_body<T, DP>(theta, meta, L, d, gpart, epart, nblocks, N, P, want_grad, inverse, gsum, (int)(blockIdx.x * blockDim.x + threadIdx.x),
+                          accumulate);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1017,6 +1064,65 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
     NF_LAUNCH_CHECK();
   }
   return NF_OK;
+}
+
+// A run of elementwise layers [l0, l0 + Lseg) INSIDE a layered (coupling) flow (reference src/flows/utils.jl:23-26: any
+// composition of bijectors is a flow).  forward: Xout = T_seg(Xin), ld += logdet.  backward: recomputes the run from its input
+// state Xin, pulls G (d/dy -> d/dx, in place) and the per-sample logdet weights gld (nullptr = 1) back through it and ADDS the
+// parameter-gradient sums into gsum.
+template <typename T, int DP, int S>
+static int ew_segment_launch(Flow& f, int l0, int Lseg, const T* theta_dev, int64_t N, const T* Xin, T* Xout, T* ld, bool backward,
+                             T* G, const T* gld, double* gsum) {
+  const int d = f.dim;
+  constexpr int STR = ew_stride<DP>(), NACC = ew_nacc<DP>();
+  const int threads = 128;
+  const size_t smem = ((size_t)Lseg * STR + (size_t)(threads / 32) * Lseg * NACC + (size_t)Lseg * S * threads) * sizeof(T) + (size_t)Lseg * sizeof(int) + 16;
+  if (smem > 200 * 1024) {
+    set_error("a run of %d elementwise layers needs %zu B of shared memory (limit 200 KiB)", Lseg, smem);
+    return NF_ERR_UNSUPPORTED;
+  }
+  auto kern = ew_flow_kernel<T, DP, S, false>;
+  NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t group = (int64_t)threads * S;
+  int max_blocks = 0;
+  NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kern, threads, smem));
+  if (max_blocks < 1) max_blocks = 1;
+  const int grid = (int)std::min<int64_t>(ceil_div(N, group), (int64_t)kNumSMs * max_blocks);
+  T* table = (T*)f.ws_alloc((size_t)Lseg * STR * sizeof(T));
+  T* gpart = backward ? (T*)f.ws_alloc((size_t)grid * Lseg * NACC * sizeof(T)) : nullptr;
+  if (!table || (backward && !gpart)) return NF_ERR_OOM;
+  ew_prep_kernel<T, DP><<<(Lseg + 63) / 64, 64, 0, f.stream>>>(theta_dev, f.d_ew_meta + l0, Lseg, d, table);
+  NF_LAUNCH_CHECK();
+  EwArgs<T> a{};
+  a.z0 = Xin; a.table = table; a.kinds = f.d_ew_kinds + l0;
+  a.N = N; a.L = Lseg; a.d = d;
+  if (!backward) { a.flags = EW_WRITE_Y | EW_ADD_LD; a.y_out = Xout; a.ld_out = ld; }
+  else { a.flags = EW_GRAD | EW_EXT_GRAD; a.g_in = G; a.g_out = G; a.gld = gld; a.gpart = gpart; }
+  f.prof.begin("ew_segment", f.stream);
+  kern<<<grid, threads, smem, f.stream>>>(a);
+  f.prof.end(f.stream);
+  NF_LAUNCH_CHECK();
+  if (backward) {
+    ew_finalize_kernel<T, DP><<<(Lseg + 63) / 64, 64, 0, f.stream>>>(theta_dev, f.d_ew_meta + l0, Lseg, d, gpart, nullptr, grid, N, f.P, 1, 0, gsum, 1);
+    NF_LAUNCH_CHECK();
+  }
+  return NF_OK;
+}
+
+template <typename T>
+int ew_segment(Flow& f, int l0, int Lseg, const void* theta_dev, int64_t N, const void* Xin, void* Xout, void* ld, bool backward,
+               void* G, const void* gld, double* gsum) {
+  const int d = f.dim;
+#define NF_SEG(DPV, SV) return ew_segment_launch<T, DPV, SV>(f, l0, Lseg, (const T*)theta_dev, N, (const T*)Xin, (T*)Xout, (T*)ld, backward, (T*)G, (const T*)gld, gsum)
+  if (d <= 2) NF_SEG(2, 4);
+  if (d <= 4) NF_SEG(4, 2);
+  if (d <= 8) NF_SEG(8, 1);
+  if (d <= 16) NF_SEG(16, 1);
+  if (d <= 32) NF_SEG(32, 1);
+  if (d <= 64) NF_SEG(64, 1);
+#undef NF_SEG
+  set_error("planar / radial layers inside a coupling flow support dim <= 64, got %d", d);
+  return NF_ERR_UNSUPPORTED;
 }
 
 // One direction (forward sweep / inverse sweep) per translation unit: the kernels are many large instantiations, and

@@ -191,6 +191,13 @@ inline int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, 
                  : ew_run_dir<T, false>(f, tgt, theta_dev, N, z0_dev, seed, want_grad, y_out, ld_out, terms_out, gsum_dev, head);
 }
 
+// a run of planar / radial / shift layers inside a layered (coupling) flow: forward (Xout, ld +=) or backward (G in place, gsum +=)
+template <typename T>
+int ew_segment(Flow& f, int l0, int Lseg, const void* theta_dev, int64_t N, const void* Xin, void* Xout, void* ld, bool backward,
+               void* G, const void* gld, double* gsum);
+extern template int ew_segment<float>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
+extern template int ew_segment<double>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
+
 // single-launch Adam training loop for small batches of elementwise flows (elementwise.cu: ew_train_kernel)
 template <typename T>
 int ew_train(Flow& f, const Target* tgt, int64_t N, uint64_t seed, int n_iters, int t0, double eta, double b1, double b2,

@@ -40,6 +40,21 @@ struct GenState {
 };
 
 inline bool is_coupling(int kind) { return kind == NF_AFFINE_COUPLING || kind == NF_SPLINE_COUPLING; }
+// planar / radial layers composed with couplings (reference src/flows/utils.jl:23-26 puts no restriction on Ls) run as "segments":
+// a maximal run of consecutive planar / radial / shift layers goes through the fused elementwise kernel in one launch
+inline bool is_seg_kind(int kind) { return kind == NF_PLANAR || kind == NF_RADIAL || kind == NF_SHIFT; }
+inline bool is_seg_core(int kind) { return kind == NF_PLANAR || kind == NF_RADIAL; }
+// [lo, hi] = the maximal run of segment-kind layers containing layer li, if that run holds a planar / radial layer (else lo = hi = -1)
+inline void segment_of(const Flow& f, int li, int* lo, int* hi) {
+  *lo = *hi = -1;
+  if (!is_seg_kind(f.layers[li].kind)) return;
+  int a = li, b = li;
+  while (a > 0 && is_seg_kind(f.layers[a - 1].kind)) --a;
+  while (b + 1 < (int)f.layers.size() && is_seg_kind(f.layers[b + 1].kind)) ++b;
+  bool core = false;
+  for (int i = a; i <= b; ++i) core |= is_seg_core(f.layers[i].kind);
+  if (core) { *lo = a; *hi = b; }
+}
 
 int max_width(const Flow& f) {
   int w = 1;
@@ -356,13 +371,24 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
 }
 
 template <typename T>
-int check_supported(const Flow& f) {
-  for (auto& L : f.layers)
+int check_supported(const Flow& f, int op) {
+  bool seg = false;
+  for (auto& L : f.layers) {
+    if (is_seg_core(L.kind)) { seg = true; continue; }
     if (!is_coupling(L.kind) && L.kind != NF_SHIFT && L.kind != NF_SCALE) {
-      set_error("flows mixing planar / radial / Hamiltonian layers with coupling layers are not supported in this build "
-                "(Shift and Scale may be mixed with couplings)");
+      set_error("flows mixing Hamiltonian (LeapFrog / momentum) layers with coupling layers are not supported in this build");
       return NF_ERR_UNSUPPORTED;
     }
+  }
+  if (seg && f.dim > 64) {
+    set_error("planar / radial layers inside a coupling flow support dim <= 64, got %d", f.dim);
+    return NF_ERR_UNSUPPORTED;
+  }
+  if (seg && (op == OP_INVERSE || op == OP_LOGLIK)) {
+    set_error("inverse / logpdf / loglikelihood of flows that mix planar / radial layers with coupling layers is not implemented "
+              "(forward, rand and the ELBO objective are)");
+    return NF_ERR_UNSUPPORTED;
+  }
   return NF_OK;
 }
 
@@ -375,6 +401,19 @@ int sweep_forward(Flow& f, Chunk& c, const T* theta, int32_t* bins, int64_t bins
   int64_t bins_layer_off = 0;   // bins layout [spline layer in application order][N_total][c]
   for (int li = L - 1; li >= 0; --li) {
     const LayerDesc& Ld = f.layers[li];
+    int slo, shi;
+    segment_of(f, li, &slo, &shi);
+    if (slo >= 0) {
+      // layers slo..shi (shi applied first) in one fused launch; the states in between are never materialised
+      const int k = shi - slo + 1;
+      const T* Xin = (const T*)c.xin(state);
+      T* Xout = (T*)c.xout(state + k - 1);
+      NF_TRY(ew_segment<T>(f, slo, k, theta, c.n, Xin, Xout, c.ld, false, nullptr, nullptr, nullptr));
+      if (!c.xmeta.empty()) NF_TRY(tc_absmax(f, (const float*)Xout, c.n * f.dim, c.xmeta[state + k]));
+      state += k;
+      li = slo;
+      continue;
+    }
     LayerBufs& b = c.stash ? c.lb[li] : c.lb[0];
     const T* Xin = (const T*)c.xin(state);
     T* Xout = (T*)c.xout(state);
@@ -417,6 +456,15 @@ int sweep_backward_fwd(Flow& f, Chunk& c, const T* theta) {   // backward of the
   const int L = (int)f.layers.size();
   int state = L;
   for (int li = 0; li < L; ++li) {   // layer 0 was applied last
+    int slo, shi;
+    segment_of(f, li, &slo, &shi);
+    if (slo >= 0) {
+      const int k = shi - slo + 1;     // li == slo here: the run is entered at its lowest index
+      NF_TRY(ew_segment<T>(f, slo, k, theta, c.n, c.X[state - k], nullptr, nullptr, true, c.G, c.gld, f.d_gsum));
+      state -= k;
+      li = shi;
+      continue;
+    }
     NF_TRY((coupling_backward<T, false>(f, f.layers[li], c.lb[li], theta, c, (const T*)c.X[state - 1], (const T*)c.X[state], state - 1 > 0)));
     --state;
   }
@@ -436,7 +484,7 @@ int sweep_backward_inv(Flow& f, Chunk& c, const T* theta) {   // backward of the
 
 template <typename T>
 int run_typed(Flow& f, const GeneralJob& job) {
-  NF_TRY(check_supported<T>(f));
+  NF_TRY(check_supported<T>(f, job.op));
   const T* theta = (const T*)job.theta_dev;
   const int d = f.dim, L = (int)f.layers.size();
   const int64_t N = job.N;
