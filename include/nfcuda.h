@@ -127,8 +127,8 @@ NF_API int     nf_flow_set_base(nf_flow_t flow, const double* mu, const double* 
  * with `unwhiten!`; logpdf per Distributions).  L: dim x dim ROW-major lower-triangular Cholesky factor with
  * a positive diagonal (Julia: `permutedims(cholesky(Sigma).L)` of the column-major array, or pass `cholesky(Sigma).U`'s
  * memory as is); entries above the diagonal are ignored.  mu may be NULL (zeros).  Sampling, ELBO, log-likelihood, logpdf
- * and rand use it on every flow family, except log-likelihood / logpdf / inverse of purely planar / radial flows
- * (NF_ERR_UNSUPPORTED).  nf_flow_set_base switches back to the diagonal form. */
+ * and rand use it on every flow family (Hamiltonian flows: forward direction only).  nf_flow_set_base switches back to the
+ * diagonal form. */
 NF_API int     nf_flow_set_base_chol(nf_flow_t flow, const double* mu, const double* L);
 /* nf_mma_mode for the coupling MLPs; default NF_MMA_F16X3 for NF_F32 flows, NF_MMA_SIMT for NF_F64. */
 NF_API int     nf_flow_set_mma_mode(nf_flow_t flow, int mode);

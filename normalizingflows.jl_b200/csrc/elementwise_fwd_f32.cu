@@ -2,5 +2,5 @@
 #include "elementwise_impl.cuh"
 namespace nf {
 template int ew_run_dir<float, false>(Flow&, const Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*, bool);
-template int ew_segment<float>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
+template int ew_segment_dir<float, false>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
 }  // namespace nf

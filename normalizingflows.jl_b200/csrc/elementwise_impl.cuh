@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
   const int64_t group = (int64_t)nthr * S;
   const int64_t ngroups = (a.N + group - 1) / group;
   for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
-    T z[S][DP], ld[S];
+    T z[S][DP], ld[S], wl[S];
     bool live[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
 #pragma unroll
       for (int k = 0; k < DP; ++k) z[s][k] = (k < d) ? a.z0[jj * d + k] : T(0);
       ld[s] = 0;
+      wl[s] = live[s] ? (((a.flags & EW_EXT_GRAD) && a.gld) ? a.gld[jj] : T(1)) : T(0);
     }
     // ---- inverse sweep: inverse(f1∘...∘fL) applies f1^{-1} first (theta order) ----
     for (int l = 0; l < L; ++l) {
@@ -657,9 +658,24 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
         if (a.flags & EW_WRITE_LD) a.ld_out[j] = ld[s];
       }
     }
-    if (!(a.flags & EW_TARGET)) continue;     // EW_TARGET here means "log-likelihood head"
-    // ---- head: logpdf(q0, x0) + logdet_inv ;  g = d logq0 / d x0 ----
+    if (a.flags & EW_ADD_LD) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int64_t j = gi * group + (int64_t)s * nthr + tid;
+        if (live[s]) a.ld_out[j] += ld[s];
+      }
+    }
+    if (!(a.flags & (EW_TARGET | EW_EXT_GRAD))) continue;     // EW_TARGET here means "log-likelihood head"
+    // ---- head: logpdf(q0, x0) + logdet_inv ;  g = d logq0 / d x0  (EW_EXT_GRAD: the caller's d/dx instead) ----
     T gz[S][DP];
+    if (a.flags & EW_EXT_GRAD) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int64_t j = gi * group + (int64_t)s * nthr + tid;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) gz[s][k] = (live[s] && k < d) ? a.g_in[j * d + k] : T(0);
+      }
+    } else
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       T q = 0;
@@ -690,7 +706,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
         T g_m = 0, g_b = 0;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          const T w8 = live[s] ? T(1) : T(0);
+          const T w8 = wl[s];
           T dot = b;
 #pragma unroll
           for (int k = 0; k < DP; ++k) dot += e[4 + k] * z[s][k];
@@ -736,7 +752,7 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
         for (int k = 0; k < DP; ++k) gz0[k] = 0;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          const T w8 = live[s] ? T(1) : T(0);
+          const T w8 = wl[s];
           T u[DP], r2 = 0;
 #pragma unroll
           for (int k = 0; k < DP; ++k) { u[k] = (k < d) ? z[s][k] - e[4 + k] : T(0); r2 += u[k] * u[k]; }
@@ -821,6 +837,16 @@ __global__ void __launch_bounds__(128) ew_inv_flow_kernel(EwArgs<T> a) {
           const T v = warp_sum(ge[k]);
           if (lane == 0) acc[k] += v;
         }
+      }
+    }
+    if (a.flags & EW_EXT_GRAD) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int64_t j = gi * group + (int64_t)s * nthr + tid;
+        if (!live[s]) continue;
+#pragma unroll
+        for (int k = 0; k < DP; ++k)
+          if (k < d) a.g_out[j * d + k] = gz[s][k];
       }
     }
   }
@@ -1030,7 +1056,7 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
     // q0 = MvNormal(mu, L L^T): the draws (or the caller's x0) and their log-density come from base_dense_kernel; the fused
     // kernel then sees ready-made x0 and a per-sample log q0
     if (inverse) {
-      set_error("full-covariance base: log-likelihood / inverse of purely elementwise (planar / radial) flows is not implemented");
+      set_error("full-covariance base: the inverse direction of elementwise flows runs on the layered path (internal routing error)");
       return NF_ERR_UNSUPPORTED;
     }
     T* lq0 = (T*)f.ws_alloc((size_t)N * sizeof(T));
@@ -1066,22 +1092,23 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
   return NF_OK;
 }
 
-// A run of elementwise layers [l0, l0 + Lseg) INSIDE a layered (coupling) flow (reference src/flows/utils.jl:23-26: any
+// A run of elementwise layers [l0, l0 + Lseg) INSIDE a layered (coupling) flow, forward direction or (INV) the inverse direction (reference src/flows/utils.jl:23-26: any
 // composition of bijectors is a flow).  forward: Xout = T_seg(Xin), ld += logdet.  backward: recomputes the run from its input
 // state Xin, pulls G (d/dy -> d/dx, in place) and the per-sample logdet weights gld (nullptr = 1) back through it and ADDS the
 // parameter-gradient sums into gsum.
-template <typename T, int DP, int S>
+template <typename T, int DP, int S, bool INV>
 static int ew_segment_launch(Flow& f, int l0, int Lseg, const T* theta_dev, int64_t N, const T* Xin, T* Xout, T* ld, bool backward,
                              T* G, const T* gld, double* gsum) {
   const int d = f.dim;
   constexpr int STR = ew_stride<DP>(), NACC = ew_nacc<DP>();
   const int threads = 128;
-  const size_t smem = ((size_t)Lseg * STR + (size_t)(threads / 32) * Lseg * NACC + (size_t)Lseg * S * threads) * sizeof(T) + (size_t)Lseg * sizeof(int) + 16;
+  const size_t smem = ((size_t)Lseg * STR + (size_t)(threads / 32) * Lseg * NACC + (INV ? 0 : (size_t)Lseg * S * threads)) * sizeof(T) + (size_t)Lseg * sizeof(int) + 16;
   if (smem > 200 * 1024) {
     set_error("a run of %d elementwise layers needs %zu B of shared memory (limit 200 KiB)", Lseg, smem);
     return NF_ERR_UNSUPPORTED;
   }
-  auto kern = ew_flow_kernel<T, DP, S, false>;
+  void (*kern)(EwArgs<T>);
+  if constexpr (INV) kern = ew_inv_flow_kernel<T, DP, S, false>; else kern = ew_flow_kernel<T, DP, S, false>;
   NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t group = (int64_t)threads * S;
   int max_blocks = 0;
@@ -1103,17 +1130,17 @@ static int ew_segment_launch(Flow& f, int l0, int Lseg, const T* theta_dev, int6
   f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
   if (backward) {
-    ew_finalize_kernel<T, DP><<<(Lseg + 63) / 64, 64, 0, f.stream>>>(theta_dev, f.d_ew_meta + l0, Lseg, d, gpart, nullptr, grid, N, f.P, 1, 0, gsum, 1);
+    ew_finalize_kernel<T, DP><<<(Lseg + 63) / 64, 64, 0, f.stream>>>(theta_dev, f.d_ew_meta + l0, Lseg, d, gpart, nullptr, grid, N, f.P, 1, INV ? 1 : 0, gsum, 1);
     NF_LAUNCH_CHECK();
   }
   return NF_OK;
 }
 
-template <typename T>
-int ew_segment(Flow& f, int l0, int Lseg, const void* theta_dev, int64_t N, const void* Xin, void* Xout, void* ld, bool backward,
-               void* G, const void* gld, double* gsum) {
+template <typename T, bool INV>
+int ew_segment_dir(Flow& f, int l0, int Lseg, const void* theta_dev, int64_t N, const void* Xin, void* Xout, void* ld, bool backward,
+                   void* G, const void* gld, double* gsum) {
   const int d = f.dim;
-#define NF_SEG(DPV, SV) return ew_segment_launch<T, DPV, SV>(f, l0, Lseg, (const T*)theta_dev, N, (const T*)Xin, (T*)Xout, (T*)ld, backward, (T*)G, (const T*)gld, gsum)
+#define NF_SEG(DPV, SV) return ew_segment_launch<T, DPV, SV, INV>(f, l0, Lseg, (const T*)theta_dev, N, (const T*)Xin, (T*)Xout, (T*)ld, backward, (T*)G, (const T*)gld, gsum)
   if (d <= 2) NF_SEG(2, 4);
   if (d <= 4) NF_SEG(4, 2);
   if (d <= 8) NF_SEG(8, 1);

@@ -191,12 +191,21 @@ inline int ew_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, 
                  : ew_run_dir<T, false>(f, tgt, theta_dev, N, z0_dev, seed, want_grad, y_out, ld_out, terms_out, gsum_dev, head);
 }
 
-// a run of planar / radial / shift layers inside a layered (coupling) flow: forward (Xout, ld +=) or backward (G in place, gsum +=)
+// a run of planar / radial / shift layers inside a layered (coupling) flow, in the forward or the inverse direction:
+// forward pass (Xout, ld +=) or backward pass (G in place, gsum +=)
+template <typename T, bool INV>
+int ew_segment_dir(Flow& f, int l0, int Lseg, const void* theta_dev, int64_t N, const void* Xin, void* Xout, void* ld, bool backward,
+                   void* G, const void* gld, double* gsum);
+extern template int ew_segment_dir<float, false>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
+extern template int ew_segment_dir<float, true>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
+extern template int ew_segment_dir<double, false>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
+extern template int ew_segment_dir<double, true>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
 template <typename T>
-int ew_segment(Flow& f, int l0, int Lseg, const void* theta_dev, int64_t N, const void* Xin, void* Xout, void* ld, bool backward,
-               void* G, const void* gld, double* gsum);
-extern template int ew_segment<float>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
-extern template int ew_segment<double>(Flow&, int, int, const void*, int64_t, const void*, void*, void*, bool, void*, const void*, double*);
+inline int ew_segment(Flow& f, int l0, int Lseg, const void* theta_dev, int64_t N, const void* Xin, void* Xout, void* ld, bool backward,
+                      void* G, const void* gld, double* gsum, bool inverse = false) {
+  return inverse ? ew_segment_dir<T, true>(f, l0, Lseg, theta_dev, N, Xin, Xout, ld, backward, G, gld, gsum)
+                 : ew_segment_dir<T, false>(f, l0, Lseg, theta_dev, N, Xin, Xout, ld, backward, G, gld, gsum);
+}
 
 // single-launch Adam training loop for small batches of elementwise flows (elementwise.cu: ew_train_kernel)
 template <typename T>

@@ -384,11 +384,6 @@ int check_supported(const Flow& f, int op) {
     set_error("planar / radial layers inside a coupling flow support dim <= 64, got %d", f.dim);
     return NF_ERR_UNSUPPORTED;
   }
-  if (seg && (op == OP_INVERSE || op == OP_LOGLIK)) {
-    set_error("inverse / logpdf / loglikelihood of flows that mix planar / radial layers with coupling layers is not implemented "
-              "(forward, rand and the ELBO objective are)");
-    return NF_ERR_UNSUPPORTED;
-  }
   return NF_OK;
 }
 
@@ -439,6 +434,18 @@ int sweep_inverse(Flow& f, Chunk& c, const T* theta) {
   int state = 0;
   for (int li = 0; li < L; ++li) {
     const LayerDesc& Ld = f.layers[li];
+    int slo, shi;
+    segment_of(f, li, &slo, &shi);
+    if (slo >= 0) {      // li == slo: the inverse of the run applies slo first
+      const int k = shi - slo + 1;
+      const T* Xin = (const T*)c.xin(state);
+      T* Xout = (T*)c.xout(state + k - 1);
+      NF_TRY(ew_segment<T>(f, slo, k, theta, c.n, Xin, Xout, c.ld, false, nullptr, nullptr, nullptr, true));
+      if (!c.xmeta.empty()) NF_TRY(tc_absmax(f, (const float*)Xout, c.n * f.dim, c.xmeta[state + k]));
+      state += k;
+      li = shi;
+      continue;
+    }
     LayerBufs& b = c.stash ? c.lb[li] : c.lb[0];
     const T* Xin = (const T*)c.xin(state);
     T* Xout = (T*)c.xout(state);
@@ -476,6 +483,15 @@ int sweep_backward_inv(Flow& f, Chunk& c, const T* theta) {   // backward of the
   const int L = (int)f.layers.size();
   int state = L;
   for (int li = L - 1; li >= 0; --li) {   // layer L-1's inverse was applied last
+    int slo, shi;
+    segment_of(f, li, &slo, &shi);
+    if (slo >= 0) {      // li == shi
+      const int k = shi - slo + 1;
+      NF_TRY(ew_segment<T>(f, slo, k, theta, c.n, c.X[state - k], nullptr, nullptr, true, c.G, c.gld, f.d_gsum, true));
+      state -= k;
+      li = slo;
+      continue;
+    }
     NF_TRY((coupling_backward<T, true>(f, f.layers[li], c.lb[li], theta, c, (const T*)c.X[state - 1], (const T*)c.X[state], state - 1 > 0)));
     --state;
   }
@@ -612,7 +628,7 @@ int backward_from_stash_typed(Flow& f, const void* gy_host, const void* gld_host
 }  // namespace
 
 int general_plan_workspace(Flow& f, int op, int64_t N, size_t extra_bytes) {
-  if (f.all_elementwise) {
+  if (f.all_elementwise && !(f.base_dense && (op == OP_INVERSE || op == OP_LOGLIK))) {
     f.chunk_N = N;
     return f.ws_reserve(extra_bytes + ((size_t)16 << 20));
   }
@@ -647,7 +663,7 @@ int general_plan_workspace(Flow& f, int op, int64_t N, size_t extra_bytes) {
 }
 
 int general_run(Flow& f, const GeneralJob& job) {
-  if (f.all_elementwise) {
+  if (f.all_elementwise && !(f.base_dense && (job.op == OP_INVERSE || job.op == OP_LOGLIK))) {
     set_error("operation %d is not implemented for purely elementwise (planar/radial) flows in this build", job.op);
     return NF_ERR_UNSUPPORTED;
   }

@@ -318,7 +318,9 @@ struct Job {
 // Runs the job; leaves un-normalised sums in f.d_gsum (gradient sums [0,P), objective sum at [P]).
 static int run_job(Flow& f, const Job& j) {
   NF_REQUIRE(j.N > 0, "N must be positive");
-  if (f.all_elementwise && (j.op == OP_ELBO || j.op == OP_FORWARD || j.op == OP_INVERSE || j.op == OP_LOGLIK)) {
+  // (a full-covariance base in the inverse direction goes through the layered path: the whole flow is one elementwise segment there)
+  const bool dense_inv = f.base_dense && (j.op == OP_INVERSE || j.op == OP_LOGLIK);
+  if (f.all_elementwise && !dense_inv && (j.op == OP_ELBO || j.op == OP_FORWARD || j.op == OP_INVERSE || j.op == OP_LOGLIK)) {
     const bool inv = j.op == OP_INVERSE || j.op == OP_LOGLIK;
     const bool head = j.op == OP_LOGLIK;
     double* gs = (j.op == OP_ELBO || j.op == OP_LOGLIK) ? f.d_gsum : nullptr;

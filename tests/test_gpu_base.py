@@ -75,9 +75,18 @@ def test_dense_base_sampling_moments(gpu):
     assert not np.array_equal(gf.rand_base(16, seed=1), gf.rand_base(16, seed=2))
 
 
-def test_dense_base_unsupported_case_fails_loudly(gpu):
+@pytest.mark.parametrize("kind,dim", [("planar", 5), ("radial", 2)])
+def test_dense_base_elementwise_inverse_direction(gpu, kind, dim):
+    """logpdf / loglikelihood of purely planar / radial flows over a full-covariance base (routed through the layered path)."""
     nf = gpu
-    of, _ = _dense(oracle_flow("planar", 2, np.float32, nlayers=4))
-    gf = gpu_flow(nf, of, np.float32)
-    with pytest.raises(nf.NFCudaError):
-        gf.logpdf(z0(10, 2, np.float32))
+    dtype = np.float64
+    of, _ = _dense(oracle_flow(kind, dim, dtype, nlayers=5))
+    gf = gpu_flow(nf, of, dtype)
+    ys = (0.7 * z0(100, dim, np.float64, seed=3)).astype(dtype)
+    np.testing.assert_allclose(gf.logpdf(ys), of.logpdf(torch.from_numpy(ys)).detach().numpy(), rtol=1e-7, atol=1e-7)
+    v_ref, g_ref = O.loglik_value_and_grad(of, of.theta(), torch.from_numpy(ys))
+    K = nf._capi
+    val = C.c_double()
+    g = np.empty(gf.theta.size, dtype=dtype)
+    K.check(K.lib().nf_loglik_value_and_grad(gf.handle(), K.ptr(gf.theta), 100, K.ptr(ys), 1.0, C.byref(val), K.ptr(g)))
+    assert abs(val.value - v_ref) <= 1e-9 * max(abs(v_ref), 1.0) and rel_err(g, g_ref) <= 1e-7

@@ -36,7 +36,7 @@ def bin_mismatches(of, got, dtype):
                 out.append((li, float("inf")))
                 continue
             knot = kn[n, c, lo]
-            out.append((li, float(abs(np.float64(v[n, c]) - np.float64(knot)) / np.spacing(np.abs(knot).astype(dtype)))))
+            out.append((li, float(abs(np.float64(v[n, c]) - np.float64(knot)) / np.spacing(np.float32(abs(knot))))))
     return out
 
 
@@ -58,8 +58,8 @@ def main(out_path):
                    elbo_rel_gpu_vs_f32oracle=abs(v - v32) / max(abs(v32), 1.0), grad_rel_gpu_vs_f32oracle=rel_err(g, g32))
         if kind == "nsf":
             got = nf.spline_bins(gf, xs)
-            of32.forward(torch.from_numpy(xs))
-            mm = bin_mismatches(of32, got, np.float32)
+            of64.forward(torch.from_numpy(xs).double())
+            mm = bin_mismatches(of64, got, np.float32)
             row.update(bins_total=int(sum(a.size for a in got)), bins_mismatch=len(mm),
                        bins_mismatch_max_ulps=max([u for _, u in mm], default=0.0),
                        bins_mismatch_ulps=sorted(u for _, u in mm))
