@@ -16,6 +16,7 @@ namespace nf {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 extern thread_local int64_t g_launch_count;
+extern int g_opt_fused_variant;    // 1 (default): 128-column MMAs (fused_coupling_w128.cuh); 0: the first, 64-column version
 extern int g_opt_fused_coupling;   // nf_set_option("fused_coupling", .); initialised from NFCUDA_FUSED
 
 #define NF_CUDA(expr)                                                                          \

@@ -137,6 +137,7 @@ struct FusedFwdMaps {
   CUtensorMap w[2][3];      // weight planes, K-major, box {64, 64 | 32, 1}
   CUtensorMap x2;           // stash of the x2 planes: box {64, 128, 1}
   CUtensorMap h[2][2];      // stash of the hidden planes [net][layer]: box {16, 32, 1}, SWIZZLE_32B
+  CUtensorMap w128[2][2];   // wide variant: first / second Dense weight planes with box {64, 128, 1}
 };
 
 struct FusedCfg {
@@ -185,7 +186,9 @@ __device__ __forceinline__ int fused_build_seq(uint8_t* seq, int nch) {
 // (SWIZZLE_32B pattern, conflict-free 16-byte stores) -> one TMA store per plane.  Rows past the batch are clipped by the map.
 __device__ __forceinline__ void fused_stash_store(uint8_t* stg, const CUtensorMap* map, const uint32_t (&hi)[8], const uint32_t (&lo)[8],
                                                   int lane, int col0, int row_base, bool two_planes) {
-  if (lane == 0) tma_store_wait_read();          // the previous stores of this warp have read the tile
+  // one ELECTED lane waits / issues (elect.sync keeps the bulk-tensor instructions on the uniform datapath; a `lane == 0`
+  // branch costs an election loop per instruction)
+  if (elect_one_sync()) tma_store_wait_read();   // the previous stores of this warp have read the tile
   __syncwarp();
   const int sw = (lane >> 2) & 1;
   uint8_t* rowp = stg + lane * 32;
@@ -197,10 +200,11 @@ __device__ __forceinline__ void fused_stash_store(uint8_t* stg, const CUtensorMa
   }
   fence_proxy_async();
   __syncwarp();
-  if (lane == 0) {
+  if (elect_one_sync()) {
     tma_store_3d(map, smem_u32(stg), col0, row_base, 0);
     if (two_planes) tma_store_3d(map, smem_u32(stg) + 1024, col0, row_base, 1);
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(FusedCfg::THREADS, 1)

@@ -12,6 +12,7 @@ namespace nf {
 
 static thread_local std::string g_last_error;
 thread_local int64_t g_launch_count = 0;
+int g_opt_fused_variant = !(getenv("NFCUDA_FUSED_VARIANT") && atoi(getenv("NFCUDA_FUSED_VARIANT")) == 0);
 int g_opt_fused_coupling = !(getenv("NFCUDA_FUSED") && atoi(getenv("NFCUDA_FUSED")) == 0);
 
 void set_error(const char* fmt, ...) {
@@ -951,6 +952,7 @@ int64_t nf_launch_count(int reset) {
 
 int nf_set_option(const char* name, int value) {
   if (name && !strcmp(name, "fused_coupling")) { g_opt_fused_coupling = value; return NF_OK; }
+  if (name && !strcmp(name, "fused_variant")) { g_opt_fused_variant = value; return NF_OK; }
   set_error("nf_set_option: unknown option '%s'", name ? name : "(null)");
   return NF_ERR_INVALID;
 }

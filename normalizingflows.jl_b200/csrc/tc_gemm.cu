@@ -1241,6 +1241,7 @@ int split_into_planes(Flow& f, TcState* st, const float* X, int d, const int* d_
 }
 
 #include "fused_coupling.cuh"
+#include "fused_coupling_w128.cuh"
 
 }  // namespace
 
@@ -1473,6 +1474,7 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
       N.bias[i] = st->bias_pool + dp.bias_off;
       NF_REQUIRE(dp.kin_p == (i == 0 ? 64 : h_ld) && dp.nf_rows >= (i == 2 ? 32 : h_ld), "fused coupling: unexpected weight plane shape");
       NF_TRY(make_map_kmajor(st, st->pool + dp.wf_off, dp.nf_rows, dp.kin_p, (int64_t)dp.nf_rows * dp.kin_p, i == 2 ? 32 : 64, &maps.w[m][i]));
+      if (i < 2) NF_TRY(make_map_kmajor(st, st->pool + dp.wf_off, dp.nf_rows, dp.kin_p, (int64_t)dp.nf_rows * dp.kin_p, 128, &maps.w128[m][i]));
       if (i < 2) {
         Planes O = planes_of(acts[m][i], n, H);
         N.h_planes[i] = O.p;
@@ -1482,15 +1484,17 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
         NF_REQUIRE(N.h_meta[i], "tcgen05 path: out of tensor metadata slots");
       }
     }
-    N.out = (float*)acts[m][2];
+    N.out = m == 0 ? (float*)acts[m][2] : nullptr;      // the backward pass needs s (after tanh) only
   }
   p.dbg_flags = getenv("NFCUDA_DBG_FLAGS") ? atoi(getenv("NFCUDA_DBG_FLAGS")) : 0;
   p.rz[0] = rz_compensation(cbar, 1, 1);
   p.rz[1] = rz_compensation(H, h_ld / 64, 1);
   p.rz[2] = rz_compensation(H, h_ld / 64, 1);
+  const bool wide = g_opt_fused_variant != 0;
   static bool attr_set[64] = {};
   if (!attr_set[f.device & 63]) {
     NF_CUDA(cudaFuncSetAttribute(fused_affine_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::SMEM));
+    NF_CUDA(cudaFuncSetAttribute(fused_affine_fwd_w128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Cfg::SMEM));
     attr_set[f.device & 63] = true;
   }
   const int64_t tiles = ceil_div(n, 128);
@@ -1503,7 +1507,8 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
     p.dbg = d_dbg;
   }
   f.prof.begin("fused_affine_fwd", f.stream);
-  fused_affine_fwd_kernel<<<grid, FusedCfg::THREADS, FusedCfg::SMEM, f.stream>>>(maps, p);
+  if (wide) fused_affine_fwd_w128_kernel<<<grid, F2Cfg::THREADS, F2Cfg::SMEM, f.stream>>>(maps, p);
+  else fused_affine_fwd_kernel<<<grid, FusedCfg::THREADS, FusedCfg::SMEM, f.stream>>>(maps, p);
   f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
   if (d_dbg) {
@@ -1514,6 +1519,12 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
     long long t0 = 0;
     for (auto v : h) if (v && (!t0 || v < t0)) t0 = v;
     fprintf(stderr, "[nfcuda dbg] fused_fwd grid %u tiles %lld: clock64 relative to the first event (CTA 0)\n", grid, (long long)tiles);
+    if (wide) {     // tagged event list of epilogue thread 0: (tag, cycles since the previous event)
+      long long prev = h[512];
+      fprintf(stderr, "  events:");
+      for (int i = 0; i < 511 && h[512 + i]; ++i) { fprintf(stderr, " %lld:+%lld", h[1024 + i], h[512 + i] - prev); prev = h[512 + i]; }
+      fprintf(stderr, "\n");
+    } else
     for (int r = 0; r < 3; ++r) {
       fprintf(stderr, "  role %d:", r);
       for (int i = 0; i < 512; ++i) { if (i % 4 == 0) fprintf(stderr, " |"); fprintf(stderr, " %lld", h[r * 512 + i] ? h[r * 512 + i] - t0 : -1); }

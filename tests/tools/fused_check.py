@@ -25,6 +25,10 @@ def set_fused(on):
     nf._capi.check(lib.nf_set_option(b"fused_coupling", int(on)))
 
 
+if "--narrow" in sys.argv:
+    nf._capi.check(lib.nf_set_option(b"fused_variant", 0))
+
+
 def case(dim, hd, N, nlayers=1, tname="funnel"):
     of32 = oracle_flow("realnvp", dim, np.float32, hdims=hd, nlayers=nlayers)
     of64 = oracle_flow("realnvp", dim, np.float64, hdims=hd, nlayers=nlayers)
