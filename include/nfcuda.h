@@ -143,6 +143,10 @@ NF_API int  nf_target_create(nf_target_t* out, int kind, int dim, const double* 
  * dimension 2 * dim(inner).  `inner` is copied. */
 NF_API int  nf_target_create_joint(nf_target_t* out, nf_target_t inner);
 NF_API void nf_target_destroy(nf_target_t target);
+/* log-density and score of a device target at host-supplied points (x: [N][dim] of dtype; logp_out: [N]; score_out: [N][dim]
+ * or NULL).  A host can check with it that the `logp` closure it was handed IS the device target it named (the Julia shim
+ * does, before training), and tests pin the targets against the reference formulas (example/targets/*.jl). */
+NF_API int nf_target_logp(nf_target_t target, int dtype, const void* x_host, int64_t N, void* logp_host_out, void* score_host_out);
 
 /* ---- objectives: value and gradient ---------------------------------------------------------- */
 /* Replaces _value_and_gradient(loss, prep, ad, theta, rng, logp, n) for vo = elbo / elbo_batch

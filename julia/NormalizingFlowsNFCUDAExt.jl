@@ -13,6 +13,7 @@ module NormalizingFlowsNFCUDAExt
 
 using NormalizingFlows
 using NormalizingFlows: Bijectors, Distributions, Optimisers, ADTypes, Random
+using LinearAlgebra: cholesky, Symmetric, isdiag, diag
 import NormalizingFlows: _prepare_gradient, _value_and_gradient, _device_specific_rand
 
 const libnfcuda = get(ENV, "NFCUDA_LIB", "libnfcuda")
@@ -40,7 +41,13 @@ end
 
 # ---- the ADTypes backend tag -------------------------------------------------------------------------
 """
-    AutoNFCUDA(; device = 0, target)
+    AutoNFCUDA(; device = 0, devices = nothing, target, verify_logp = true)
+
+`devices = 0:7` runs every objective evaluation data-parallel on those GPUs from this one Julia process (`nf_comm_init_all`,
+one flow / target replica per device, `nf_elbo_value_and_grad_multi`: samples sharded, ONE ncclAllReduce of the P+1 sums
+inside libnfcuda); `device` is the single-GPU form.  With `verify_logp` (default) the `logp` closure handed to `train_flow`
+is evaluated at a few points and compared with the device target named by `target` -- a mismatch is an error, not a silent
+wrong density.
 
 `target` names a device-side log-density: `(:banana, b, var)`, `(:funnel, μ, σ)`, `(:warped_gauss, σ1, σ2)`,
 `(:cross, μ, σ)`, `(:diag_normal, μ, σ)`, `(:logreg, σ₀, n, X, y)`; `(:joint, kind, params...)` wraps any of them with N(0, I) momenta.  The Julia `logp` closure handed to `train_flow` is used only
@@ -48,10 +55,13 @@ to recognise the example targets; an arbitrary closure cannot cross the C ABI (u
 `nf_backward` with CUDA.jl evaluating logp and its score on the device buffer).
 """
 struct AutoNFCUDA <: ADTypes.AbstractADType
-    device::Int
+    devices::Vector{Int}
     target::Tuple
+    verify_logp::Bool
 end
-AutoNFCUDA(; device=0, target) = AutoNFCUDA(device, target)
+AutoNFCUDA(; device=0, devices=nothing, target, verify_logp=true) =
+    AutoNFCUDA(devices === nothing ? [device] : collect(Int, devices), target, verify_logp)
+AutoNFCUDA(device::Int, target::Tuple) = AutoNFCUDA([device], target, false)
 export AutoNFCUDA
 
 # ---- flow structure -> nf_layer_desc[] in theta (= Ls) order ------------------------------------------
@@ -103,17 +113,38 @@ function describe(layer, keep::Vector{Any}; score_target::Ptr{Cvoid}=C_NULL)
 end
 
 mutable struct Prep
-    flow::Ptr{Cvoid}
+    flow::Ptr{Cvoid}             # replica on the first device (single-GPU calls use it)
     target::Ptr{Cvoid}
     P::Int
     T::DataType
+    comm::Ptr{Cvoid}             # nf_comm_t over ad.devices (C_NULL for one device)
+    flows::Vector{Ptr{Cvoid}}    # one replica per device, in communicator order
+    targets::Vector{Ptr{Cvoid}}
+    verified::Bool
 end
 
 target_kind(s::Symbol) = Dict(:banana => 1, :funnel => 2, :warped_gauss => 3, :cross => 4, :diag_normal => 5, :logreg => 6)[s]
 # (:logreg, σ₀, n, vec(X'), y): X' is the n×dim design matrix flattened row by row, i.e. vec of the dim×n Julia matrix
 
 function make_prep(flow::Bijectors.TransformedDistribution, ad::AutoNFCUDA, ::Type{T}) where {T}
-    check(ccall((:nf_init, libnfcuda), Cint, (Cint,), ad.device))
+    reps = [make_replica(flow, ad, T, dev) for dev in ad.devices]
+    comm = Ref{Ptr{Cvoid}}(C_NULL)
+    if length(ad.devices) > 1
+        check(ccall((:nf_comm_init_all, libnfcuda), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}), comm, length(ad.devices), Cint.(ad.devices)))
+    end
+    P = ccall((:nf_flow_num_params, libnfcuda), Int64, (Ptr{Cvoid},), reps[1][1])
+    prep = Prep(reps[1][1], reps[1][2], P, T, comm[], first.(reps), last.(reps), false)
+    finalizer(prep) do p
+        p.comm == C_NULL || ccall((:nf_comm_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), p.comm)
+        foreach(h -> ccall((:nf_flow_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), h), p.flows)
+        foreach(h -> ccall((:nf_target_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), h), p.targets)
+    end
+    return prep
+end
+
+# one (flow, target) replica on device `dev`
+function make_replica(flow::Bijectors.TransformedDistribution, ad::AutoNFCUDA, ::Type{T}, dev::Int) where {T}
+    check(ccall((:nf_init, libnfcuda), Cint, (Cint,), dev))
     keep = Any[]
     layers, base = unwrap(flow)
     d = length(base)
@@ -134,16 +165,33 @@ function make_prep(flow::Bijectors.TransformedDistribution, ad::AutoNFCUDA, ::Ty
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep descs check(ccall((:nf_flow_create, libnfcuda), Cint,
         (Ref{Ptr{Cvoid}}, Ptr{NFLayerDesc}, Cint, Cint, Cint), h, descs, length(descs), d, T === Float32 ? NF_F32 : NF_F64))
-    μ = Float64.(Distributions.mean(base)); σ = Float64.(sqrt.(Distributions.var(base)))   # diagonal q₀
-    check(ccall((:nf_flow_set_base, libnfcuda), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h[], μ, σ))
-    joint && ccall((:nf_target_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), inner)   # both users hold copies
-    P = ccall((:nf_flow_num_params, libnfcuda), Int64, (Ptr{Cvoid},), h[])
-    prep = Prep(h[], t[], P, T)
-    finalizer(prep) do p
-        ccall((:nf_flow_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), p.flow)
-        ccall((:nf_target_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), p.target)
+    μ = Float64.(Distributions.mean(base))
+    Σ = Matrix{Float64}(Distributions.cov(base))
+    if isdiag(Σ)
+        σ = sqrt.(diag(Σ))
+        check(ccall((:nf_flow_set_base, libnfcuda), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h[], μ, σ))
+    else
+        # full covariance (ext/NormalizingFlowsCUDAExt.jl:43-47): the column-major memory of U = L' IS the row-major L
+        U = Matrix{Float64}(cholesky(Symmetric(Σ)).U)
+        check(ccall((:nf_flow_set_base_chol, libnfcuda), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), h[], μ, U))
     end
-    return prep
+    joint && ccall((:nf_target_destroy, libnfcuda), Cvoid, (Ptr{Cvoid},), inner)   # both users hold copies
+    return (h[], t[])
+end
+
+# The Julia `logp` argument cannot cross the C ABI; what runs is the device target named in `ad.target`.  Before the first
+# evaluation, compare the two at a few points (device side: nf_target_logp) and refuse to train against a different density.
+function verify_logp!(prep::Prep, ad::AutoNFCUDA, logp, d::Int)
+    (prep.verified || !ad.verify_logp || ad.target[1] === :joint) && return
+    rng = Random.Xoshiro(0x5eed)
+    xs = 0.7 .* randn(rng, Float64, d, 8)
+    ref = [logp(xs[:, j]) for j in 1:8]
+    dev = Vector{Float64}(undef, 8)
+    check(ccall((:nf_target_logp, libnfcuda), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cvoid}),
+        prep.target, NF_F64, xs, 8, dev, C_NULL))
+    all(isapprox.(ref, dev; rtol=1e-8, atol=1e-8)) ||
+        error("NFCUDA: the `logp` passed to train_flow is not the device target $(ad.target) (logp = $ref, device = $dev)")
+    prep.verified = true
 end
 
 # `loss` is the closure of src/NormalizingFlows.jl:69: loss(θ, rng, args...) = -vo(rng, re(θ), args...)
@@ -161,7 +209,15 @@ function _value_and_gradient(loss, prep::Prep, ad::AutoNFCUDA, θ::AbstractVecto
     vo = loss.vo
     if vo === NormalizingFlows.elbo || vo === NormalizingFlows.elbo_batch
         logp, n_or_xs = args
-        if n_or_xs isa Integer                  # elbo([rng,] flow, logp, n): draws on the device (Philox)
+        verify_logp!(prep, ad, logp, ccall((:nf_flow_dim, libnfcuda), Cint, (Ptr{Cvoid},), prep.flow))
+        if prep.comm != C_NULL                  # data parallel over ad.devices: shards + all-reduce inside libnfcuda
+            N = n_or_xs isa Integer ? n_or_xs : size(n_or_xs, 2)
+            xs = n_or_xs isa Integer ? Ptr{T}(C_NULL) : Matrix{T}(n_or_xs)
+            seed = n_or_xs isa Integer ? rand(rng, UInt64) : UInt64(0)
+            GC.@preserve xs check(ccall((:nf_elbo_value_and_grad_multi, libnfcuda), Cint,
+                (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{T}, Int64, Ptr{T}, UInt64, Cdouble, Ref{Cdouble}, Ptr{T}),
+                prep.comm, prep.flows, prep.targets, θ, N, xs isa Ptr ? xs : pointer(xs), seed, -1.0, val, g))
+        elseif n_or_xs isa Integer              # elbo([rng,] flow, logp, n): draws on the device (Philox)
             seed = rand(rng, UInt64)
             check(ccall((:nf_elbo_value_and_grad, libnfcuda), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{T}, Int64, Ptr{T}, UInt64, Cdouble, Ref{Cdouble}, Ptr{T}),
@@ -172,6 +228,11 @@ function _value_and_gradient(loss, prep::Prep, ad::AutoNFCUDA, θ::AbstractVecto
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{T}, Int64, Ptr{T}, UInt64, Cdouble, Ref{Cdouble}, Ptr{T}),
                 prep.flow, prep.target, θ, size(xs, 2), xs, 0, -1.0, val, g))
         end
+    elseif vo === NormalizingFlows.loglikelihood && prep.comm != C_NULL
+        xs = Matrix{T}(args[1])
+        check(ccall((:nf_loglik_value_and_grad_multi, libnfcuda), Cint,
+            (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{T}, Int64, Ptr{T}, Cdouble, Ref{Cdouble}, Ptr{T}),
+            prep.comm, prep.flows, θ, size(xs, 2), xs, -1.0, val, g))
     elseif vo === NormalizingFlows.loglikelihood
         xs = Matrix{T}(args[1])
         check(ccall((:nf_loglik_value_and_grad, libnfcuda), Cint,

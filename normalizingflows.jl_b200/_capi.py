@@ -48,6 +48,7 @@ SIGNATURES = {
     "nf_target_create": (_i, [C.POINTER(_vp), _i, _i, C.POINTER(_d), _i]),
     "nf_target_create_joint": (_i, [C.POINTER(_vp), _vp]),
     "nf_target_destroy": (None, [_vp]),
+    "nf_target_logp": (_i, [_vp, _i, _vp, _i64, _vp, _vp]),
     "nf_elbo_value_and_grad": (_i, [_vp, _vp, _vp, _i64, _vp, _u64, _d, C.POINTER(_d), _vp]),
     "nf_elbo_value_and_grad_dev": (_i, [_vp, _vp, _vp, _i64, _vp, _u64, _d, C.POINTER(_d), _vp]),
     "nf_elbo_sums_dev": (_i, [_vp, _vp, _vp, _i64, _vp, _u64, _vp]),

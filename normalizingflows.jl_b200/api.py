@@ -82,6 +82,15 @@ class _Target:
             self._h = h
         return self._h
 
+    def logp(self, xs, paramtype=np.float64, with_score=False):
+        """log-density (and score) of the device target at the rows of xs -- `logpdf(target, x)` of reference example/targets/*.jl."""
+        xs = np.ascontiguousarray(np.atleast_2d(xs), dtype=paramtype)
+        lp = np.empty(xs.shape[0], dtype=paramtype)
+        sc = np.empty_like(xs) if with_score else None
+        K.check(K.lib().nf_target_logp(self.handle(), K.NF_F64 if paramtype == np.float64 else K.NF_F32, K.ptr(xs), xs.shape[0],
+                                       K.ptr(lp), K.ptr(sc)))
+        return (lp, sc) if with_score else lp
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and K is not None and getattr(K, "_lib", None) is not None:   # K is None during interpreter shutdown

@@ -44,6 +44,14 @@ int Flow::ws_reserve(size_t bytes) {
 }
 
 template <typename T>
+__global__ void target_logp_kernel(TargetParams<T> tp, const T* __restrict__ X, int64_t N, T* __restrict__ lp, T* __restrict__ G) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const int d = tp.joint ? 2 * tp.dim : tp.dim;
+  lp[r] = target_logp_score<T, 0>(tp, X + r * d, G + r * d);
+}
+
+template <typename T>
 __global__ void scale_out_kernel(const double* __restrict__ gsum, int64_t n, double factor, T* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (T)(gsum[i] * factor);
@@ -621,6 +629,33 @@ int nf_target_create_joint(nf_target_t* out, nf_target_t inner) {
   t->dim = 2 * in->dim;
   *out = reinterpret_cast<nf_target_t>(t.release());
   return NF_OK;
+}
+
+int nf_target_logp(nf_target_t target, int dtype, const void* x_host, int64_t N, void* logp_host_out, void* score_host_out) {
+  const Target* t = reinterpret_cast<const Target*>(target);
+  NF_REQUIRE(t && x_host && logp_host_out && N > 0, "nf_target_logp: null argument / N must be positive");
+  NF_REQUIRE(dtype == NF_F32 || dtype == NF_F64, "dtype must be NF_F32 or NF_F64");
+  NF_REQUIRE(!t->joint, "nf_target_logp: joint [x, rho] targets are evaluated through their inner target");
+  NF_TRY(check_device());
+  const size_t es = dtype == NF_F64 ? 8 : 4;
+  const int d = t->dim;
+  void *dx = nullptr, *dl = nullptr, *dg = nullptr;
+  auto body = [&]() -> int {
+    NF_CUDA(cudaMalloc(&dx, (size_t)N * d * es));
+    NF_CUDA(cudaMalloc(&dl, (size_t)N * es));
+    NF_CUDA(cudaMalloc(&dg, (size_t)N * d * es));
+    NF_CUDA(cudaMemcpy(dx, x_host, (size_t)N * d * es, cudaMemcpyHostToDevice));
+    NF_CUDA(cudaMemset(dg, 0, (size_t)N * d * es));
+    if (dtype == NF_F32) target_logp_kernel<float><<<(unsigned)ceil_div(N, 128), 128>>>(t->params<float>(), (const float*)dx, N, (float*)dl, (float*)dg);
+    else target_logp_kernel<double><<<(unsigned)ceil_div(N, 128), 128>>>(t->params<double>(), (const double*)dx, N, (double*)dl, (double*)dg);
+    NF_LAUNCH_CHECK();
+    NF_CUDA(cudaMemcpy(logp_host_out, dl, (size_t)N * es, cudaMemcpyDeviceToHost));
+    if (score_host_out) NF_CUDA(cudaMemcpy(score_host_out, dg, (size_t)N * d * es, cudaMemcpyDeviceToHost));
+    return NF_OK;
+  };
+  const int s = body();
+  cudaFree(dx); cudaFree(dl); cudaFree(dg);
+  return s;
 }
 
 void nf_target_destroy(nf_target_t target) {

@@ -162,3 +162,23 @@ def test_train_flow_on_device_converges(gpu):
     assert len(stats) == 3000 and stats[0]["iteration"] == 1 and "gradient_norm" in stats[-1]
     assert np.all(np.abs(theta[:2] - mu) < 0.2) and np.all(np.abs(theta[2:] - 2) < 0.2)
     assert stats[-1]["loss"] < stats[0]["loss"]
+
+
+@pytest.mark.parametrize("tname,dim", [("banana", 2), ("funnel", 64), ("warped", 2), ("cross", 16), ("diag", 5)])
+def test_device_targets_match_reference_formulas(gpu, tname, dim):
+    import torch
+    from helpers import gpu_target, oracle_target, z0
+    """nf_target_logp: the device log-densities and scores equal the restated reference formulas (example/targets/*.jl) --
+    the check the Julia shim runs against the `logp` closure it is handed before it trusts a named target."""
+    nf = gpu
+    ot = oracle_target(tname, dim)
+    gt = gpu_target(nf, ot)
+    xs = 0.8 * z0(64, dim, np.float64, seed=12)
+    x = torch.from_numpy(xs).requires_grad_(True)
+    lp_ref = ot.logp(x)
+    sc_ref, = torch.autograd.grad(lp_ref.sum(), x)
+    lp, sc = gt.logp(xs, np.float64, with_score=True)
+    np.testing.assert_allclose(lp, lp_ref.detach().numpy(), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(sc, sc_ref.numpy(), rtol=1e-8, atol=1e-9)
+    lp32 = gt.logp(xs.astype(np.float32), np.float32)
+    np.testing.assert_allclose(lp32, lp_ref.detach().numpy(), rtol=2e-5, atol=2e-5)
