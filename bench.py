@@ -570,6 +570,18 @@ def main():
                 side["c4"] = side_c4(nf, K, lib, torch)
             except Exception as e:   # noqa: a side block must not take the headline line down
                 side["c4"] = {"error": str(e)}
+            try:
+                # the chunked fallback: same step with the workspace capped at 12 GB (the stash of 2^20 draws needs ~46 GB),
+                # so the library walks the batch in sample chunks (forward + backward per chunk)
+                K.check(lib.nf_flow_set_workspace_limit(h, 12 << 30))
+                for _ in range(2):
+                    step_resident()
+                dtc, dmc, _, _ = timed(step_resident, 3)
+                side["chunked_workspace_12GB"] = {"value": n_total * 3 / dtc, "unit": "samples/s", "ms_per_step": 1e3 * dtc / 3,
+                                                  "device_ms_per_step": dmc / 3, "steps": 3}
+                K.check(lib.nf_flow_set_workspace_limit(h, 64 << 30))
+            except Exception as e:   # noqa
+                side["chunked_workspace_12GB"] = {"error": str(e)}
 
     if rank == 0:
         out = {

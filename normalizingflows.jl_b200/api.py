@@ -441,7 +441,7 @@ class Flow:
         K.check(K.lib().nf_logpdf(self.handle(), K.ptr(self.theta), ys.shape[0], K.ptr(ys), K.ptr(out)))
         return out
 
-    def rand(self, n: int, seed: int = 0, out=None):
+    def rand(self, n: int, seed: Optional[int] = None, out=None):
         """rand(flow, n): device Philox base draws pushed through the flow in one batched pass.  `out`: optional preallocated
         [n, dim] array (a fresh pageable array per call costs more in page faults than the flow itself at n = 2^20)."""
         if out is None:
@@ -450,12 +450,16 @@ class Flow:
             raise ValueError("out must be a contiguous %s array of shape (%d, %d)" % (np.dtype(self.paramtype).name, n, self.dim))
         else:
             ys = out
+        if seed is None:                      # fresh draws per call, like rand(flow, n) advancing the RNG; pass a seed to reproduce
+            seed = int(_RNG.integers(0, 2 ** 63))
         K.check(K.lib().nf_sample(self.handle(), K.ptr(self.theta), n, seed, K.ptr(ys)))
         return ys
 
-    def rand_base(self, n: int, seed: int = 0):
+    def rand_base(self, n: int, seed: Optional[int] = None):
         """_device_specific_rand(rng, flow.dist, n) -- reference src/NormalizingFlows.jl:109-115."""
         zs = np.empty((n, self.dim), dtype=self.paramtype)
+        if seed is None:
+            seed = int(_RNG.integers(0, 2 ** 63))
         K.check(K.lib().nf_base_sample(self.handle(), n, seed, K.ptr(zs)))
         return zs
 

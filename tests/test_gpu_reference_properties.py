@@ -182,3 +182,14 @@ def test_device_targets_match_reference_formulas(gpu, tname, dim):
     np.testing.assert_allclose(sc, sc_ref.numpy(), rtol=1e-8, atol=1e-9)
     lp32 = gt.logp(xs.astype(np.float32), np.float32)
     np.testing.assert_allclose(lp32, lp_ref.detach().numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_rand_advances_the_rng(gpu):
+    """rand(flow, n) draws a fresh batch per call (the reference advances its RNG); an explicit seed reproduces."""
+    nf = gpu
+    nf.seed(5)
+    flow = nf.planarflow(nf.MvNormal(np.zeros(2)), 3, np.float32)
+    a, b = flow.rand(64), flow.rand(64)
+    assert not np.array_equal(a, b)
+    assert np.array_equal(flow.rand(64, seed=9), flow.rand(64, seed=9))
+    assert not np.array_equal(flow.rand_base(64), flow.rand_base(64))
