@@ -58,24 +58,6 @@ __device__ __forceinline__ int f2_build_seq(uint8_t* seq, int nck, int nks) {
   return n;
 }
 
-__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr_a, uint32_t taddr_b, uint32_t (&va)[16], uint32_t (&vb)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(va[0]), "=r"(va[1]), "=r"(va[2]), "=r"(va[3]), "=r"(va[4]), "=r"(va[5]), "=r"(va[6]), "=r"(va[7]),
-        "=r"(va[8]), "=r"(va[9]), "=r"(va[10]), "=r"(va[11]), "=r"(va[12]), "=r"(va[13]), "=r"(va[14]), "=r"(va[15])
-      : "r"(taddr_a)
-      : "memory");
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(vb[0]), "=r"(vb[1]), "=r"(vb[2]), "=r"(vb[3]), "=r"(vb[4]), "=r"(vb[5]), "=r"(vb[6]), "=r"(vb[7]),
-        "=r"(vb[8]), "=r"(vb[9]), "=r"(vb[10]), "=r"(vb[11]), "=r"(vb[12]), "=r"(vb[13]), "=r"(vb[14]), "=r"(vb[15])
-      : "r"(taddr_b)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // bias + leakyrelu + sign bits + hi/lo split of 16 scaled pre-activations
 __device__ __forceinline__ uint32_t f2_act_split(const float (&acc)[16], float ds, const float* __restrict__ bias, uint32_t (&hi)[8],
                                                  uint32_t (&lo)[8]) {
@@ -517,9 +499,9 @@ fused_affine_fwd_w128_kernel(const __grid_constant__ FusedFwdMaps maps, const Fu
         float2 xv[8];
         float ldv = 0.f;
         if (t < rows_here && p.ld) ldv = p.ld[row0 + t];
-#pragma unroll
         const float* xrow0 = p.Xin + row0 * d;
         float* yrow0 = p.Xout + row0 * d;
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int idx = t + 512 * i;
           const int r = reg_idx ? r0i + i * rstep : idx / dh, jp = reg_idx ? jp0 : idx - (idx / dh) * dh;
@@ -575,6 +557,9 @@ fused_affine_fwd_w128_kernel(const __grid_constant__ FusedFwdMaps maps, const Fu
       run_max = warp_max(run_max);
       if (lane == 0) meta_amax(p.y_meta, run_max);
     }
+    // every thread that issued bulk stores (stash pieces, sign bits) waits for them before the CTA's shared memory goes away
+    __syncwarp();
+    if (elect_one_sync()) tma_store_wait_all();
     if (t == 0) tma_store_wait_all();
   }
   tc_fence_before();

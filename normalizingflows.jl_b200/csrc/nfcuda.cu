@@ -12,7 +12,8 @@ namespace nf {
 
 static thread_local std::string g_last_error;
 thread_local int64_t g_launch_count = 0;
-int g_opt_fused_variant = !(getenv("NFCUDA_FUSED_VARIANT") && atoi(getenv("NFCUDA_FUSED_VARIANT")) == 0);
+// 0: two-team streaming kernel (fused_coupling.cuh, default), 1: 128-column-MMA kernel (fused_coupling_w128.cuh)
+int g_opt_fused_variant = getenv("NFCUDA_FUSED_VARIANT") ? atoi(getenv("NFCUDA_FUSED_VARIANT")) : 0;
 int g_opt_fused_coupling = !(getenv("NFCUDA_FUSED") && atoi(getenv("NFCUDA_FUSED")) == 0);
 
 void set_error(const char* fmt, ...) {

@@ -25,8 +25,10 @@ def set_fused(on):
     nf._capi.check(lib.nf_set_option(b"fused_coupling", int(on)))
 
 
-if "--narrow" in sys.argv:
+if "--narrow" in sys.argv:      # two-team streaming kernel (the default)
     nf._capi.check(lib.nf_set_option(b"fused_variant", 0))
+if "--wide" in sys.argv:        # 128-column-MMA kernel
+    nf._capi.check(lib.nf_set_option(b"fused_variant", 1))
 
 
 def case(dim, hd, N, nlayers=1, tname="funnel"):
