@@ -182,8 +182,8 @@ struct FusedCfg {
   // staging of the hidden-activation stash: 16 warps x {hi, lo} x [32 rows x 64 B] (SWIZZLE_64B), left by TMA stores
   static constexpr int OFF_STG = (OFF_T + 128 * ST_LD * 4 + 1023) / 1024 * 1024;
   static constexpr int OFF_BIAS = OFF_STG + 16 * 4096;             // [2 nets][256 + 256 + 32] floats
-  static constexpr int OFF_LD = OFF_BIAS + 2 * 544 * 4;           // [128] floats
-  static constexpr int OFF_BAR = OFF_LD + 512;
+  static constexpr int OFF_LD = OFF_BIAS + 2 * 544 * 4;           // [4 column groups][128 rows] partial logdets (summed in a fixed order)
+  static constexpr int OFF_BAR = OFF_LD + 2048;
   static constexpr int N_BARS = 2 * STAGES + 2 /*x full/empty*/ + 2 /*x2 ready/free*/ + 4 /*tfull/tempty*/ + 4 /*tfull3/tempty3*/ +
                                 4 /*h1 ready*/ + 2 /*h2 ready/free*/ + 2 /*s,t staging ready/free*/;
   static constexpr int OFF_POS = OFF_BAR + 8 * N_BARS + 16;   // pos[64], pos2[64]
@@ -389,7 +389,6 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
     const int t = threadIdx.x - C::EPI0;
     // zero the x2 planes once (padding columns stay zero), the logdet staging, and fetch the biases
     for (int i = t; i < 2 * C::X2_PLANE / 16; i += 512) reinterpret_cast<uint4*>(smem_raw + C::OFF_X2)[i] = make_uint4(0, 0, 0, 0);
-    if (t < 128) s_ld[t] = 0.f;
     if (t < p.d) { s_pos[t] = p.pos[t]; s_pos2[t] = p.pos2[t]; }
     for (int i = t; i < 2 * 544; i += 512) {
       const int nt = i / 544, o = i % 544;
@@ -690,9 +689,9 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
         }
       }
       if (tx == 0) NF_FDBG(3, 8 * tc + 7);
-      for (int r = tx; r < 128; r += 64) {
-        if (r < rows_here && p.ld) p.ld[row0 + r] += p.inv ? -s_ld[r] : s_ld[r];
-        s_ld[r] = 0.f;
+      for (int r = tx; r < rows_here; r += 64) {
+        const float sum_s = (s_ld[r] + s_ld[128 + r]) + (s_ld[256 + r] + s_ld[384 + r]);
+        if (p.ld) p.ld[row0 + r] += p.inv ? -sum_s : sum_s;
       }
       epi_bar_sync(3, 64);
       if (tx == 0) mbar_arrive(st_free);             // the staging tiles may take the next tile's outputs
@@ -816,7 +815,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
         // the tile warps get exp(+-s) (their pass is then one FMA per element); s itself goes straight to the stash
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) s_S[rloc * C::ST_LD + g * 8 + q8] = expf(p.inv ? -a[q8] : a[q8]);
-        atomicAdd(&s_ld[rloc], part);
+        s_ld[g * 128 + rloc] = part;
       } else {
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) s_T[rloc * C::ST_LD + g * 8 + q8] = a[q8];
