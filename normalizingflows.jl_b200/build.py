@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnfcuda.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["elementwise_fwd_f32.cu", "elementwise_fwd_f64.cu", "elementwise_inv_f32.cu", "elementwise_inv_f64.cu",
-           "elementwise_train_f32.cu", "elementwise_train_f64.cu", "tc_gemm.cu", "general.cu", "nfcuda.cu"]
+           "elementwise_train_f32.cu", "elementwise_train_f64.cu", "tc_gemm.cu", "general.cu", "hmc_warp.cu", "nfcuda.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -1165,12 +1165,18 @@ int ew_run_dir(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, con
   if (ld_out) flags |= EW_WRITE_LD;
   if (terms_out) flags |= EW_WRITE_TERMS;
   const int d = f.dim;
-  if ((f.hamiltonian || (tgt && tgt->joint)) && (d & (d - 1)) != 0) {
-    set_error("Hamiltonian flows / joint targets need dim a power of two, got %d", d);
-    return NF_ERR_UNSUPPORTED;
-  }
   // the logistic-regression target (as the objective's target or as the LeapFrog score) gets its own instantiations
   const bool lr = (tgt && tgt->kind == NF_TARGET_LOGREG) || (f.score_target && f.score_target->kind == NF_TARGET_LOGREG);
+  // Hamiltonian flows whose state does not fit one thread's registers (BASELINE config 5: 100-D posterior): a warp per sample
+  if (hmc_warp_qualifies(f, INV ? nullptr : tgt) && (g_opt_hmc_warp || d > 64 || (lr && d > 16) || (d & (d - 1)) != 0)) {
+    if constexpr (INV) return hmc_warp_inverse<T>(f, theta_dev, N, z0_dev, head, want_grad, y_out, ld_out, terms_out, gsum_dev);
+    else return hmc_warp_run<T>(f, tgt, theta_dev, N, z0_dev, seed, want_grad, y_out, ld_out, terms_out, gsum_dev);
+  }
+  if ((f.hamiltonian || (tgt && tgt->joint)) && (d & (d - 1)) != 0) {
+    set_error("Hamiltonian flows / joint targets need dim a power of two on this path (inverse direction, or layers / targets the "
+              "warp-per-sample kernel does not cover), got %d", d);
+    return NF_ERR_UNSUPPORTED;
+  }
   if (lr && d > 16) {
     set_error("elementwise flows on the logistic-regression target support dim <= 16, got %d", d);
     return NF_ERR_UNSUPPORTED;

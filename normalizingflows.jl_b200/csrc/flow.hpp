@@ -175,6 +175,20 @@ struct Target {
   }
 };
 
+// hmc_warp.cu: warp-per-sample Hamiltonian flows (dim = 2h, h <= 128; forward direction)
+bool hmc_warp_qualifies(const Flow& f, const struct Target* tgt);
+template <typename T>
+int hmc_warp_run(Flow& f, const struct Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed, bool want_grad,
+                 void* y_out, void* ld_out, void* terms_out, double* gsum_dev);
+template <typename T>
+int hmc_warp_inverse(Flow& f, const void* theta_dev, int64_t N, const void* y_dev, bool head, bool want_grad, void* x_out, void* ld_out,
+                     void* terms_out, double* gsum_dev);
+extern template int hmc_warp_inverse<float>(Flow&, const void*, int64_t, const void*, bool, bool, void*, void*, void*, double*);
+extern template int hmc_warp_inverse<double>(Flow&, const void*, int64_t, const void*, bool, bool, void*, void*, void*, double*);
+extern int g_opt_hmc_warp;      // nf_set_option("hmc_warp", 1): route every qualifying Hamiltonian flow through hmc_warp.cu (tests)
+extern template int hmc_warp_run<float>(Flow&, const struct Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*);
+extern template int hmc_warp_run<double>(Flow&, const struct Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*);
+
 // elementwise_{fwd,inv}_{f32,f64}.cu
 template <typename T, bool INV>
 int ew_run_dir(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed,

@@ -12,6 +12,7 @@ namespace nf {
 
 static thread_local std::string g_last_error;
 thread_local int64_t g_launch_count = 0;
+int g_opt_hmc_warp = getenv("NFCUDA_HMC_WARP") ? atoi(getenv("NFCUDA_HMC_WARP")) : 0;
 // 0: two-team streaming kernel (fused_coupling.cuh, default), 1: 128-column-MMA kernel (fused_coupling_w128.cuh)
 int g_opt_fused_variant = getenv("NFCUDA_FUSED_VARIANT") ? atoi(getenv("NFCUDA_FUSED_VARIANT")) : 0;
 int g_opt_fused_coupling = !(getenv("NFCUDA_FUSED") && atoi(getenv("NFCUDA_FUSED")) == 0);
@@ -195,8 +196,9 @@ static int flow_create(nf_flow_t* out, const nf_layer_desc* descs, int n_layers,
       case NF_RADIAL: off += dim + 2; f->any_elementwise = true; break;
       case NF_SHIFT: case NF_SCALE: off += dim; f->any_elementwise = true; break;
       case NF_MOMENTUM_AFFINE: case NF_LEAPFROG: {
-        NF_REQUIRE(dim == 2 || dim == 4 || dim == 8 || dim == 16 || dim == 32 || dim == 64,
-                   "layer %d: Hamiltonian layers need dim = 2h with h a power of two <= 32 in this build, got %d", i, dim);
+        // h a power of two <= 32: fused one-thread-per-sample kernel (both directions); any h <= 128: warp-per-sample kernel
+        // (hmc_warp.cu, forward direction: ELBO / gradient / transform)
+        NF_REQUIRE(dim >= 2 && (dim & 1) == 0 && dim <= 256, "layer %d: Hamiltonian layers need dim = 2h with h <= 128, got %d", i, dim);
         f->any_elementwise = true; f->hamiltonian = true;
         if (ds.kind == NF_MOMENTUM_AFFINE) { off += dim; break; }
         NF_REQUIRE(ds.n_steps >= 1, "layer %d: leapfrog needs n_steps >= 1", i);
@@ -669,8 +671,10 @@ void nf_target_destroy(nf_target_t target) {
 static int check_target(const Flow& f, const Target* t) {
   NF_REQUIRE(t, "null target");
   NF_REQUIRE(t->dim == f.dim, "target dim %d != flow dim %d", t->dim, f.dim);
-  if (t->joint && !(f.all_elementwise && f.dim == 2 * (t->dim / 2) && (f.dim & (f.dim - 1)) == 0 && f.dim <= 64)) {
-    set_error("joint [x, rho] targets are implemented for elementwise / Hamiltonian flows with dim a power of two <= 64");
+  if (t->joint && !(f.all_elementwise && f.dim == 2 * (t->dim / 2) &&
+                    (((f.dim & (f.dim - 1)) == 0 && f.dim <= 64) || hmc_warp_qualifies(f, t)))) {
+    set_error("joint [x, rho] targets are implemented for elementwise / Hamiltonian flows with dim a power of two <= 64, and for "
+              "flows of Shift / Scale / momentum-affine / LeapFrog layers with dim = 2h, h <= 128 (LogReg, Funnel, DiagNormal targets)");
     return NF_ERR_UNSUPPORTED;
   }
   return NF_OK;
@@ -989,6 +993,7 @@ int64_t nf_launch_count(int reset) {
 int nf_set_option(const char* name, int value) {
   if (name && !strcmp(name, "fused_coupling")) { g_opt_fused_coupling = value; return NF_OK; }
   if (name && !strcmp(name, "fused_variant")) { g_opt_fused_variant = value; return NF_OK; }
+  if (name && !strcmp(name, "hmc_warp")) { g_opt_hmc_warp = value; return NF_OK; }
   set_error("nf_set_option: unknown option '%s'", name ? name : "(null)");
   return NF_ERR_INVALID;
 }
