@@ -169,6 +169,17 @@ def run_side_config(args):
         inner = nf.Funnel(2, -8.0, 5.0)
         dt_ = np.float64 if cfg == "c5f64" else np.float32
         flow, tgt, n, name = nf.hamiltonian_flow(inner, 15, 3, math.log(0.05), dt_), nf.JointTarget(inner), 1 << 20, "Hamiltonian flow 15 x (momentum affine + LeapFrog L=3) on Funnel(2,-8,5) + N(0,I) momentum, %s, N=2^20" % dt_.__name__
+    elif cfg in ("c5x", "c5xf64"):
+        # BASELINE config 5 at its stated size: 100-D synthetic logistic-regression posterior (n_data = 256), flow of the
+        # reference demo (15 x (momentum affine + LeapFrog L=3)), joint target; warp-per-sample kernel (csrc/hmc_warp.cu)
+        import math
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        rng = np.random.Generator(np.random.PCG64(7))
+        X = rng.standard_normal((256, 100)) / 10.0
+        yb = (rng.uniform(size=256) < 1.0 / (1.0 + np.exp(-X @ rng.standard_normal(100)))).astype(np.float64)
+        inner = nf.LogReg(X, yb, 1.0)
+        dt_ = np.float64 if cfg == "c5xf64" else np.float32
+        flow, tgt, n, name = nf.hamiltonian_flow(inner, 15, 3, math.log(0.01), dt_), nf.JointTarget(inner), 1 << 16, "Hamiltonian flow 15 x (momentum affine + LeapFrog L=3) on a 100-D logistic-regression posterior (256 observations) + N(0,I) momentum, %s, N=2^16" % dt_.__name__
     elif cfg == "c3x1":
         flow, tgt, n, name = make_theta(nf), nf.Funnel(DIM), 1 << 20, "RealNVP C3 in NF_MMA_F16X1 (single fp16 pass, NOT parity grade)"
         flow.set_mma_mode(nf.NF_MMA_F16X1)
@@ -390,7 +401,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="base draws per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side", action="store_true", help="skip the side blocks (C4, strong scaling)")
-    ap.add_argument("--config", default="c3", help="c3 (headline) | c1 | c2 | c2p | c3b | c3x1 | c4 | c4b | c4ll | c5 | c5f64")
+    ap.add_argument("--config", default="c3", help="c3 (headline) | c1 | c2 | c2p | c3b | c3x1 | c4 | c4b | c4ll | c5 | c5f64 | c5x | c5xf64")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":

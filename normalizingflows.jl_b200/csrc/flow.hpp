@@ -177,6 +177,7 @@ struct Target {
 
 // hmc_warp.cu: warp-per-sample Hamiltonian flows (dim = 2h, h <= 128; forward direction)
 bool hmc_warp_qualifies(const Flow& f, const struct Target* tgt);
+size_t hmc_warp_workspace_bytes(const Flow& f);
 template <typename T>
 int hmc_warp_run(Flow& f, const struct Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed, bool want_grad,
                  void* y_out, void* ld_out, void* terms_out, double* gsum_dev);

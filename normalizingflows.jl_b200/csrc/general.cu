@@ -630,7 +630,7 @@ int backward_from_stash_typed(Flow& f, const void* gy_host, const void* gld_host
 int general_plan_workspace(Flow& f, int op, int64_t N, size_t extra_bytes) {
   if (f.all_elementwise && !(f.base_dense && (op == OP_INVERSE || op == OP_LOGLIK))) {
     f.chunk_N = N;
-    return f.ws_reserve(extra_bytes + ((size_t)16 << 20));
+    return f.ws_reserve(extra_bytes + ((size_t)16 << 20) + hmc_warp_workspace_bytes(f));
   }
   const bool stash = (op == OP_ELBO || op == OP_LOGLIK || op == OP_FORWARD_STASH);
   // the plan of the previous call is reused when nothing it depends on changed (cudaMemGetInfo is a driver round trip

@@ -516,6 +516,13 @@ bool hmc_warp_qualifies(const Flow& f, const Target* tgt) {
   return true;
 }
 
+// workspace of one call (layer table, per-CTA gradient partials, per-CTA objective partials), either precision
+size_t hmc_warp_workspace_bytes(const Flow& f) {
+  if (!f.hamiltonian) return 0;
+  const size_t L = f.layers.size(), d = (size_t)f.dim;
+  return (L * (4 + 2 * d) + (size_t)kNumSMs * 4 * L * 2 * d + (size_t)kNumSMs * 4) * 8 + 4096;
+}
+
 template <typename T>
 int hmc_warp_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, const void* z0_dev, uint64_t seed, bool want_grad,
                  void* y_out, void* ld_out, void* terms_out, double* gsum_dev) {
@@ -529,7 +536,7 @@ int hmc_warp_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, c
   int max_blocks = 0;
   NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, hw_flow_kernel<T>, HW_THREADS, smem));
   if (max_blocks < 1) max_blocks = 1;
-  const int grid = (int)std::min<int64_t>(ceil_div(N, (int64_t)(HW_THREADS / 32)), (int64_t)kNumSMs * max_blocks);
+  const int grid = (int)std::min<int64_t>(ceil_div(N, (int64_t)(HW_THREADS / 32)), (int64_t)kNumSMs * std::min(max_blocks, 4));
   T* table = (T*)f.ws_alloc((size_t)L * (4 + 2 * d) * sizeof(T));
   T* gpart = (T*)f.ws_alloc((size_t)grid * L * 2 * d * sizeof(T));
   double* epart = (double*)f.ws_alloc((size_t)grid * sizeof(double));
@@ -566,7 +573,7 @@ int hmc_warp_inverse(Flow& f, const void* theta_dev, int64_t N, const void* y_de
     return NF_ERR_UNSUPPORTED;
   }
   const int L = (int)f.layers.size(), d = f.dim;
-  const int grid = (int)std::min<int64_t>(ceil_div(N, (int64_t)(HW_THREADS / 32)), (int64_t)kNumSMs * 8);
+  const int grid = (int)std::min<int64_t>(ceil_div(N, (int64_t)(HW_THREADS / 32)), (int64_t)kNumSMs * 4);
   T* table = (T*)f.ws_alloc((size_t)L * (4 + 2 * d) * sizeof(T));
   double* epart = (double*)f.ws_alloc((size_t)grid * sizeof(double));
   if (!table || !epart) return NF_ERR_OOM;

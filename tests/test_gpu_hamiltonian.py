@@ -116,4 +116,11 @@ def test_hamiltonian_rejects_unsupported(gpu):
     with pytest.raises(nf.NFCudaError):
         nf.Flow([nf.LeapFrog(2, -3.0, 3, nf.WarpedGauss())], nf.MvNormal(np.zeros(4))).handle()   # no closed-form HVP
     with pytest.raises(nf.NFCudaError):
-        nf.Flow([nf.LeapFrog(3, -3.0, 3, nf.Funnel(3))], nf.MvNormal(np.zeros(6))).handle()       # h not a power of two
+        nf.Flow([nf.LeapFrog(129, -3.0, 3, nf.Funnel(129))], nf.MvNormal(np.zeros(258))).handle()  # h > 128
+    # h not a power of two is served by the warp-per-sample kernel (csrc/hmc_warp.cu)
+    f = nf.Flow([nf.LeapFrog(3, -3.0, 3, nf.Funnel(3))], nf.MvNormal(np.zeros(6)))
+    y, ld = f.with_logabsdet_jacobian(np.zeros((2, 6), np.float64) + 0.1)
+    assert y.shape == (2, 6) and np.allclose(ld, 0.0)
+    # ... but a Banana score is not among its targets: the power-of-two path's restriction is reported
+    with pytest.raises(nf.NFCudaError):
+        nf.Flow([nf.LeapFrog(3, -3.0, 3, nf.Banana(3, 1.0, 10.0))], nf.MvNormal(np.zeros(6))).with_logabsdet_jacobian(np.zeros((2, 6)))

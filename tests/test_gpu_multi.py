@@ -121,3 +121,28 @@ def test_two_devices_match_one(gpu, kind):
     v2, g2 = nf.dp.elbo_value_and_grad_multi(comm, flows, targets, flows[0].theta, 5000, None, seed=7)
     assert v2 == pytest.approx(v1, rel=2e-6) and rel_err(g2, g1) <= 5e-6
     comm.close()
+
+
+def test_two_devices_hamiltonian_100d(gpu):
+    """BASELINE config 5 as stated: the 100-D Hamiltonian flow sample-sharded over the devices of one communicator."""
+    import math
+    nf = gpu
+    if not _two_gpus(nf):
+        pytest.skip("needs two GPUs")
+    tgt = O.synthetic_logreg(100, 256)
+    of = O.hamiltonian_flow(tgt, 3, 2, math.log(0.02), dtype=torch.float64)
+    jt = O.JointTarget(tgt)
+    comm = nf.dp.Comm.init_all([0, 1])
+    flows, targets = nf.dp.replicate(comm, lambda: gpu_flow(nf, of, np.float64), lambda: gpu_target(nf, jt))
+    nf._capi.check(nf._capi.lib().nf_init(0))
+    N = 301
+    xs = z0(N, 200, np.float64)
+    v1, g1 = nf.api._elbo_impl(flows[0], targets[0], xs, want_grad=True)
+    v2, g2 = nf.dp.elbo_value_and_grad_multi(comm, flows, targets, flows[0].theta, N, xs)
+    assert v2 == pytest.approx(v1, rel=1e-12) and rel_err(g2, g1) <= 1e-11
+    v_ref, g_ref = O.elbo_value_and_grad(of, jt, of.theta(), torch.from_numpy(xs))
+    assert abs(v2 - v_ref) <= 1e-9 * max(abs(v_ref), 1.0) and rel_err(g2, g_ref) <= 1e-7
+    v1, g1 = nf.api._elbo_impl(flows[0], targets[0], 1000, want_grad=True, seed=7)
+    v2, g2 = nf.dp.elbo_value_and_grad_multi(comm, flows, targets, flows[0].theta, 1000, None, seed=7)
+    assert v2 == pytest.approx(v1, rel=1e-12) and rel_err(g2, g1) <= 1e-11
+    comm.close()
