@@ -4,9 +4,9 @@
 // target logp(x) + sum logN(rho; 0, 1)), :139-147 (flow = 15 x (momentum affine o LeapFrog) over q0 = Shift o Scale (MvNormal)).
 //
 // The fused elementwise kernel (elementwise_impl.cuh) keeps a sample's whole state in ONE thread's registers, which stops at
-// h = 32 (8 with the logistic-regression score).  Here a WARP owns a sample: lane l holds coordinates l, l + 32, l + 64, l + 96 of
-// the position x and of the momentum rho (h <= 128), the data set of the logistic-regression posterior is walked row by row with
-// coalesced loads and one butterfly reduction per row, and the reverse sweep needs no stash: every elementary update is undone
+// h = 32 (8 with the logistic-regression score).  Here a WARP owns a sample: lane l holds coordinates 4l .. 4l + 3 of
+// the position x and of the momentum rho (h <= 128), the data set of the logistic-regression posterior is walked 32 observations
+// at a time (coalesced row loads, one transposing reduction per round so that each lane evaluates one row's transcendental), and the reverse sweep needs no stash: every elementary update is undone
 // exactly while its adjoint is applied, the second-order term being a Hessian-vector product of the target (same algorithm as
 // leapfrog_backward in elementwise_impl.cuh).  Per-parameter gradient sums: shared-memory atomics per CTA, one partial row per CTA,
 // finished in double by hw_finalize_kernel (layer-table layout and chain rules identical to ew_prep_body / ew_finalize_body).
@@ -41,6 +41,45 @@ template <typename T> struct HwArgs {
 
 enum : int { HW_GRAD = 1, HW_TARGET = 2, HW_WRITE_Y = 4, HW_WRITE_LD = 8, HW_WRITE_TERMS = 16, HW_GEN_Z0 = 32 };
 
+// this lane's four entries of a data row (zero past h): one 16-byte (two for double) load when the rows are aligned
+template <typename T>
+__device__ __forceinline__ void hw_load_row(const T* __restrict__ xr, int h, int lane, bool vec, T (&xv)[HW_NPL]) {
+  const int k0 = 4 * lane;
+  if (vec) {
+    if (k0 < h) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(xr + k0);
+        xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+      } else {
+        const double2 t0 = *reinterpret_cast<const double2*>(xr + k0), t1 = *reinterpret_cast<const double2*>(xr + k0 + 2);
+        xv[0] = t0.x; xv[1] = t0.y; xv[2] = t1.x; xv[3] = t1.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < HW_NPL; ++i) xv[i] = 0;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < HW_NPL; ++i) xv[i] = (k0 + i < h) ? xr[k0 + i] : T(0);
+  }
+}
+
+// Lane l receives sum over the 32 lanes of p[l] (p is consumed): recursive halving, 31 shuffles instead of 32 x 5
+template <typename T>
+__device__ __forceinline__ T hw_transpose_sum(T (&p)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const T send = up ? p[j] : p[j + s];
+      const T keep = up ? p[j + s] : p[j];
+      p[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return p[0];
+}
+
 // logp and score of the (inner) target at x; every lane returns the same logp
 template <typename T>
 __device__ __forceinline__ T hw_score(const TargetParams<T>& tp, const T (&x)[HW_NPL], T (&g)[HW_NPL], int lane) {
@@ -48,29 +87,48 @@ __device__ __forceinline__ T hw_score(const TargetParams<T>& tp, const T (&x)[HW
   const int h = tp.dim;
   switch (tp.kind) {
     case NF_TARGET_LOGREG: {   // u_i = x_i . z ; logp = sum_i [y_i u_i - softplus(u_i)] - |z|^2 / (2 sigma0^2) + c0   (targets.cuh)
+      // 32 observations per round: every lane forms its share of the 32 dot products from coalesced row loads, a transposing
+      // reduction hands observation r to lane r, which evaluates the ONE softplus / sigmoid of that row; the residuals then
+      // go back by broadcast for the rank-one score updates (rows re-read from L1)
       const T is2 = 1 / (tp.p0 * tp.p0);
       const T* X = tp.vec;
       const T* y = tp.vec + (size_t)tp.n_data * h;
+      const bool vec = (h & 3) == 0;
       T q = 0, lp = 0;
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) { q += x[i] * x[i]; g[i] = -x[i] * is2; }
-      q = warp_sum(q);
-      for (int r = 0; r < tp.n_data; ++r) {
-        const T* xr = X + (size_t)r * h;
-        T xv[HW_NPL], u = 0;
+      for (int r0 = 0; r0 < tp.n_data; r0 += 32) {
+        T part[32];
 #pragma unroll
-        for (int i = 0; i < HW_NPL; ++i) {
-          const int k = lane + 32 * i;
-          xv[i] = k < h ? xr[k] : T(0);
-          u += xv[i] * x[i];
+        for (int rr = 0; rr < 32; ++rr) {
+          T u = 0;
+          if (r0 + rr < tp.n_data) {
+            T xv[HW_NPL];
+            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xv);
+#pragma unroll
+            for (int i = 0; i < HW_NPL; ++i) u += xv[i] * x[i];
+          }
+          part[rr] = u;
         }
-        u = warp_sum(u);
-        const T yr = y[r];
-        lp += yr * u - softplus_stable<T>(u);
-        const T res = yr - sigmoid_stable<T>(u);
+        const T u = hw_transpose_sum<T>(part, lane);
+        T res = 0;
+        if (r0 + lane < tp.n_data) {
+          const T yr = y[r0 + lane];
+          lp += yr * u - softplus_stable<T>(u);
+          res = yr - sigmoid_stable<T>(u);
+        }
 #pragma unroll
-        for (int i = 0; i < HW_NPL; ++i) g[i] += res * xv[i];
+        for (int rr = 0; rr < 32; ++rr) {
+          const T rv = __shfl_sync(0xffffffffu, res, rr);
+          if (r0 + rr < tp.n_data) {
+            T xv[HW_NPL];
+            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xv);
+#pragma unroll
+            for (int i = 0; i < HW_NPL; ++i) g[i] += rv * xv[i];
+          }
+        }
       }
+      q = warp_sum(q); lp = warp_sum(lp);
       return tp.c0 + lp - q * is2 / 2;
     }
     case NF_TARGET_FUNNEL: {   // neal_funnel.jl:54-72: mu = p0, sigma = p1
@@ -80,7 +138,7 @@ __device__ __forceinline__ T hw_score(const TargetParams<T>& tp, const T (&x)[HW
       T ss = 0;
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         if (k >= 1 && k < h) { ss += x[i] * x[i]; g[i] = -a * x[i]; } else g[i] = 0;
       }
       ss = warp_sum(ss);
@@ -91,7 +149,7 @@ __device__ __forceinline__ T hw_score(const TargetParams<T>& tp, const T (&x)[HW
       T q = 0;
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         g[i] = 0;
         if (k < h) {
           const T is = 1 / tp.vec[h + k];
@@ -116,23 +174,39 @@ __device__ __forceinline__ void hw_hvp(const TargetParams<T>& tp, const T (&x)[H
     case NF_TARGET_LOGREG: {   // H w = -X^T diag(s (1 - s)) X w - w / sigma0^2,  s = sigmoid(X x)
       const T is2 = 1 / (tp.p0 * tp.p0);
       const T* X = tp.vec;
+      const bool vec = (h & 3) == 0;
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) out[i] = -w[i] * is2;
-      for (int r = 0; r < tp.n_data; ++r) {
-        const T* xr = X + (size_t)r * h;
-        T xv[HW_NPL], u = 0, xw = 0;
+      for (int r0 = 0; r0 < tp.n_data; r0 += 32) {
+        T pu[32], pw[32];
 #pragma unroll
-        for (int i = 0; i < HW_NPL; ++i) {
-          const int k = lane + 32 * i;
-          xv[i] = k < h ? xr[k] : T(0);
-          u += xv[i] * x[i];
-          xw += xv[i] * w[i];
+        for (int rr = 0; rr < 32; ++rr) {
+          T u = 0, xw = 0;
+          if (r0 + rr < tp.n_data) {
+            T xv[HW_NPL];
+            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xv);
+#pragma unroll
+            for (int i = 0; i < HW_NPL; ++i) { u += xv[i] * x[i]; xw += xv[i] * w[i]; }
+          }
+          pu[rr] = u; pw[rr] = xw;
         }
-        u = warp_sum(u); xw = warp_sum(xw);
-        const T sg = sigmoid_stable<T>(u);
-        const T cfac = -sg * (1 - sg) * xw;
+        const T u = hw_transpose_sum<T>(pu, lane);
+        const T xw = hw_transpose_sum<T>(pw, lane);
+        T cfac = 0;
+        if (r0 + lane < tp.n_data) {
+          const T sg = sigmoid_stable<T>(u);
+          cfac = -sg * (1 - sg) * xw;
+        }
 #pragma unroll
-        for (int i = 0; i < HW_NPL; ++i) out[i] += cfac * xv[i];
+        for (int rr = 0; rr < 32; ++rr) {
+          const T cv = __shfl_sync(0xffffffffu, cfac, rr);
+          if (r0 + rr < tp.n_data) {
+            T xv[HW_NPL];
+            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xv);
+#pragma unroll
+            for (int i = 0; i < HW_NPL; ++i) out[i] += cv * xv[i];
+          }
+        }
       }
       return;
     }
@@ -143,7 +217,7 @@ __device__ __forceinline__ void hw_hvp(const TargetParams<T>& tp, const T (&x)[H
       T ss = 0, xw = 0;
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         out[i] = 0;
         if (k >= 1 && k < h) { ss += x[i] * x[i]; xw += x[i] * w[i]; out[i] = a * (x[i] * w1 - w[i]); }
       }
@@ -154,7 +228,7 @@ __device__ __forceinline__ void hw_hvp(const TargetParams<T>& tp, const T (&x)[H
     case NF_TARGET_DIAG_NORMAL: {
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         out[i] = 0;
         if (k < h) { const T is = 1 / tp.vec[h + k]; out[i] = -w[i] * is * is; }
       }
@@ -266,7 +340,7 @@ __global__ void __launch_bounds__(HW_THREADS) hw_flow_kernel(HwArgs<T> a) {
     // ---- base draws, base log-density ----
 #pragma unroll
     for (int i = 0; i < HW_NPL; ++i) {
-      const int k = lane + 32 * i;
+      const int k = 4 * lane + i;
       x[i] = 0; v[i] = 0;
       if (k < h) {
         T zx, zv;
@@ -303,13 +377,13 @@ __global__ void __launch_bounds__(HW_THREADS) hw_flow_kernel(HwArgs<T> a) {
       if (kind == NF_LEAPFROG) {
         T eps[HW_NPL];
 #pragma unroll
-        for (int i = 0; i < HW_NPL; ++i) { const int k = lane + 32 * i; eps[i] = k < h ? v0[k] : T(0); }
+        for (int i = 0; i < HW_NPL; ++i) { const int k = 4 * lane + i; eps[i] = k < h ? v0[k] : T(0); }
         hw_leapfrog_apply<T>(a.sp, x, v, eps, (int)e[0], lane);
         continue;
       }
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         if (k >= h) continue;
         if (kind == NF_SHIFT) { x[i] += v0[k]; v[i] += v0[h + k]; }
         else if (kind == NF_SCALE) { x[i] *= v0[k]; v[i] *= v0[h + k]; }
@@ -320,7 +394,7 @@ __global__ void __launch_bounds__(HW_THREADS) hw_flow_kernel(HwArgs<T> a) {
     if (a.flags & HW_WRITE_Y) {
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         if (k < h) { a.y_out[j * d + k] = x[i]; a.y_out[j * d + h + k] = v[i]; }
       }
     }
@@ -350,15 +424,15 @@ __global__ void __launch_bounds__(HW_THREADS) hw_flow_kernel(HwArgs<T> a) {
       if (kind == NF_LEAPFROG) {
         T eps[HW_NPL], ge[HW_NPL];
 #pragma unroll
-        for (int i = 0; i < HW_NPL; ++i) { const int k = lane + 32 * i; eps[i] = k < h ? v0[k] : T(0); ge[i] = 0; }
+        for (int i = 0; i < HW_NPL; ++i) { const int k = 4 * lane + i; eps[i] = k < h ? v0[k] : T(0); ge[i] = 0; }
         hw_leapfrog_backward<T>(a.sp, x, v, gx, gv, eps, (int)e[0], ge, lane);
 #pragma unroll
-        for (int i = 0; i < HW_NPL; ++i) { const int k = lane + 32 * i; if (k < h) atomicAdd(&acc[k], ge[i]); }
+        for (int i = 0; i < HW_NPL; ++i) { const int k = 4 * lane + i; if (k < h) atomicAdd(&acc[k], ge[i]); }
         continue;
       }
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         if (k >= h) continue;
         if (kind == NF_SHIFT) {
           atomicAdd(&acc[k], gx[i]); atomicAdd(&acc[h + k], gv[i]);
@@ -404,7 +478,7 @@ __global__ void __launch_bounds__(HW_THREADS) hw_inv_kernel(HwArgs<T> a) {
     T x[HW_NPL], v[HW_NPL];
 #pragma unroll
     for (int i = 0; i < HW_NPL; ++i) {
-      const int k = lane + 32 * i;
+      const int k = 4 * lane + i;
       x[i] = k < h ? a.z0[j * d + k] : T(0);
       v[i] = k < h ? a.z0[j * d + h + k] : T(0);
     }
@@ -417,13 +491,13 @@ __global__ void __launch_bounds__(HW_THREADS) hw_inv_kernel(HwArgs<T> a) {
       if (kind == NF_LEAPFROG) {
         T eps[HW_NPL];
 #pragma unroll
-        for (int i = 0; i < HW_NPL; ++i) { const int k = lane + 32 * i; eps[i] = k < h ? -v0[k] : T(0); }
+        for (int i = 0; i < HW_NPL; ++i) { const int k = 4 * lane + i; eps[i] = k < h ? -v0[k] : T(0); }
         hw_leapfrog_apply<T>(a.sp, x, v, eps, (int)e[0], lane);
         continue;
       }
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         if (k >= h) continue;
         if (kind == NF_SHIFT) { x[i] -= v0[k]; v[i] -= v0[h + k]; }
         else if (kind == NF_SCALE) { x[i] *= v1[k]; v[i] *= v1[h + k]; }
@@ -434,7 +508,7 @@ __global__ void __launch_bounds__(HW_THREADS) hw_inv_kernel(HwArgs<T> a) {
     if (a.flags & HW_WRITE_Y) {
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) {
-        const int k = lane + 32 * i;
+        const int k = 4 * lane + i;
         if (k < h) { a.y_out[j * d + k] = x[i]; a.y_out[j * d + h + k] = v[i]; }
       }
     }
@@ -443,7 +517,7 @@ __global__ void __launch_bounds__(HW_THREADS) hw_inv_kernel(HwArgs<T> a) {
     T q = 0;
 #pragma unroll
     for (int i = 0; i < HW_NPL; ++i) {
-      const int k = lane + 32 * i;
+      const int k = 4 * lane + i;
       if (k >= h) continue;
       T ux = x[i], uv = v[i];
       if (a.base) { ux = (ux - a.base[k]) / a.base[d + k]; uv = (uv - a.base[h + k]) / a.base[d + h + k]; }

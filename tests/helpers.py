@@ -25,6 +25,13 @@ def oracle_flow(kind, dim, dtype, seed=123, **kw):
         th = f.theta().double().numpy()
         f.set_theta(torch.from_numpy(th + 0.05 * rng.standard_normal(th.size)).to(td))
         return f
+    if kind == "hamiltonian_logreg":   # BASELINE config 5 at its size: dim = 2h, LeapFrog on the h-D logistic-regression posterior
+        import math
+        tgt = O.synthetic_logreg(dim // 2, kw.get("n_data", 256))
+        f = O.hamiltonian_flow(tgt, kw.get("nlayers", 15), kw.get("L", 3), math.log(kw.get("eps", 0.02)), dtype=td)
+        th = f.theta().double().numpy()
+        f.set_theta(torch.from_numpy(th + 0.05 * rng.standard_normal(th.size)).to(td))
+        return f
     raise ValueError(kind)
 
 
@@ -73,6 +80,8 @@ def oracle_target(name, dim):
         return O.Cross(dim, 2.0, 0.15)
     if name == "joint_funnel":
         return O.JointTarget(O.Funnel(dim // 2, -8.0, 5.0))
+    if name == "joint_logreg":
+        return O.JointTarget(O.synthetic_logreg(dim // 2, 256))
     if name == "diag":
         rng = np.random.Generator(np.random.PCG64(7))
         return O.DiagNormal(rng.standard_normal(dim), rng.uniform(0.5, 1.5, dim))
