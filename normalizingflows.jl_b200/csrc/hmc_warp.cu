@@ -64,11 +64,16 @@ __device__ __forceinline__ void hw_load_row(const T* __restrict__ xr, int h, int
   }
 }
 
-// Lane l receives sum over the 32 lanes of p[l] (p is consumed): recursive halving, 31 shuffles instead of 32 x 5
-template <typename T>
-__device__ __forceinline__ T hw_transpose_sum(T (&p)[32], int lane) {
+// Lane l receives the sum over the 32 lanes of p[l % R] (p is consumed): recursive halving, 31 shuffles for R = 32 or 16
+// instead of R x 5
+template <typename T, int R>
+__device__ __forceinline__ T hw_transpose_sum(T (&p)[R], int lane) {
+  if constexpr (R == 16) {
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
+    for (int j = 0; j < 16; ++j) p[j] += __shfl_xor_sync(0xffffffffu, p[j], 16);
+  }
+#pragma unroll
+  for (int s = (R == 32 ? 16 : 8); s >= 1; s >>= 1) {
     const bool up = (lane & s) != 0;
 #pragma unroll
     for (int j = 0; j < s; ++j) {
@@ -79,6 +84,8 @@ __device__ __forceinline__ T hw_transpose_sum(T (&p)[32], int lane) {
   }
   return p[0];
 }
+// observations per round: the rows of a round stay in registers between the dot products and the rank-one updates
+template <typename T> constexpr int hw_round() { return sizeof(T) == 4 ? 32 : 16; }
 
 // logp and score of the (inner) target at x; every lane returns the same logp
 template <typename T>
@@ -87,9 +94,9 @@ __device__ __forceinline__ T hw_score(const TargetParams<T>& tp, const T (&x)[HW
   const int h = tp.dim;
   switch (tp.kind) {
     case NF_TARGET_LOGREG: {   // u_i = x_i . z ; logp = sum_i [y_i u_i - softplus(u_i)] - |z|^2 / (2 sigma0^2) + c0   (targets.cuh)
-      // 32 observations per round: every lane forms its share of the 32 dot products from coalesced row loads, a transposing
-      // reduction hands observation r to lane r, which evaluates the ONE softplus / sigmoid of that row; the residuals then
-      // go back by broadcast for the rank-one score updates (rows re-read from L1)
+      // R observations per round (32 float / 16 double): every lane forms its share of the R dot products from vector row loads, a
+      // transposing reduction hands observation r to lane r, which evaluates the ONE softplus / sigmoid of that row; the
+      // residuals then go back by broadcast for the rank-one score updates on the rows still held in registers
       const T is2 = 1 / (tp.p0 * tp.p0);
       const T* X = tp.vec;
       const T* y = tp.vec + (size_t)tp.n_data * h;
@@ -97,35 +104,34 @@ __device__ __forceinline__ T hw_score(const TargetParams<T>& tp, const T (&x)[HW
       T q = 0, lp = 0;
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) { q += x[i] * x[i]; g[i] = -x[i] * is2; }
-      for (int r0 = 0; r0 < tp.n_data; r0 += 32) {
-        T part[32];
+      constexpr int R = hw_round<T>();
+      for (int r0 = 0; r0 < tp.n_data; r0 += R) {
+        T part[R], xk[R][HW_NPL];
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
+        for (int rr = 0; rr < R; ++rr) {
           T u = 0;
-          if (r0 + rr < tp.n_data) {
-            T xv[HW_NPL];
-            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xv);
 #pragma unroll
-            for (int i = 0; i < HW_NPL; ++i) u += xv[i] * x[i];
+          for (int i = 0; i < HW_NPL; ++i) xk[rr][i] = 0;
+          if (r0 + rr < tp.n_data) {
+            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xk[rr]);
+#pragma unroll
+            for (int i = 0; i < HW_NPL; ++i) u += xk[rr][i] * x[i];
           }
           part[rr] = u;
         }
-        const T u = hw_transpose_sum<T>(part, lane);
+        const T u = hw_transpose_sum<T, R>(part, lane);
+        const int row = r0 + (lane & (R - 1));
         T res = 0;
-        if (r0 + lane < tp.n_data) {
-          const T yr = y[r0 + lane];
-          lp += yr * u - softplus_stable<T>(u);
+        if (row < tp.n_data) {
+          const T yr = y[row];
+          if (lane < R) lp += yr * u - softplus_stable<T>(u);
           res = yr - sigmoid_stable<T>(u);
         }
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          const T rv = __shfl_sync(0xffffffffu, res, rr);
-          if (r0 + rr < tp.n_data) {
-            T xv[HW_NPL];
-            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xv);
+        for (int rr = 0; rr < R; ++rr) {
+          const T rv = __shfl_sync(0xffffffffu, res, rr);        // rows past n_data hold zeros and rv = 0
 #pragma unroll
-            for (int i = 0; i < HW_NPL; ++i) g[i] += rv * xv[i];
-          }
+          for (int i = 0; i < HW_NPL; ++i) g[i] += rv * xk[rr][i];
         }
       }
       q = warp_sum(q); lp = warp_sum(lp);
@@ -177,35 +183,33 @@ __device__ __forceinline__ void hw_hvp(const TargetParams<T>& tp, const T (&x)[H
       const bool vec = (h & 3) == 0;
 #pragma unroll
       for (int i = 0; i < HW_NPL; ++i) out[i] = -w[i] * is2;
-      for (int r0 = 0; r0 < tp.n_data; r0 += 32) {
-        T pu[32], pw[32];
+      constexpr int R = hw_round<T>();
+      for (int r0 = 0; r0 < tp.n_data; r0 += R) {
+        T pu[R], pw[R], xk[R][HW_NPL];
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
+        for (int rr = 0; rr < R; ++rr) {
           T u = 0, xw = 0;
-          if (r0 + rr < tp.n_data) {
-            T xv[HW_NPL];
-            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xv);
 #pragma unroll
-            for (int i = 0; i < HW_NPL; ++i) { u += xv[i] * x[i]; xw += xv[i] * w[i]; }
+          for (int i = 0; i < HW_NPL; ++i) xk[rr][i] = 0;
+          if (r0 + rr < tp.n_data) {
+            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xk[rr]);
+#pragma unroll
+            for (int i = 0; i < HW_NPL; ++i) { u += xk[rr][i] * x[i]; xw += xk[rr][i] * w[i]; }
           }
           pu[rr] = u; pw[rr] = xw;
         }
-        const T u = hw_transpose_sum<T>(pu, lane);
-        const T xw = hw_transpose_sum<T>(pw, lane);
+        const T u = hw_transpose_sum<T, R>(pu, lane);
+        const T xw = hw_transpose_sum<T, R>(pw, lane);
         T cfac = 0;
-        if (r0 + lane < tp.n_data) {
+        if (r0 + (lane & (R - 1)) < tp.n_data) {
           const T sg = sigmoid_stable<T>(u);
           cfac = -sg * (1 - sg) * xw;
         }
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
+        for (int rr = 0; rr < R; ++rr) {
           const T cv = __shfl_sync(0xffffffffu, cfac, rr);
-          if (r0 + rr < tp.n_data) {
-            T xv[HW_NPL];
-            hw_load_row<T>(X + (size_t)(r0 + rr) * h, h, lane, vec, xv);
 #pragma unroll
-            for (int i = 0; i < HW_NPL; ++i) out[i] += cv * xv[i];
-          }
+          for (int i = 0; i < HW_NPL; ++i) out[i] += cv * xk[rr][i];
         }
       }
       return;
