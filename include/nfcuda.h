@@ -69,7 +69,10 @@ typedef enum nf_layer_kind {
   NF_SPLINE_COUPLING = 4,   /* theta: nn-chain with (3K-1)*n_mask outputs */
   NF_SHIFT           = 5,   /* theta: a(d) */
   NF_SCALE           = 6,   /* theta: a(d) */
-  /* Hamiltonian flow on z = [x, rho], dim = 2h (reference example/demo_hamiltonian_flow.jl): */
+  /* Hamiltonian flow on z = [x, rho], dim = 2h (reference example/demo_hamiltonian_flow.jl).  h a power of two <= 32 (<= 8 with the
+   * logistic-regression score): fused one-thread-per-sample kernels, every entry point.  Any h <= 128 (BASELINE config 5: h = 100):
+   * warp-per-sample kernels -- flows of Shift / Scale / these two kinds, LogReg / Funnel / DiagNormal scores, joint target;
+   * ELBO value + gradient, terms, forward, inverse, logpdf, sampling (not the forward-KL gradient): */
   NF_MOMENTUM_AFFINE = 7,   /* Stacked((identity, Shift(b) ∘ Scale(a)), [1:h, h+1:2h]) (:94-99); theta: b(h), a(h) */
   NF_LEAPFROG        = 8    /* LeapFrog bijector (:27-91), logdet 0; theta: log_eps(h) (`@functor LeapFrog (logϵ,)` :39) */
 } nf_layer_kind;
@@ -260,6 +263,10 @@ NF_API void nf_shard_range(int64_t N_total, int n_ranks, int rank, int64_t* begi
 
 /* Process-wide execution options (diagnostics / A-B measurements; results are parity grade either way).
  *   "fused_coupling"  1 (default): AffineCoupling layers that qualify run the fused conditioner kernels; 0: layer by layer
+ *   "fused_variant"   0 (default): two-team streaming kernel (csrc/fused_coupling.cuh); 1: 128-column-MMA kernel
+ *   "hmc_warp"        1: every Hamiltonian flow the warp-per-sample kernels cover runs on them (csrc/hmc_warp.cu; default 0:
+ *                     only flows the one-thread-per-sample kernels cannot take -- h not a power of two, h > 32, or h > 8 with
+ *                     the logistic-regression score)
  * Returns NF_ERR_INVALID for an unknown name. */
 NF_API int nf_set_option(const char* name, int value);
 /* Duration (ms, CUDA events on the flow's stream) of the device work of the last value_and_grad call. */
