@@ -111,6 +111,18 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+// both members of Box-Muller pair `pair` (elements 2 pair and 2 pair + 1 of the draw matrix): one Philox call, one log / sqrt /
+// sincospi -- bit-identical to two philox_randn calls
+template <typename T> __device__ __forceinline__ void philox_randn_pair(uint64_t seed, uint64_t pair, T& even, T& odd) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), 0x6e66u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const double u1 = ((double)r[0] + 1.0) * (1.0 / 4294967296.0);
+  const double u2 = (double)r[1] * (1.0 / 4294967296.0);
+  const double rad = ::sqrt(-2.0 * ::log(u1));
+  double s, c;
+  ::sincospi(2.0 * u2, &s, &c);
+  even = (T)(rad * c); odd = (T)(rad * s);
+}
 // element e of the N x dim draw matrix for (seed): deterministic, independent of launch geometry
 template <typename T> __device__ __forceinline__ T philox_randn(uint64_t seed, uint64_t elem) {
   uint32_t r[4];

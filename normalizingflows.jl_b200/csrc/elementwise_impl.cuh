@@ -1064,7 +1064,7 @@ static int ew_launch(Flow& f, const Target* tgt, const T* theta_dev, int64_t N, 
     if (!z0_dev) {
       T* x0 = (T*)f.ws_alloc((size_t)N * d * sizeof(T));
       if (!x0) return NF_ERR_OOM;
-      base_sample_kernel<T><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>(x0, nullptr, d, N, seed, f.draw_row_offset);
+      base_sample_kernel<T><<<base_sample_grid(N, d, f.draw_row_offset), 256, 0, f.stream>>>(x0, nullptr, d, N, seed, f.draw_row_offset);
       NF_LAUNCH_CHECK();
       NF_TRY(base_dense_launch<T>(f, x0, N, 0, lq0, nullptr));
       z0_dev = x0;

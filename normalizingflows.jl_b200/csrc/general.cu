@@ -525,7 +525,7 @@ int run_typed(Flow& f, const GeneralJob& job) {
       if (!lq0) return NF_ERR_OOM;
     }
     if (!in) {
-      base_sample_kernel<T><<<(unsigned)ceil_div(n * d, 256), 256, 0, f.stream>>>((T*)c.X[0], base, d, n, job.seed, c0 + f.draw_row_offset, job.seed_iter_dev);
+      base_sample_kernel<T><<<base_sample_grid(n, d, c0 + f.draw_row_offset), 256, 0, f.stream>>>((T*)c.X[0], base, d, n, job.seed, c0 + f.draw_row_offset, job.seed_iter_dev);
       NF_LAUNCH_CHECK();
       if (f.base_dense) NF_TRY(base_dense_launch<T>(f, (T*)c.X[0], n, 0, lq0, nullptr));    // eps -> mu + L eps, lq0 from eps
     } else if (f.base_dense && job.op == OP_ELBO) {
@@ -685,9 +685,9 @@ int base_sample_dev(Flow& f, int64_t N, uint64_t seed, void* z_dev) {
   const int d = f.dim;
   const bool plain = f.base_is_standard || f.base_dense;
   if (f.dtype == NF_F32)
-    base_sample_kernel<float><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>((float*)z_dev, plain ? nullptr : (const float*)f.d_base, d, N, seed, 0);
+    base_sample_kernel<float><<<base_sample_grid(N, d, 0), 256, 0, f.stream>>>((float*)z_dev, plain ? nullptr : (const float*)f.d_base, d, N, seed, 0);
   else
-    base_sample_kernel<double><<<(unsigned)ceil_div(N * d, 256), 256, 0, f.stream>>>((double*)z_dev, plain ? nullptr : (const double*)f.d_base, d, N, seed, 0);
+    base_sample_kernel<double><<<base_sample_grid(N, d, 0), 256, 0, f.stream>>>((double*)z_dev, plain ? nullptr : (const double*)f.d_base, d, N, seed, 0);
   NF_LAUNCH_CHECK();
   if (f.base_dense) {       // unwhiten!(Sigma, x) .+ mu of reference ext/NormalizingFlowsCUDAExt.jl:43-47
     if (f.dtype == NF_F32) NF_TRY(base_dense_launch<float>(f, (float*)z_dev, N, 0, nullptr, nullptr));
