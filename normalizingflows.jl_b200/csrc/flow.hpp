@@ -107,6 +107,11 @@ struct Flow {
   size_t plan_extra = 0, plan_limit = 0, plan_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host-supplied inputs of large batches arrive in two halves: the second half's copy (copy_stream) overlaps the first half's
+  // compute; the chunk loop of the layered path waits on in_ev before it touches rows >= in_split  (stage_host_input)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t in_ev = nullptr;
+  bool in_ev_armed = false;
   double last_ms = 0;
 
   // base distribution q0 = MvNormal(mu, Diagonal(sigma^2))

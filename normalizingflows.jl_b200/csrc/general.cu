@@ -515,6 +515,10 @@ int run_typed(Flow& f, const GeneralJob& job) {
   for (int64_t c0 = 0; c0 < N; c0 += Nc) {
     const int64_t n = std::min(Nc, N - c0);
     f.ws.off = ws_mark;
+    if (c0 > 0 && f.in_ev_armed) {          // second half of a host-supplied batch: its copy ran beside the first half's compute
+      NF_CUDA(cudaStreamWaitEvent(f.stream, f.in_ev, 0));
+      f.in_ev_armed = false;
+    }
     if (f.mma_mode != NF_MMA_SIMT && c0 > 0) NF_TRY(tc_begin_chunk(f));
     Chunk c;
     const T* in = job.in_dev ? (const T*)job.in_dev + c0 * d : nullptr;
