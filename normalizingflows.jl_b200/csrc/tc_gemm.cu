@@ -209,7 +209,13 @@ template <int BN> struct GemmCfg {
   static constexpr int A_PLANE = 128 * 128;                  // 128 rows x 128 B
   static constexpr int B_PLANE = BN * 128;
   static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
-  static constexpr int STAGES = (STAGE * 4 <= 200 * 1024) ? 4 : ((STAGE * 3 <= 200 * 1024) ? 3 : 2);
+  // narrow tiles (BN <= 64): two CTAs per SM with two stages each instead of one CTA with four -- the same bytes in flight, but
+  // one CTA's epilogue overlaps the other's loads and MMAs (NFCUDA_GEMM_CTAS is a compile-time A/B switch)
+#ifndef NFCUDA_GEMM_CTAS
+#define NFCUDA_GEMM_CTAS 2
+#endif
+  static constexpr int CTAS = (BN <= 64) ? NFCUDA_GEMM_CTAS : 1;
+  static constexpr int STAGES = CTAS == 2 ? 2 : ((STAGE * 4 <= 200 * 1024) ? 4 : ((STAGE * 3 <= 200 * 1024) ? 3 : 2));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   // epilogue: 4 warps (one per TMEM lane quarter) per column group; wide tiles use four groups = 16 warps so that
   // the per-element epilogue math has 4 warps per scheduler to hide its latencies
@@ -229,7 +235,7 @@ template <int BN> struct GemmCfg {
 // accumulator is still tiny), the epilogue warps drain it and carry the running sum in registers with
 // round-to-nearest adds, the same split Ootomo & Yokota use for fp32 emulation on tensor cores.
 template <int BN>
-__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::THREADS, GemmCfg<BN>::CTAS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                const __grid_constant__ CUtensorMap tmapO, GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -1132,7 +1138,7 @@ int launch_gemm_bn(Flow& f, const CUtensorMap& ma, const CUtensorMap& mb, const 
     attr_set[f.device & 63] = true;
   }
   const int64_t tiles = ceil_div(p.M, 128);
-  dim3 grid((unsigned)std::min<int64_t>(tiles, std::max(1, kNumSMs / n_tiles_n)), (unsigned)n_tiles_n);
+  dim3 grid((unsigned)std::min<int64_t>(tiles, std::max(1, Cfg::CTAS * kNumSMs / n_tiles_n)), (unsigned)n_tiles_n);
   char key[64];
   snprintf(key, sizeof(key), "tc_gemm_n%d_k%d_e%d", BN, p.num_k_chunks * 64, p.epi);
   // NFCUDA_DBG=<class>: dump the clock64 timeline of CTA 0 for the n-th (NFCUDA_DBG_SKIP) launch of that class
