@@ -1323,7 +1323,10 @@ int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, s
     const bool last = (i + 1 == nd);
     void* abuf = i == 0 ? act0 : acts[i - 1];
     Planes A = planes_of(abuf, n, dp.kin);
-    const int bn = std::min(dp.nf_rows, 256);
+    // a one-chunk contraction (K <= 64) is all epilogue: 64-column tiles run two CTAs per SM whose phases interleave
+    static const int fwd_bn_k64 = getenv("NFCUDA_FWD_BN_K64") ? atoi(getenv("NFCUDA_FWD_BN_K64")) : 256;
+    int bn = std::min(dp.nf_rows, 256);
+    if (dp.kin_p == 64 && dp.nf_rows % fwd_bn_k64 == 0 && fwd_bn_k64 < bn) bn = fwd_bn_k64;
     const int n_tiles_n = dp.nf_rows / bn;
     CUtensorMap ma, mb;
     NF_TRY(make_map_kmajor(st, A.p, n, A.ld, A.plane_elems(), 128, &ma));
@@ -1406,7 +1409,12 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
       }
     }
     if (i > 0 || G) {  // data gradient (skipped for the first Dense when nobody needs d/d(conditioner input))
-      const int bn = std::min(dp.nd_rows, 256);
+      // a one-chunk contraction (K <= 64) is all epilogue: narrower tiles run two CTAs per SM whose phases interleave
+      static const int dgrad_bn_k64 = getenv("NFCUDA_DGRAD_BN_K64") ? atoi(getenv("NFCUDA_DGRAD_BN_K64")) : 64;   // measured (C3, 2^20): 256: 0.388 ms, 128: 0.350, 64: 0.324, 32: 0.487
+      int bn = std::min(dp.nd_rows, 256);
+      if (dp.nout_p == 64 && dp.nd_rows % dgrad_bn_k64 == 0 && dgrad_bn_k64 < bn) bn = dgrad_bn_k64;
+      static const int dgrad_bn_big = getenv("NFCUDA_DGRAD_BN_BIG") ? atoi(getenv("NFCUDA_DGRAD_BN_BIG")) : 256;
+      if (dp.nout_p > 64 && dp.nd_rows % dgrad_bn_big == 0 && dgrad_bn_big < bn) bn = dgrad_bn_big;
       const int n_tiles_n = dp.nd_rows / bn;
       CUtensorMap ma, mb;
       NF_TRY(make_map_kmajor(st, Gp.p, n, Gp.ld, Gp.plane_elems(), 128, &ma));
