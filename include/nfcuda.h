@@ -222,6 +222,11 @@ NF_API int nf_spline_bins(nf_flow_t flow, const void* theta_host, int64_t N, con
 NF_API int nf_rqs_bin_search(int dtype, const void* knots_host, const void* v_host, int64_t M, int K, int32_t* bins_out);
 /* One Dense layer Y[n,N] = X[n,K] Wt[K,N] + b through the tcgen05 forward GEMM (terms: 1 or 3 fp16 products). */
 NF_API int nf_tc_gemm_test(int64_t n, int K, int N, const float* X, const float* Wt, const float* b, int terms, float* Y);
+/* Host-side test hook (no device needed): the per-network item schedule of the two-team fused coupling kernel for a hidden
+ * width of n_chunks x 64 columns, accumulation chains of `chain` K chunks, n_hoist first-Dense chunks issued in the previous
+ * network's tail and third-Dense slabs `delay` items after their chunk's last slab.  Item bytes: see csrc/fused_coupling.cuh.
+ * Returns the number of items (written up to cap) or a negative error code. */
+NF_API int nf_fused_schedule(int n_chunks, int chain, int n_hoist, int delay, unsigned char* items_out, int cap);
 /* Number of kernels launched by this thread's library calls since the last reset (bench.py `gpu_launches`). */
 NF_API int64_t nf_launch_count(int reset);
 /* ---- multi-GPU data parallelism (the call that replaces reference src/optimize.jl:86 on G devices) ----------

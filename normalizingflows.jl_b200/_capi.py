@@ -66,6 +66,7 @@ SIGNATURES = {
     "nf_spline_bins": (_i, [_vp, _vp, _i64, _vp, C.POINTER(C.c_int32)]),
     "nf_rqs_bin_search": (_i, [_i, _vp, _vp, _i64, _i, C.POINTER(C.c_int32)]),
     "nf_tc_gemm_test": (_i, [_i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "nf_fused_schedule": (_i, [_i, _i, _i, _i, C.POINTER(C.c_ubyte), _i]),
     "nf_launch_count": (_i64, [_i]),
     "nf_set_option": (_i, [C.c_char_p, _i]),
     "nf_comm_init_all": (_i, [C.POINTER(_vp), _i, C.POINTER(_i)]),

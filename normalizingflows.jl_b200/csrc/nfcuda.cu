@@ -1012,6 +1012,13 @@ int nf_tc_gemm_test(int64_t n, int K, int N, const float* X, const float* Wt, co
   return tc_gemm_selftest(n, K, N, X, Wt, b, terms, Y);
 }
 
+int nf_fused_schedule(int n_chunks, int chain, int n_hoist, int delay, unsigned char* items_out, int cap) {
+  NF_REQUIRE(items_out && cap > 0 && n_chunks >= 1 && n_chunks <= 4 && (chain == 1 || chain == 2) && n_hoist >= std::min(chain, n_chunks) &&
+                 delay >= 1,
+             "nf_fused_schedule: n_chunks in 1..4, chain in {1, 2}, n_hoist >= min(chain, n_chunks), delay >= 1");
+  return tc_fused_schedule(n_chunks, chain, std::min(n_hoist, n_chunks), delay, items_out, cap);
+}
+
 int64_t nf_launch_count(int reset) {
   const int64_t c = g_launch_count;
   if (reset) g_launch_count = 0;

@@ -1574,6 +1574,10 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
   return NF_OK;
 }
 
+int tc_fused_schedule(int nch, int slab, int n_hoist, int delay, unsigned char* out, int cap) {
+  return fused_build_schedule(out, cap, nch, delay, slab, n_hoist);
+}
+
 // Test hook: Y[n, N] = X[n, K] * Wt[K, N] + b through the tcgen05 forward GEMM (one Dense, no activation).
 int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* Wt_host, const float* b_host, int terms,
                      float* Y_host) {

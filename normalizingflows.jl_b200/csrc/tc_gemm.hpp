@@ -30,5 +30,7 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
 void tc_release(Flow& f);
 int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* Wt_host, const float* b_host, int terms,
                      float* Y_host);
+// host-side item schedule of the two-team fused coupling kernel (fused_coupling.cuh: fused_build_schedule); no device needed
+int tc_fused_schedule(int nch, int slab, int n_hoist, int delay, unsigned char* out, int cap);
 
 }  // namespace nf
