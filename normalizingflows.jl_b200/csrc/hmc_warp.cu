@@ -11,8 +11,8 @@
 // leapfrog_backward in elementwise_impl.cuh).  Per-parameter gradient sums: shared-memory atomics per CTA, one partial row per CTA,
 // finished in double by hw_finalize_kernel (layer-table layout and chain rules identical to ew_prep_body / ew_finalize_body).
 //
-// Forward direction: ELBO value / gradient, per-sample terms, transform + logdet.  Inverse direction: transform, logdet and the
-// log-density head (logpdf); the gradient of the forward-KL objective is not built for flows this large.
+// Forward direction: ELBO value / gradient, per-sample terms, transform + logdet.  Inverse direction: transform, logdet, the
+// log-density head (logpdf) and the gradient of the forward-KL objective (reference src/objectives/loglikelihood.jl:26-33).
 #include "flow.hpp"
 #include "targets.cuh"
 
@@ -469,13 +469,17 @@ __global__ void __launch_bounds__(HW_THREADS) hw_flow_kernel(HwArgs<T> a) {
 }
 
 // Inverse direction: x = T^{-1}(y) (theta order: the first layer's inverse first), logdet of the inverse, and -- with HW_TARGET --
-// the log-density head  log q(y) = logpdf(q0, x) + logdet_inv  (reference src/objectives/loglikelihood.jl:26-33 evaluates it;
-// its gradient is not built for flows this large).  LeapFrog^{-1} is the same map with -eps (demo_hamiltonian_flow.jl:63-82).
+// the log-density head  log q(y) = logpdf(q0, x) + logdet_inv and its gradient (reference src/objectives/loglikelihood.jl:26-33).  LeapFrog^{-1} is the same map with -eps (demo_hamiltonian_flow.jl:63-82).
 template <typename T>
 __global__ void __launch_bounds__(HW_THREADS) hw_inv_kernel(HwArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char hw_smem[];
+  T* s_acc = reinterpret_cast<T*>(hw_smem);      // [L][2 d] (HW_GRAD only)
   __shared__ double s_e[HW_THREADS / 32];
   const int L = a.L, d = a.d, h = d / 2, str = 4 + 2 * d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool want_grad = a.flags & HW_GRAD;
+  if (want_grad) for (int i = tid; i < L * 2 * d; i += HW_THREADS) s_acc[i] = 0;
+  __syncthreads();
   double obj_local = 0;
   const int64_t nw = (int64_t)gridDim.x * (HW_THREADS / 32);
   for (int64_t j = (int64_t)blockIdx.x * (HW_THREADS / 32) + warp; j < a.N; j += nw) {
@@ -519,13 +523,19 @@ __global__ void __launch_bounds__(HW_THREADS) hw_inv_kernel(HwArgs<T> a) {
     if ((a.flags & HW_WRITE_LD) && lane == 0) a.ld_out[j] = ld;
     if (!(a.flags & HW_TARGET)) continue;
     T q = 0;
+    T gx[HW_NPL], gv[HW_NPL];                      // d log q0 / d x0
 #pragma unroll
     for (int i = 0; i < HW_NPL; ++i) {
       const int k = 4 * lane + i;
+      gx[i] = 0; gv[i] = 0;
       if (k >= h) continue;
-      T ux = x[i], uv = v[i];
-      if (a.base) { ux = (ux - a.base[k]) / a.base[d + k]; uv = (uv - a.base[h + k]) / a.base[d + h + k]; }
+      T ux = x[i], uv = v[i], isx = 1, isv = 1;
+      if (a.base) {
+        isx = 1 / a.base[d + k]; isv = 1 / a.base[d + h + k];
+        ux = (ux - a.base[k]) * isx; uv = (uv - a.base[h + k]) * isv;
+      }
       q += ux * ux + uv * uv;
+      gx[i] = -ux * isx; gv[i] = -uv * isv;
     }
     q = warp_sum(q);
     const T term = a.base_c0 - q / 2 + ld;
@@ -533,7 +543,45 @@ __global__ void __launch_bounds__(HW_THREADS) hw_inv_kernel(HwArgs<T> a) {
       obj_local += (double)term;
       if (a.flags & HW_WRITE_TERMS) a.terms_out[j] = term;
     }
+    if (!want_grad) continue;
+    // ---- backward sweep: layers L-1 .. 0, walking the forward maps from x0 back to y (ew_inv_flow_kernel's scheme) ----
+    for (int l = L - 1; l >= 0; --l) {
+      const T* e = a.table + (size_t)l * str;
+      const T* v0 = e + 4;
+      const T* v1 = e + 4 + d;
+      T* acc = s_acc + (size_t)l * 2 * d;
+      const int kind = a.kinds[l];
+      if (kind == NF_LEAPFROG) {                    // the inverse applied the map with -eps: d/d(eps) = -d/d(-eps)
+        T eps[HW_NPL], ge[HW_NPL];
+#pragma unroll
+        for (int i = 0; i < HW_NPL; ++i) { const int k = 4 * lane + i; eps[i] = k < h ? -v0[k] : T(0); ge[i] = 0; }
+        hw_leapfrog_backward<T>(a.sp, x, v, gx, gv, eps, (int)e[0], ge, lane);
+#pragma unroll
+        for (int i = 0; i < HW_NPL; ++i) { const int k = 4 * lane + i; if (k < h) atomicAdd(&acc[k], -ge[i]); }
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < HW_NPL; ++i) {
+        const int k = 4 * lane + i;
+        if (k >= h) continue;
+        if (kind == NF_SHIFT) {                     // z = y - a
+          atomicAdd(&acc[k], -gx[i]); atomicAdd(&acc[h + k], -gv[i]);
+          x[i] += v0[k]; v[i] += v0[h + k];
+        } else if (kind == NF_SCALE) {              // z = y / a
+          atomicAdd(&acc[k], -gx[i] * x[i] * v1[k]); atomicAdd(&acc[h + k], -gv[i] * v[i] * v1[h + k]);
+          gx[i] *= v1[k]; gv[i] *= v1[h + k];
+          x[i] *= v0[k]; v[i] *= v0[h + k];
+        } else {                                    // NF_MOMENTUM_AFFINE: rho_in = (rho_out - b) / a
+          gv[i] /= v1[h + k];
+          atomicAdd(&acc[h + k], -gv[i]); atomicAdd(&acc[d + h + k], -gv[i] * v[i]);
+          v[i] = v[i] * v1[h + k] + v0[h + k];
+        }
+      }
+    }
   }
+  __syncthreads();
+  if (a.gpart && want_grad)
+    for (int i = tid; i < L * 2 * d; i += HW_THREADS) a.gpart[(size_t)blockIdx.x * L * 2 * d + i] = s_acc[i];
   if (a.epart) {
     if (lane == 0) s_e[warp] = obj_local;
     __syncthreads();
@@ -549,7 +597,7 @@ __global__ void __launch_bounds__(HW_THREADS) hw_inv_kernel(HwArgs<T> a) {
 template <typename T>
 __global__ void hw_finalize_kernel(const T* __restrict__ theta, const EwLayerMeta* __restrict__ meta, int L, int d,
                                    const T* __restrict__ gpart, const double* __restrict__ epart, int nblocks, int64_t N, int64_t P,
-                                   int want_grad, double* __restrict__ gsum) {
+                                   int want_grad, int inverse, double* __restrict__ gsum) {
   const int l = blockIdx.x, h = d / 2;
   if (l == 0 && threadIdx.x == 0 && epart) {
     double e = 0;
@@ -568,10 +616,10 @@ __global__ void hw_finalize_kernel(const T* __restrict__ theta, const EwLayerMet
   for (int k = threadIdx.x; k < d; k += blockDim.x) {
     switch (kind) {
       case NF_SHIFT: g[k] = G(k); break;
-      case NF_SCALE: g[k] = G(k) + (double)N / (double)p[k]; break;
+      case NF_SCALE: g[k] = G(k) + (inverse ? -1.0 : 1.0) * (double)N / (double)p[k]; break;
       case NF_MOMENTUM_AFFINE:
         if (k < h) g[k] = G(h + k);
-        else g[k] = G(d + k) + (double)N / (double)p[k];
+        else g[k] = G(d + k) + (inverse ? -1.0 : 1.0) * (double)N / (double)p[k];
         break;
       case NF_LEAPFROG:
         if (k < h) g[k] = G(k) * exp((double)p[k]);
@@ -637,7 +685,7 @@ int hmc_warp_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, c
   f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
   if (gsum_dev) {
-    hw_finalize_kernel<T><<<L, 128, 0, f.stream>>>((const T*)theta_dev, f.d_ew_meta, L, d, gpart, epart, grid, N, f.P, want_grad ? 1 : 0, gsum_dev);
+    hw_finalize_kernel<T><<<L, 128, 0, f.stream>>>((const T*)theta_dev, f.d_ew_meta, L, d, gpart, epart, grid, N, f.P, want_grad ? 1 : 0, 0, gsum_dev);
     NF_LAUNCH_CHECK();
   }
   return NF_OK;
@@ -646,15 +694,21 @@ int hmc_warp_run(Flow& f, const Target* tgt, const void* theta_dev, int64_t N, c
 template <typename T>
 int hmc_warp_inverse(Flow& f, const void* theta_dev, int64_t N, const void* y_dev, bool head, bool want_grad, void* x_out, void* ld_out,
                      void* terms_out, double* gsum_dev) {
-  if (want_grad) {
-    set_error("Hamiltonian flows with dim %d: the gradient of the inverse direction (forward-KL) is built for dim a power of two <= 64 only", f.dim);
+  const int L = (int)f.layers.size(), d = f.dim;
+  const size_t smem = want_grad ? (size_t)L * 2 * d * sizeof(T) : 16;
+  if (smem > 200 * 1024) {
+    set_error("Hamiltonian flow with %d layers over dim %d needs %zu B of shared memory for its gradient sums (limit 200 KiB)", L, d, smem);
     return NF_ERR_UNSUPPORTED;
   }
-  const int L = (int)f.layers.size(), d = f.dim;
-  const int grid = (int)std::min<int64_t>(ceil_div(N, (int64_t)(HW_THREADS / 32)), (int64_t)kNumSMs * 4);
+  NF_CUDA(cudaFuncSetAttribute(hw_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int max_blocks = 0;
+  NF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, hw_inv_kernel<T>, HW_THREADS, smem));
+  if (max_blocks < 1) max_blocks = 1;
+  const int grid = (int)std::min<int64_t>(ceil_div(N, (int64_t)(HW_THREADS / 32)), (int64_t)kNumSMs * std::min(max_blocks, 4));
   T* table = (T*)f.ws_alloc((size_t)L * (4 + 2 * d) * sizeof(T));
+  T* gpart = want_grad ? (T*)f.ws_alloc((size_t)grid * L * 2 * d * sizeof(T)) : nullptr;
   double* epart = (double*)f.ws_alloc((size_t)grid * sizeof(double));
-  if (!table || !epart) return NF_ERR_OOM;
+  if (!table || !epart || (want_grad && !gpart)) return NF_ERR_OOM;
   hw_prep_kernel<T><<<L, 128, 0, f.stream>>>((const T*)theta_dev, f.d_ew_meta, L, d, table);
   NF_LAUNCH_CHECK();
   HwArgs<T> a{};
@@ -663,14 +717,16 @@ int hmc_warp_inverse(Flow& f, const void* theta_dev, int64_t N, const void* y_de
   a.base_c0 = (T)f.base_c0;
   if (f.score_target) a.sp = f.score_target->params<T>();
   a.y_out = (T*)x_out; a.ld_out = (T*)ld_out; a.terms_out = (T*)terms_out;
-  a.epart = epart; a.N = N; a.L = L; a.d = d;
-  a.flags = (head ? HW_TARGET : 0) | (x_out ? HW_WRITE_Y : 0) | (ld_out ? HW_WRITE_LD : 0) | (terms_out ? HW_WRITE_TERMS : 0);
+  a.gpart = gpart; a.epart = epart; a.N = N; a.L = L; a.d = d;
+  a.flags = ((head || want_grad) ? HW_TARGET : 0) | (want_grad ? HW_GRAD : 0) | (x_out ? HW_WRITE_Y : 0) | (ld_out ? HW_WRITE_LD : 0) |
+            (terms_out ? HW_WRITE_TERMS : 0);
   f.prof.begin("hmc_warp_inverse", f.stream);
-  hw_inv_kernel<T><<<grid, HW_THREADS, 0, f.stream>>>(a);
+  hw_inv_kernel<T><<<grid, HW_THREADS, smem, f.stream>>>(a);
   f.prof.end(f.stream);
   NF_LAUNCH_CHECK();
   if (gsum_dev) {
-    hw_finalize_kernel<T><<<1, 32, 0, f.stream>>>((const T*)theta_dev, f.d_ew_meta, 0, d, nullptr, epart, grid, N, f.P, 0, gsum_dev);
+    hw_finalize_kernel<T><<<want_grad ? L : 1, 128, 0, f.stream>>>((const T*)theta_dev, f.d_ew_meta, want_grad ? L : 0, d, gpart, epart, grid, N,
+                                                                   f.P, want_grad ? 1 : 0, 1, gsum_dev);
     NF_LAUNCH_CHECK();
   }
   return NF_OK;

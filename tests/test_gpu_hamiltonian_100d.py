@@ -153,3 +153,26 @@ def test_hamiltonian_100d_train_flow(gpu, on_device):
     assert np.abs(trained.theta - flow.theta).max() > 0
     v1, _ = nf.api._elbo_impl(trained, jt, 512, want_grad=True, seed=11)
     assert v1 > v0, (v0, v1)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("h,n_data", [(100, 256), (33, 50)], ids=["h100", "h33"])
+def test_hamiltonian_large_loglikelihood_grad(gpu, h, n_data, dtype):
+    """Forward-KL objective (reference src/objectives/loglikelihood.jl:26-33) and its gradient through the inverse direction."""
+    import ctypes as C
+    nf = gpu
+    tgt = O.synthetic_logreg(h, n_data)
+    of = _flow(tgt, 3, 2, dtype)
+    of64 = _flow(tgt, 3, 2, np.float64)
+    of64.set_theta(of.theta().double())
+    gf = gpu_flow(nf, of, dtype)
+    rng = np.random.Generator(np.random.PCG64(11))
+    xs = (0.7 * rng.standard_normal((60, 2 * h))).astype(dtype)
+    v64, g64 = O.loglik_value_and_grad(of64, of64.theta(), torch.from_numpy(xs).double())
+    K = nf._capi
+    val = C.c_double()
+    g = np.empty(gf.theta.size, dtype=dtype)
+    K.check(K.lib().nf_loglik_value_and_grad(gf.handle(), K.ptr(gf.theta), xs.shape[0], K.ptr(xs), 1.0, C.byref(val), K.ptr(g)))
+    tv, tg = (1e-9, 1e-7) if dtype == np.float64 else (1e-5, 1e-4)
+    assert abs(val.value - v64) <= tv * max(abs(v64), 1.0), (val.value, v64)
+    assert rel_err(g, g64) <= tg, rel_err(g, g64)
