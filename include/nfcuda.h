@@ -71,7 +71,7 @@ typedef enum nf_layer_kind {
   NF_SCALE           = 6,   /* theta: a(d) */
   /* Hamiltonian flow on z = [x, rho], dim = 2h (reference example/demo_hamiltonian_flow.jl).  h a power of two <= 32 (<= 8 with the
    * logistic-regression score): fused one-thread-per-sample kernels, every entry point.  Any h <= 128 (BASELINE config 5: h = 100):
-   * warp-per-sample kernels -- flows of Shift / Scale / these two kinds, LogReg / Funnel / DiagNormal scores, joint target;
+   * warp-per-sample kernels -- flows of Shift / Scale / these two kinds, LogReg / Funnel / Banana / DiagNormal scores, joint target;
    * both objectives (value + gradient), terms, forward, inverse, logpdf, sampling: */
   NF_MOMENTUM_AFFINE = 7,   /* Stacked((identity, Shift(b) ∘ Scale(a)), [1:h, h+1:2h]) (:94-99); theta: b(h), a(h) */
   NF_LEAPFROG        = 8    /* LeapFrog bijector (:27-91), logdet 0; theta: log_eps(h) (`@functor LeapFrog (logϵ,)` :39) */

@@ -137,6 +137,21 @@ __device__ __forceinline__ T hw_score(const TargetParams<T>& tp, const T (&x)[HW
       q = warp_sum(q); lp = warp_sum(lp);
       return tp.c0 + lp - q * is2 / 2;
     }
+    case NF_TARGET_BANANA: {   // banana.jl:77-83: b = p0, var = p1 (coordinates 0 and 1 live in lane 0)
+      const T b = tp.p0, vr = tp.p1;
+      const T u1 = __shfl_sync(0xffffffffu, x[0], 0);
+      const T u2 = __shfl_sync(0xffffffffu, x[1], 0) + b * u1 * u1 - vr * b;
+      T q = 0;
+#pragma unroll
+      for (int i = 0; i < HW_NPL; ++i) {
+        const int k = 4 * lane + i;
+        g[i] = 0;
+        if (k >= 2 && k < h) { q += x[i] * x[i]; g[i] = -x[i]; }
+      }
+      q = warp_sum(q) + u1 * u1 / vr + u2 * u2;
+      if (lane == 0) { g[0] = -u1 / vr - u2 * (2 * b * u1); g[1] = -u2; }
+      return tp.c0 - q / 2;
+    }
     case NF_TARGET_FUNNEL: {   // neal_funnel.jl:54-72: mu = p0, sigma = p1
       const T mu = tp.p0, sg = tp.p1;
       const T x1 = __shfl_sync(0xffffffffu, x[0], 0);
@@ -212,6 +227,16 @@ __device__ __forceinline__ void hw_hvp(const TargetParams<T>& tp, const T (&x)[H
           for (int i = 0; i < HW_NPL; ++i) out[i] += cv * xk[rr][i];
         }
       }
+      return;
+    }
+    case NF_TARGET_BANANA: {
+      const T b = tp.p0, vr = tp.p1;
+      const T x0 = __shfl_sync(0xffffffffu, x[0], 0), x1 = __shfl_sync(0xffffffffu, x[1], 0);
+      const T u2 = x1 + b * x0 * x0 - vr * b;
+      const T h11 = -1 / vr - 2 * b * u2 - 4 * b * b * x0 * x0, h12 = -2 * b * x0;
+#pragma unroll
+      for (int i = 0; i < HW_NPL; ++i) { const int k = 4 * lane + i; out[i] = (k >= 2 && k < h) ? -w[i] : T(0); }
+      if (lane == 0) { const T w0 = w[0], w1 = w[1]; out[0] = h11 * w0 + h12 * w1; out[1] = h12 * w0 - w1; }
       return;
     }
     case NF_TARGET_FUNNEL: {
@@ -628,7 +653,7 @@ __global__ void hw_finalize_kernel(const T* __restrict__ theta, const EwLayerMet
   }
 }
 
-bool hw_target_ok(int kind) { return kind == NF_TARGET_LOGREG || kind == NF_TARGET_FUNNEL || kind == NF_TARGET_DIAG_NORMAL; }
+bool hw_target_ok(int kind) { return kind == NF_TARGET_LOGREG || kind == NF_TARGET_FUNNEL || kind == NF_TARGET_DIAG_NORMAL || kind == NF_TARGET_BANANA; }
 
 }  // namespace
 

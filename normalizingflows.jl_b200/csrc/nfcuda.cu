@@ -702,7 +702,7 @@ static int check_target(const Flow& f, const Target* t) {
   if (t->joint && !(f.all_elementwise && f.dim == 2 * (t->dim / 2) &&
                     (((f.dim & (f.dim - 1)) == 0 && f.dim <= 64) || hmc_warp_qualifies(f, t)))) {
     set_error("joint [x, rho] targets are implemented for elementwise / Hamiltonian flows with dim a power of two <= 64, and for "
-              "flows of Shift / Scale / momentum-affine / LeapFrog layers with dim = 2h, h <= 128 (LogReg, Funnel, DiagNormal targets)");
+              "flows of Shift / Scale / momentum-affine / LeapFrog layers with dim = 2h, h <= 128 (LogReg, Funnel, Banana, DiagNormal targets)");
     return NF_ERR_UNSUPPORTED;
   }
   return NF_OK;

@@ -52,10 +52,13 @@ def test_hamiltonian_logreg_large(gpu, h, n_data, nlayers, nsteps, N, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
-def test_hamiltonian_funnel_large(gpu, dtype):
-    """The demo's own target family (Funnel) at a size only the warp-per-sample kernel takes (h = 40, not a power of two)."""
+@pytest.mark.parametrize("tname", ["funnel", "banana", "diag"])
+def test_hamiltonian_funnel_large(gpu, tname, dtype):
+    """The demo's own target families at a size only the warp-per-sample kernel takes (h = 40, not a power of two)."""
     nf = gpu
-    tgt = O.Funnel(40, -2.0, 3.0)
+    rng = np.random.Generator(np.random.PCG64(3))
+    tgt = {"funnel": O.Funnel(40, -2.0, 3.0), "banana": O.Banana(40, 0.3, 4.0),
+           "diag": O.DiagNormal(rng.standard_normal(40), rng.uniform(0.5, 1.5, 40))}[tname]
     of = _flow(tgt, 5, 3, dtype, seed=2, eps=0.05)
     jt = O.JointTarget(tgt)
     xs = z0(64, 80, dtype, seed=4)
