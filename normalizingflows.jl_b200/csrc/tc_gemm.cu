@@ -577,6 +577,7 @@ struct WgradParams {
   const float* g_meta;
   double* gW;         // gsum + w_off (+ sub-block offset), row-major with row stride ldw
   int ldw;            // row stride of gW = nout of the whole Dense (kin / nout above are the sizes of this sub-block)
+  double* colsum;     // optional: bias gradient = column sums of G over the samples (gsum + b_off + sub-block offset)
 };
 
 template <int BN> struct WgradCfg {
@@ -611,7 +612,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmapX);
     tma_prefetch_desc(&tmapG);
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // with colsum the epilogue warps that own a 64-column block of G read every stage too
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1 + (p.colsum ? (BN / 64 < 4 ? BN / 64 : 4) : 0)); }
     mbar_init(done_bar, 1);
     fence_barrier_init();
   }
@@ -669,6 +671,58 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant
     }
   } else {
     const bool any = (int64_t)blockIdx.x < num_chunks;
+    // ---- bias gradient while the MMAs run: these warps are idle until the accumulator is complete, and the G planes of every
+    // stage are already in shared memory.  Warp w owns 64-column block w of G ([32 samples][128 B], SWIZZLE_128B: 16-byte chunk
+    // index ^ (row & 7)).  Lane l reads 16-byte chunk l & 7 (8 columns) of rows (l >> 3) + 4 i: eight independent fp32 sums per
+    // stage, double across stages, one cross-lane reduction at the very end.
+    if (p.colsum && (warp - 2) < BN / 64) {
+      const int cb = warp - 2;
+      const uint32_t chunk = (uint32_t)lane & 7u, rbase = (uint32_t)lane >> 3;
+      double acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+      uint32_t it = 0;
+      for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        if (lane == 0) mbar_wait(full_bar(s), ph);
+        __syncwarp();
+        const uint32_t gb = base + s * Cfg::STAGE + 2 * Cfg::A_PLANE + cb * Cfg::BLK;
+        float sum[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum[q] = 0.f;
+        for (int pl = 0; pl < (p.terms > 1 ? 2 : 1); ++pl) {
+#pragma unroll
+          for (int i = 0; i < Cfg::KS / 4; ++i) {
+            const uint32_t r = rbase + 4u * i;
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(gb + pl * Cfg::B_PLANE + r * 128u + ((chunk ^ (r & 7u)) << 4)));
+            const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+              sum[2 * q] += fv.x; sum[2 * q + 1] += fv.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += (double)sum[q];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
+      }
+      if (any) {
+        const double dg = 1.0 / (double)p.g_meta[0];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          double v = acc[q];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          const int col = cb * 64 + (int)chunk * 8 + q;
+          if (lane < 8 && col < p.nout) atomicAdd(&p.colsum[col], v * dg);
+        }
+      }
+    }
     if (any) {
       const int quarter = warp & 3;
       const float descale = 1.f / (p.x_meta[0] * p.g_meta[0]);
@@ -1372,6 +1426,11 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
   const int nd = md.n_dense();
   void* gbuf = scratch0;
   void* gnext = scratch1;
+  // Bias gradients as column sums of G inside the weight-gradient kernel (its epilogue warps idle during the K loop) instead of
+  // in the dgrad epilogue: OFF by default.  Measured (C3, 2^20): the dgrad GEMMs gain 1.4 ms per step (K=256: 0.446 -> 0.406 ms,
+  // K=64: 0.320 -> 0.271 ms) but the weight-gradient kernels lose 3-4 ms (256x256: 0.393 -> 0.490 ms) -- their MMAs read both
+  // MN-major operands from shared memory at ~75 % of its bandwidth, and the extra 32 KB of reads per stage do not fit.
+  static const bool wgrad_colsum = getenv("NFCUDA_WGRAD_COLSUM") && atoi(getenv("NFCUDA_WGRAD_COLSUM")) != 0;
   // gradient w.r.t. the last pre-activation -> split planes
   // ... and, in the same pass, the bias gradient of the last Dense (column sums of the fp32 gradient)
   NF_TRY(split_into_planes(f, st, g_last, md.dims[nd], nullptr, md.dims[nd], n, gbuf, g_last_amax,
@@ -1399,6 +1458,10 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
           wp.n = n; wp.kin = std::min(256, dp.kin - i0); wp.nout = std::min(256, dp.nout - j0); wp.mt = mt; wp.terms = terms;
           wp.gW = gsum + dp.w_off + (int64_t)i0 * dp.nout + j0; wp.ldw = dp.nout;
           wp.x_meta = x_meta; wp.g_meta = g_meta;
+          // bias gradient of this Dense = column sums of its pre-activation gradient G: summed here from the G stages (idle
+          // epilogue warps) instead of in the epilogue of the dgrad GEMM that produced G; the last Dense's comes from
+          // split_into_planes above
+          wp.colsum = (wgrad_colsum && i0 == 0 && i < nd - 1) ? gsum + dp.b_off + j0 : nullptr;
           switch (gl) {
             case 64: NF_TRY(launch_wgrad_bn<64>(f, mx, mg, wp)); break;
             case 128: NF_TRY(launch_wgrad_bn<128>(f, mx, mg, wp)); break;
@@ -1434,7 +1497,7 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
         p.out_hi = O.p; p.out_lo = O.p + O.plane_elems(); p.out_ld = O.ld;
         p.mask_bits = X.bits(); p.mask_ld = X.bits_ld();
         const DensePrep& below = st->preps[st->index[li][m][i - 1]];
-        p.colsum_out = gsum + below.b_off; p.colsum_n = below.nout;   // bias gradient of Dense i-1, fused
+        if (!wgrad_colsum) { p.colsum_out = gsum + below.b_off; p.colsum_n = below.nout; }   // bias gradient of Dense i-1, fused (A/B path)
       } else {
         p.epi = EPI_SCATTER_ADD; p.n_store = dp.kin; p.G = G; p.ldg = f.dim; p.idx = Ld.d_idx2;
       }
