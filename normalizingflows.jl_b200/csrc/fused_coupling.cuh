@@ -120,6 +120,11 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 __device__ __forceinline__ void epi_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// producer side of a named barrier: non-blocking arrival (the consumers bar.sync on the same id / count)
+__device__ __forceinline__ void epi_bar_arrive(int id, int nthreads) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 struct FusedNet {
   const float* w_sc[3];     // per-Dense scalars {weight scale, max row L1, max col L1, max |b|}
@@ -185,7 +190,7 @@ struct FusedCfg {
   static constexpr int OFF_LD = OFF_BIAS + 2 * 544 * 4;           // [4 column groups][128 rows] partial logdets (summed in a fixed order)
   static constexpr int OFF_BAR = OFF_LD + 2048;
   static constexpr int N_BARS = 2 * STAGES + 2 /*x full/empty*/ + 2 /*x2 ready/free*/ + 4 /*tfull/tempty*/ + 4 /*tfull3/tempty3*/ +
-                                4 /*h1 ready*/ + 2 /*h2 ready/free*/ + 2 /*s,t staging ready/free*/;
+                                4 /*h1 ready*/ + 2 /*h2 ready/free*/;
   static constexpr int OFF_POS = OFF_BAR + 8 * N_BARS + 16;   // pos[64], pos2[64]
   static constexpr int SMEM = OFF_POS + 512;
   // warp 0 producer, 1 MMA issuer, 2-3 tile warps (conditioner input, coupling arithmetic), 4..19 epilogue
@@ -348,7 +353,6 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
   auto tempty3 = [&](int a) { return bars + 8u * (2 * S + 10 + a); };
   auto h1_ready = [&](int k) { return bars + 8u * (2 * S + 12 + k); };
   const uint32_t h2_ready = bars + 8u * (2 * S + 16), h2_free = bars + 8u * (2 * S + 17);
-  const uint32_t st_ready = bars + 8u * (2 * S + 18), st_free = bars + 8u * (2 * S + 19);
   const uint32_t tmem_slot = bars + 8u * C::N_BARS;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 8 * C::N_BARS);
   float* s_bias = reinterpret_cast<float*>(smem_raw + C::OFF_BIAS);
@@ -381,7 +385,6 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); mbar_init(tfull3(a), 1); mbar_init(tempty3(a), 16); }
     for (int k = 0; k < 4; ++k) mbar_init(h1_ready(k), 8);
     mbar_init(h2_ready, 8); mbar_init(h2_free, 1);
-    mbar_init(st_ready, 16); mbar_init(st_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -650,8 +653,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
       // the tile's rows were read a whole tile ago: bring them back into L2 while the second network finishes
       for (int o = tx * 128; o < rows_here * d * 4; o += 64 * 128)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(xrow0) + o));
-      if (lane == 0) mbar_wait(st_ready, tc & 1);
-      __syncwarp();
+      epi_bar_sync(1, 576);                          // both networks' outputs of this tile are staged (512 epilogue threads arrive)
       if (tx == 0) NF_FDBG(3, 8 * tc + 2);
       // ---- coupling arithmetic: coalesced float4 passes ----
       auto couple4 = [&](const float4 x, int r, int k0, int k1, int k2, int k3) -> float4 {
@@ -693,8 +695,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
         const float sum_s = (s_ld[r] + s_ld[128 + r]) + (s_ld[256 + r] + s_ld[384 + r]);
         if (p.ld) p.ld[row0 + r] += p.inv ? -sum_s : sum_s;
       }
-      epi_bar_sync(3, 64);
-      if (tx == 0) mbar_arrive(st_free);             // the staging tiles may take the next tile's outputs
+      epi_bar_arrive(2, 576);                        // the staging tiles may take the next tile's outputs
       if (tx == 0) NF_FDBG(3, 8 * tc + 3);
     }
     if (p.y_meta) {
@@ -809,8 +810,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) { a[q8] = tanhf(a[q8]); if (g * 8 + q8 < p.c) part += a[q8]; }
         if (tc > 0) {                                // the tile warps are done with the previous tile's staging
-          if (lane == 0) mbar_wait(st_free, (tc - 1) & 1);
-          __syncwarp();
+          epi_bar_sync(2, 576);
         }
         // the tile warps get exp(+-s) (their pass is then one FMA per element); s itself goes straight to the stash
 #pragma unroll
@@ -819,8 +819,7 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
       } else {
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) s_T[rloc * C::ST_LD + g * 8 + q8] = a[q8];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(st_ready);
+        epi_bar_arrive(1, 576);
       }
       float* o = p.net[nt].out;
       if (o && row < p.n) {
