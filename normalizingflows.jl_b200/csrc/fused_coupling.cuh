@@ -154,6 +154,7 @@ struct FusedFwdParams {
   int h_ld;                 // 64 * nch
   float rz[3];
   int dbg_flags;            // experiments (NFCUDA_DBG_FLAGS): 1 skip the hidden-activation stash stores
+  int no_stash;             // 1: no backward pass will follow -- skip every stash store (hidden planes, sign bits, x2 planes, s)
   long long* dbg;           // optional clock64 timeline of CTA 0: [role][512]
   FusedNet net[2];
   // streaming variant: per-network item schedules (fused_build_schedule), MMA / producer order and epilogue order
@@ -637,8 +638,10 @@ fused_affine_fwd_kernel(const __grid_constant__ FusedFwdMaps maps, const __grid_
       if (tx == 0) {
         mbar_arrive(x2_ready);
         mbar_arrive(x_empty);                      // the X buffer is free again: the next tile's rows may land
-        tma_store_3d(&maps.x2, base + C::OFF_X2, 0, (int)r0, 0);     // stash of the x2 planes for the weight-gradient kernel
-        if (p.terms > 1) tma_store_3d(&maps.x2, base + C::OFF_X2 + C::X2_PLANE, 0, (int)r0, 1);
+        if (!p.no_stash) {
+          tma_store_3d(&maps.x2, base + C::OFF_X2, 0, (int)r0, 0);     // stash of the x2 planes for the weight-gradient kernel
+          if (p.terms > 1) tma_store_3d(&maps.x2, base + C::OFF_X2 + C::X2_PLANE, 0, (int)r0, 1);
+        }
       }
     };
     build_x2(0);

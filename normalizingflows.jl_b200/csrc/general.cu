@@ -249,7 +249,7 @@ RqsLaunch rqs_launch_shape(int K, int64_t pairs) {
 
 template <typename T, bool INV>
 int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, int64_t n, const T* Xin, T* Xout, T* ld,
-                   int32_t* bins, const float* amax_in, float* amax_out) {
+                   int32_t* bins, const float* amax_in, float* amax_out, bool stash = true) {
   const int d = f.dim, c = (int)Ld.idx1.size(), cbar = (int)Ld.idx2.size();
   const bool tc = f.mma_mode != NF_MMA_SIMT;
   if (Ld.kind == NF_SHIFT || Ld.kind == NF_SCALE) {
@@ -260,7 +260,7 @@ int coupling_apply(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta, i
   }
   if (tc && amax_in && tc_fused_affine_ok(f, Ld)) {
     // both conditioners, all Dense layers and the coupling arithmetic in one launch (fused_coupling.cuh)
-    return tc_affine_forward_fused(f, Ld, n, (const float*)Xin, (float*)Xout, (float*)ld, b.act0, b.acts, amax_in, amax_out, INV);
+    return tc_affine_forward_fused(f, Ld, n, (const float*)Xin, (float*)Xout, (float*)ld, b.act0, b.acts, amax_in, amax_out, INV, stash);
   }
   if (tc) {
     NF_TRY(tc_gather_split(f, (const float*)Xin, d, Ld.d_idx2, cbar, n, b.act0, amax_in));
@@ -419,7 +419,7 @@ int sweep_forward(Flow& f, Chunk& c, const T* theta, int32_t* bins, int64_t bins
     }
     const bool track = !c.xmeta.empty();
     NF_TRY((coupling_apply<T, false>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, bl, c.xmeta.empty() ? nullptr : c.xmeta[state],
-                                     track ? c.xmeta[state + 1] : nullptr)));
+                                     track ? c.xmeta[state + 1] : nullptr, c.stash)));
     if (!c.xmeta.empty() && !track) c.xmeta[state + 1] = nullptr;   // unknown bound: the next split measures it
     ++state;
   }
@@ -451,7 +451,7 @@ int sweep_inverse(Flow& f, Chunk& c, const T* theta) {
     T* Xout = (T*)c.xout(state);
     const bool track = !c.xmeta.empty();
     NF_TRY((coupling_apply<T, true>(f, Ld, b, theta, c.n, Xin, Xout, (T*)c.ld, nullptr, c.xmeta.empty() ? nullptr : c.xmeta[state],
-                                    track ? c.xmeta[state + 1] : nullptr)));
+                                    track ? c.xmeta[state + 1] : nullptr, c.stash)));
     if (!c.xmeta.empty() && !track) c.xmeta[state + 1] = nullptr;
     ++state;
   }

@@ -1525,7 +1525,7 @@ bool tc_fused_affine_ok(const Flow& f, const LayerDesc& Ld) {
 }
 
 int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float* Xin, float* Xout, float* ld, void* act0,
-                            std::vector<std::vector<void*>>& acts, const float* x_meta, float* y_meta, bool inv) {
+                            std::vector<std::vector<void*>>& acts, const float* x_meta, float* y_meta, bool inv, bool stash) {
   TcState* st = get_state(f);
   NF_REQUIRE(st && x_meta, "fused coupling: missing state / input bound");
   const int li = (int)(&Ld - f.layers.data());
@@ -1569,9 +1569,11 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
         NF_REQUIRE(N.h_meta[i], "tcgen05 path: out of tensor metadata slots");
       }
     }
-    N.out = m == 0 ? (float*)acts[m][2] : nullptr;      // the backward pass needs s (after tanh) only
+    N.out = (m == 0 && stash) ? (float*)acts[m][2] : nullptr;      // the backward pass needs s (after tanh) only
   }
   p.dbg_flags = getenv("NFCUDA_DBG_FLAGS") ? atoi(getenv("NFCUDA_DBG_FLAGS")) : 0;
+  p.no_stash = stash ? 0 : 1;      // sampling / logpdf / plain transforms: nothing will read the stash
+  if (!stash) p.dbg_flags |= 1;
   {
     const int dm = (p.dbg_flags >> 8) & 15, de = (p.dbg_flags >> 12) & 15;
     static const int slab_env = getenv("NFCUDA_FUSED_SLAB") ? atoi(getenv("NFCUDA_FUSED_SLAB")) : 2;

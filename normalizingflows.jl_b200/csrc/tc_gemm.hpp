@@ -26,7 +26,7 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
 // (x2 / hidden planes, sign bits, s) the layer-by-layer path writes, so tc_mlp_backward consumes it unchanged
 bool tc_fused_affine_ok(const Flow& f, const LayerDesc& Ld);
 int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float* Xin, float* Xout, float* ld, void* act0,
-                            std::vector<std::vector<void*>>& acts, const float* x_meta, float* y_meta, bool inv);
+                            std::vector<std::vector<void*>>& acts, const float* x_meta, float* y_meta, bool inv, bool stash = true);
 void tc_release(Flow& f);
 int tc_gemm_selftest(int64_t n, int K, int N, const float* X_host, const float* Wt_host, const float* b_host, int terms,
                      float* Y_host);
