@@ -1,30 +1,38 @@
 // K3f -- fused conditioner of an AffineCoupling (reference src/flows/realnvp.jl:57-110, src/flows/utils.jl:71-100).
 //
-// One persistent CTA per SM carries a 128-sample tile through BOTH conditioner networks (s and t), all three Dense
+// One persistent CTA per SM carries 128-sample tiles through BOTH conditioner networks (s and t), all three Dense
 // layers each, and the coupling arithmetic, without a hidden activation ever visiting HBM as an operand:
 //
 //   X tile (fp32, one 1-D bulk copy) -> x2 = X[:, idx2] split into fp16 hi/lo planes (smem, UMMA K-major)
-//   L1: acc[128 x 64] = x2 W1[chunk]^T        A from smem,  B (weights) streamed by TMA through a 16 KB-stage ring
+//   L1: acc[128 x 64] = x2 W1[chunk]^T        A from smem,  B (weights) streamed by TMA through a 3 x 16 KB ring
 //       epilogue: bias + leakyrelu + hi/lo split -> TMEM (tcgen05.st) as the A operand of L2   (+ stash, see below)
-//   L2: acc[128 x 64] = h1 W2[chunk, slab]^T  A from TMEM (tcgen05.mma .ts form), one K slab of 64 per accumulator,
-//       slabs summed in registers with round-to-nearest adds (the tensor core truncates its fp32 accumulator)
+//   L2: acc[128 x 64] = h1 W2[chunk, K chunks]^T  A from TMEM (tcgen05.mma .ts form); an accumulation chain covers two K
+//       chunks of 64, chains are summed in registers with round-to-nearest adds (the tensor core truncates its fp32
+//       accumulator; rz_compensation removes the remaining bias)
 //       epilogue: bias + leakyrelu + split -> TMEM chunk buffer = A operand of L3
 //   L3: acc[128 x 32] += h2[chunk] W3[:, chunk]^T, drained per slab; s = tanh(.), t = (.)
 //   coupling: y1 = exp(s) x1 + t, logdet += sum(s)   (inverse direction: x1 = (y1 - t) exp(-s), logdet -= sum(s))
 //
-// TMEM (512 columns): [0,128) h1 hi | [128,256) h1 lo | [256,384) two 64-column accumulators |
+// TMEM (512 columns): [0,128) h1 hi | [128,256) h1 lo | [256,384) two 64-column accumulators (one per team) |
 //                     [384,416) h2 chunk hi | [416,448) h2 chunk lo | [448,512) two 32-column L3 accumulators
 // fp16 operands in TMEM are packed two per 32-bit column (element k of row m: lane m, column k/2, half k%2).
 //
-// Warp roles: warp 0 producer (TMA weights, bulk copy of X tiles), warp 1 MMA issuer (one elected thread),
-// warps 2..17 epilogue in TWO TEAMS of eight (TMEM lane quarter = warp % 4).  Team t owns accumulator t and the hidden
-// chunks j with j % 2 == t; inside a team a thread owns 32 of the chunk's 64 columns.  The MMA schedule interleaves the two
-// teams' K loops with team 0 two slabs ahead, so while one team runs the activation / split pass of a finished chunk the
-// tensor pipe works on the other team's slabs and that team drains them (with all sixteen warps in lock step the tensor
-// pipe idled through every activation pass: profiles/r2_fused_fwd_notes.md).
+// Warp roles (640 threads):
+//   warp 0      producer: TMA weight stages in schedule order, bulk copy of the next X tile
+//   warp 1      MMA issuer: walks the schedule with warp-uniform control flow, one elected lane issues (no divisions in the loop)
+//   warps 2-3   tile warps: build the NEXT tile's x2 planes as soon as this tile's first-Dense MMAs are complete, and do the
+//               coupling arithmetic of the finished tile from the staged exp(+-s) / t tiles (rows re-read after an L2 prefetch)
+//   warps 4-19  epilogue in TWO TEAMS of eight (TMEM lane quarter = warp % 4).  Team t owns accumulator t and the hidden chunks
+//               j with j % 2 == t; a thread owns 32 of the chunk's 64 columns.  The schedule alternates the teams' chains, so
+//               one team's activation / split pass runs while the tensor pipe works for the other team.
+// The item schedule (fused_build_schedule, host side) is a STREAM across networks and tiles: the next network's first Dense is
+// issued in this network's tail, the last third-Dense slabs of a network are drained inside the next one.  Hand-overs:
+// mbarriers between the async proxies (TMA, tcgen05) and the warps; two named barriers per tile between the epilogue and the
+// tile warps for the staged network outputs.  Measurements and the reasons for each piece: profiles/r2_fused_fwd_notes.md.
 //
 // What still goes to HBM is the stash the backward pass consumes (same formats as the layer-by-layer path, so
-// tc_mlp_backward works unchanged): x2 planes, h1 / h2 planes + sign bits per network, s (fp32), and the new state.
+// tc_mlp_backward works unchanged): x2 planes, h1 / h2 planes + sign bits per network, s (fp32), and the new state.  Calls
+// that no backward pass follows (sampling, logpdf, value-only objectives) skip every stash store (p.no_stash).
 //
 // This file is included by tc_gemm.cu inside namespace nf { namespace { ... } }.
 
