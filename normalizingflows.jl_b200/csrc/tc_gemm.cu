@@ -1580,8 +1580,13 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
     p.slab = slab_env >= 2 ? 2 : 1;
     static const int hoist_env = getenv("NFCUDA_FUSED_HOIST") ? atoi(getenv("NFCUDA_FUSED_HOIST")) : 4;   // measured: all chunks hoisted 0.271 ms, two 0.277 ms (C3, 2^17)
     p.n_hoist = std::min(h_ld / 64, std::max(hoist_env, p.slab));     // the first chains read chunks 0 .. slab - 1
-    p.n_seq_m = fused_build_schedule(p.seq_m, (int)sizeof(p.seq_m), h_ld / 64, dm ? dm : 4, p.slab, p.n_hoist);
-    p.n_seq_e = fused_build_schedule(p.seq_e, (int)sizeof(p.seq_e), h_ld / 64, de ? de : 6, p.slab, p.n_hoist);
+    // Third-Dense placement: `delay` items after the chunk's last K chunk in the issuer's copy (measured, C3 2^17: 2: 0.259 ms,
+    // 3: 0.263, 4: 0.266), later in the epilogue's copy (4 / 6: same, 9: +3 %).  The issuer's delay must not exceed one turn of
+    // each team (2 x slab items): beyond that the slab sits behind a chain of the OTHER team, whose accumulator that team only
+    // drains after its own activation pass -- which waits for this very slab (h2_free): a cycle (delay 6 hangs).
+    const int dm_eff = std::min(dm ? dm : 2, 2 * p.slab), de_eff = std::min(de ? de : 6, 9);
+    p.n_seq_m = fused_build_schedule(p.seq_m, (int)sizeof(p.seq_m), h_ld / 64, dm_eff, p.slab, p.n_hoist);
+    p.n_seq_e = fused_build_schedule(p.seq_e, (int)sizeof(p.seq_e), h_ld / 64, de_eff, p.slab, p.n_hoist);
     NF_REQUIRE(p.n_seq_m <= (int)sizeof(p.seq_m) && p.n_seq_e == p.n_seq_m, "fused coupling: schedule does not fit");
   }
   p.rz[0] = rz_compensation(cbar, 1, 1);
