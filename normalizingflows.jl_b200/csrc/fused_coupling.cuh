@@ -221,7 +221,7 @@ static_assert(FusedCfg::SMEM <= 232448, "fused coupling: shared memory budget");
 // and the third-Dense slab of a chunk comes `delay` items after the chunk's last slab (its operand needs the chunk's
 // activation pass first).  The epilogue's copy drains the third Dense later still (the two 32-column accumulators decouple
 // them).  Third-Dense slabs stay in chunk order in both copies, everything else is in the same order in both.
-inline int fused_build_schedule(uint8_t* seq, int cap, int nch, int delay, int slab, int n_hoist) {
+inline int fused_build_schedule(uint8_t* seq, int cap, int nch, int delay, int slab, int n_hoist, int lead = 1) {
   std::vector<uint8_t> base;
   int jt[2] = {0, 1}, kt[2] = {0, 0};
   // one accumulation chain (`slab` consecutive K chunks of one hidden chunk) per turn
@@ -238,7 +238,7 @@ inline int fused_build_schedule(uint8_t* seq, int cap, int nch, int delay, int s
   // network) follows them, so its epilogues overlap those chains instead of delaying them.
   int turns = 1;
   take(0);
-  if (slab == 1) { take(0); ++turns; }
+  if (slab == 1 || lead > 1) { take(0); ++turns; }
   int tm = 1;
   bool placed = n_hoist >= nch;
   while (jt[0] < nch || jt[1] < nch) {

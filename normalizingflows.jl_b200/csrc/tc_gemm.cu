@@ -1585,8 +1585,9 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
     // each team (2 x slab items): beyond that the slab sits behind a chain of the OTHER team, whose accumulator that team only
     // drains after its own activation pass -- which waits for this very slab (h2_free): a cycle (delay 6 hangs).
     const int dm_eff = std::min(dm ? dm : 2, 2 * p.slab), de_eff = std::min(de ? de : 6, 9);
-    p.n_seq_m = fused_build_schedule(p.seq_m, (int)sizeof(p.seq_m), h_ld / 64, dm_eff, p.slab, p.n_hoist);
-    p.n_seq_e = fused_build_schedule(p.seq_e, (int)sizeof(p.seq_e), h_ld / 64, de_eff, p.slab, p.n_hoist);
+    const int lead = (p.dbg_flags >> 20) & 1 ? 2 : 1;      // experiment: team 0 two chains ahead instead of one
+    p.n_seq_m = fused_build_schedule(p.seq_m, (int)sizeof(p.seq_m), h_ld / 64, dm_eff, p.slab, p.n_hoist, lead);
+    p.n_seq_e = fused_build_schedule(p.seq_e, (int)sizeof(p.seq_e), h_ld / 64, de_eff, p.slab, p.n_hoist, lead);
     NF_REQUIRE(p.n_seq_m <= (int)sizeof(p.seq_m) && p.n_seq_e == p.n_seq_m, "fused coupling: schedule does not fit");
   }
   p.rz[0] = rz_compensation(cbar, 1, 1);
