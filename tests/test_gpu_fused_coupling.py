@@ -125,3 +125,28 @@ def test_fused_state_is_reproducible(gpu, restore, variant):
             assert np.array_equal(ld1, ld2)
         else:       # four shared-memory atomic adds per row: the order of the partial sums is free
             np.testing.assert_allclose(ld1, ld2, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS), ids=list(VARIANTS))
+def test_fused_no_stash_mode_gives_the_same_state(gpu, restore, variant):
+    """Calls that no backward pass follows (forward, sampling, logpdf) skip every stash store inside the fused kernel: the state and
+    logdet must be bit-identical to the stashing call (`nf_forward_stash`), and the stash of the latter must still drive
+    `nf_backward` to the fused ELBO gradient."""
+    nf = gpu
+    of32, _ = _pair(64, [256, 256], 2)
+    _set(nf, 1, VARIANTS[variant])
+    gf = gpu_flow(nf, of32, np.float32)
+    xs = z0(1500, 64, np.float32, seed=21)
+    y_plain, ld_plain = gf.with_logabsdet_jacobian(xs)              # no stash
+    y_stash, ld_stash = nf.forward_stash(gf, xs)                    # stash kept for nf_backward
+    assert np.array_equal(y_plain, y_stash)
+    if variant == "two_team":
+        assert np.array_equal(ld_plain, ld_stash)
+    else:
+        np.testing.assert_allclose(ld_plain, ld_stash, rtol=1e-5, atol=1e-5)
+    rng = np.random.Generator(np.random.PCG64(4))
+    mu, sg = rng.standard_normal(64), rng.uniform(0.5, 1.5, 64)
+    score = (-(y_stash - mu) / sg ** 2).astype(np.float32)
+    g2 = nf.backward(gf, score / len(xs), np.full(len(xs), 1.0 / len(xs), dtype=np.float32))
+    v, g = nf.api._elbo_impl(gf, nf.DiagNormal(mu, sg), xs, want_grad=True)
+    assert np.linalg.norm(g2 - g) <= 1e-4 * np.linalg.norm(g)
