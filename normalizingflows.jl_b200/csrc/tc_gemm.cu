@@ -1003,6 +1003,14 @@ struct TcState {
 
 inline int pick_bn(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : 256)); }
 inline int pad64(int v) { return (int)round_up(v, 64); }
+// Row stride (elements) of a pair of split planes holding `width` columns.  Tensors of at most 32 columns keep 64-byte rows:
+// the 64-column TMA boxes of the GEMM / weight-gradient loads zero-fill the columns past the tensor map's extent, so the
+// narrow tensors of a spline conditioner ([N, 8] input, [N, 32] hidden layers) and the 32-wide ends of the RealNVP conditioners
+// move half the bytes.  (NFCUDA_NARROW_PLANES=0 restores 128-byte rows: A/B switch.)
+inline int plane_ld(int width) {
+  static const bool narrow = !(getenv("NFCUDA_NARROW_PLANES") && atoi(getenv("NFCUDA_NARROW_PLANES")) == 0);
+  return (narrow && width <= 32) ? 32 : pad64(width);
+}
 
 TcState* get_state(Flow& f) { return (TcState*)f.tc_state; }
 
@@ -1169,7 +1177,8 @@ int make_map_mnmajor(TcState* st, const void* basep, int64_t rows, int64_t cols,
   if (itf != st->maps.end()) { *out = itf->second; return NF_OK; }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return NF_ERR_CUDA; }
-  cuuint64_t gdim[4] = {64, (cuuint64_t)rows, (cuuint64_t)(avail_cols / 64), 2};
+  // planes narrower than one 64-column block (plane_ld): the box still spans 64 columns, the tail is zero-filled
+  cuuint64_t gdim[4] = {(cuuint64_t)std::min<int64_t>(64, cols), (cuuint64_t)rows, (cuuint64_t)std::max<int64_t>(1, avail_cols / 64), 2};
   cuuint64_t gstr[3] = {(cuuint64_t)cols * 2, 128, (cuuint64_t)plane_elems * 2};
   cuuint32_t box[4] = {64, 32, (cuuint32_t)nblocks, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -1275,7 +1284,7 @@ struct Planes {
   uint32_t* bits() const { return reinterpret_cast<uint32_t*>(p + 2 * plane_elems()); }   // [rows_pad, ld/32] sign bits
   int bits_ld() const { return ld / 32; }
 };
-inline Planes planes_of(void* buf, int64_t n, int width) { return Planes{(__half*)buf, round_up(n, 128), pad64(width)}; }
+inline Planes planes_of(void* buf, int64_t n, int width) { return Planes{(__half*)buf, round_up(n, 128), plane_ld(width)}; }
 
 // fp32 [n, ld_src] (optionally gathered columns) -> split planes.  The scale comes from `amax_src` (a bound on
 // max |X| recorded by the producer of X) when given, else from an exact absmax pass.
@@ -1313,7 +1322,7 @@ int split_into_planes(Flow& f, TcState* st, const float* X, int d, const int* d_
 }  // namespace
 
 size_t tc_act_bytes(int64_t n, int width) {
-  const size_t rows = (size_t)round_up(n, 128), ld = (size_t)pad64(width);
+  const size_t rows = (size_t)round_up(n, 128), ld = (size_t)plane_ld(width);
   return rows * ld * 4 /* hi + lo planes */ + rows * (ld / 32) * 4 /* packed sign bits */;
 }
 size_t tc_weight_bytes(const Flow&) { return 0; }
@@ -1453,7 +1462,7 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
           CUtensorMap mx, mg;
           const int mt = (int)ceil_div(xl, 128);
           NF_TRY(make_map_mnmajor(st, X.p + i0, n, X.ld, X.plane_elems(), mt * 2, &mx, xl));
-          NF_TRY(make_map_mnmajor(st, Gp.p + j0, n, Gp.ld, Gp.plane_elems(), gl / 64, &mg, gl));
+          NF_TRY(make_map_mnmajor(st, Gp.p + j0, n, Gp.ld, Gp.plane_elems(), std::max(1, gl / 64), &mg, gl));
           WgradParams wp{};
           wp.n = n; wp.kin = std::min(256, dp.kin - i0); wp.nout = std::min(256, dp.nout - j0); wp.mt = mt; wp.terms = terms;
           wp.gW = gsum + dp.w_off + (int64_t)i0 * dp.nout + j0; wp.ldw = dp.nout;
@@ -1463,7 +1472,7 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
           // split_into_planes above
           wp.colsum = (wgrad_colsum && i0 == 0 && i < nd - 1) ? gsum + dp.b_off + j0 : nullptr;
           switch (gl) {
-            case 64: NF_TRY(launch_wgrad_bn<64>(f, mx, mg, wp)); break;
+            case 32: case 64: NF_TRY(launch_wgrad_bn<64>(f, mx, mg, wp)); break;
             case 128: NF_TRY(launch_wgrad_bn<128>(f, mx, mg, wp)); break;
             case 192: NF_TRY(launch_wgrad_bn<192>(f, mx, mg, wp)); break;
             default: NF_TRY(launch_wgrad_bn<256>(f, mx, mg, wp)); break;
@@ -1519,7 +1528,8 @@ bool tc_fused_affine_ok(const Flow& f, const LayerDesc& Ld) {
   if ((d & 3) || d > 64 || c < 1 || c > 32 || cbar < 1 || cbar > 64) return false;
   for (const MLPDesc& md : Ld.mlps) {
     if (md.n_dense() != 3 || md.dims[0] != cbar || md.dims[3] != c) return false;
-    if (md.dims[1] != md.dims[2] || pad64(md.dims[1]) > 256) return false;
+    // hidden layers of at most 32 columns keep narrow planes (plane_ld), which the fused kernel's stash stores do not write
+    if (md.dims[1] != md.dims[2] || pad64(md.dims[1]) > 256 || plane_ld(md.dims[1]) != pad64(md.dims[1])) return false;
   }
   return Ld.mlps[0].dims[1] == Ld.mlps[1].dims[1];
 }
@@ -1545,7 +1555,7 @@ int tc_affine_forward_fused(Flow& f, const LayerDesc& Ld, int64_t n, const float
   p.Xin = Xin; p.Xout = Xout; p.ld = ld; p.pos = Ld.d_pos; p.pos2 = d_pos2; p.x_meta = x_meta; p.y_meta = y_meta;
   p.h_ld = h_ld; p.h_plane_elems = round_up(n, 128) * h_ld;
   Planes A0 = planes_of(act0, n, cbar);
-  NF_REQUIRE(A0.ld == 64, "fused coupling: conditioner input wider than 64");
+  NF_REQUIRE(A0.ld == 64 || A0.ld == 32, "fused coupling: conditioner input wider than 64");
   NF_TRY(make_map_kmajor(st, A0.p, n, A0.ld, A0.plane_elems(), 128, &maps.x2));
   p.x2_meta = new_meta(st, act0);
   NF_REQUIRE(p.x2_meta, "tcgen05 path: out of tensor metadata slots");
