@@ -371,6 +371,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       const int64_t row = tile * 128 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const int ncols_here = p.n_store - (n0 + cbase);   // columns of this thread's range that matter (warp-uniform)
+      // masked dgrad: the stashed sign bits of this thread's row do not depend on the accumulator -- fetch them before waiting
+      // for it (one exposed global-load latency per 32-column chunk otherwise)
+      uint32_t mask_pre[CPT / 32];
+#pragma unroll
+      for (int c = 0; c < CPT / 32; ++c) {
+        const int col0 = n0 + cbase + c * 32;
+        mask_pre[c] = (p.epi == EPI_PLANES_MASK && row_ok && col0 < p.n_store) ? __ldg(p.mask_bits + row * p.mask_ld + (col0 >> 5)) : 0u;
+      }
       const int nslabs = (nk + p.slab_stages - 1) / p.slab_stages;
       for (int kc = 0; kc < nslabs; ++kc, ++it) {
         const uint32_t acc = it & 1, accph = (it >> 1) & 1;
@@ -415,7 +423,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             }
             if (row_ok && p.out_bits && !(p.dbg_flags & 2)) p.out_bits[row * p.out_bits_ld + (col0 >> 5)] = bits;
           } else {
-            const uint32_t mbits = row_ok ? p.mask_bits[row * p.mask_ld + (col0 >> 5)] : 0u;
+            const uint32_t mbits = mask_pre[c];
             float cs[32];
             const float dpos = row_ok ? ds_out : 0.f, dneg = 0.01f * dpos;   // rows past M contribute exact zeros
 #pragma unroll
