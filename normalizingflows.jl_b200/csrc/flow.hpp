@@ -191,6 +191,9 @@ int hmc_warp_inverse(Flow& f, const void* theta_dev, int64_t N, const void* y_de
                      void* terms_out, double* gsum_dev);
 extern template int hmc_warp_inverse<float>(Flow&, const void*, int64_t, const void*, bool, bool, void*, void*, void*, double*);
 extern template int hmc_warp_inverse<double>(Flow&, const void*, int64_t, const void*, bool, bool, void*, void*, void*, double*);
+extern int g_opt_rqs_planes;    // nf_set_option("rqs_planes", v): spline backward writes the conditioner-output gradient as split planes (1, default),
+                                // as an fp32 matrix plus a split pass (0), or as planes with a deliberately wrong predicted scale so that the
+                                // redo pass runs (2: tests)
 extern int g_opt_hmc_warp;      // nf_set_option("hmc_warp", 1): route every qualifying Hamiltonian flow through hmc_warp.cu (tests)
 extern template int hmc_warp_run<float>(Flow&, const struct Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*);
 extern template int hmc_warp_run<double>(Flow&, const struct Target*, const void*, int64_t, const void*, uint64_t, bool, void*, void*, void*, double*);

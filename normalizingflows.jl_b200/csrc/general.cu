@@ -350,11 +350,46 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
     fused_bias = (rl.threads % cc == 0) && (cc * (3 * Ld.K - 1) <= 4 * rl.threads);
     double* cs = fused_bias ? f.d_gsum + md.b_off[md.n_dense() - 1] : nullptr;
     const T* raw = (const T*)b.acts[0].back();
+    // tcgen05 path: the gradient w.r.t. the conditioner output leaves the spline kernel as the split planes the GEMMs read
+    // (RqsPlanesOut: estimate pass over every 64th tile, speculative pass, commit-or-redo) instead of an fp32 matrix plus a
+    // split pass.  nf_set_option("rqs_planes", 0) / NFCUDA_RQS_PLANES=0: the fp32 form (A/B switch); 2 forces the redo pass (tests).
+    const int ncol = cc * (3 * Ld.K - 1);
+    const bool planes = tc && g_opt_rqs_planes != 0 && fused_bias && (ncol % 2 == 0) && sizeof(T) == 4;
+    RqsPlanesOut<T> po{};
+    if (planes) {
+      TcPlanesOut P;
+      NF_TRY(tc_planes_out(f, c.ga[2], n, ncol, &P));
+      float* est = tc_alloc_meta(f);
+      NF_REQUIRE(est, "tcgen05 path: out of tensor metadata slots");
+      po.hi = (__half*)P.hi; po.plane_elems = P.plane_elems; po.ld = P.ld; po.meta = P.meta; po.est = est;
+      po.gside = gA; po.tile_step = 64;
+      po.headroom = g_opt_rqs_planes == 2 ? 1.0e-6f : kRqsSpecHeadroom;
+      NF_REQUIRE(P.ld <= 4 * rl.threads, "spline backward: planes wider than four column pairs per thread pair");
+    }
 #define NF_RQS_BWD(KM)                                                                                                \
     do {                                                                                                                \
-      auto kern = rqs_bwd_kernel<T, KM, INV>;                                                                           \
-      if (rl.smem > 48 * 1024) NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.smem)); \
-      kern<<<rl.grid, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR, cs, rl.stages); \
+      auto kern = rqs_bwd_kernel<T, KM, INV, 0>;                                                                        \
+      auto kern1 = rqs_bwd_kernel<T, KM, INV, 1>;                                                                       \
+      auto kern2 = rqs_bwd_kernel<T, KM, INV, 2>;                                                                       \
+      auto kern3 = rqs_bwd_kernel<T, KM, INV, 3>;                                                                       \
+      if (rl.smem > 48 * 1024) {                                                                                        \
+        NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.smem));                 \
+        NF_CUDA(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.smem));                \
+        NF_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.smem));                \
+        NF_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rl.smem));                \
+      }                                                                                                                 \
+      if (!planes) {                                                                                                    \
+        kern<<<rl.grid, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, mR, cs, rl.stages, po); \
+      } else {                                                                                                          \
+        const int64_t tiles_all = (n * cc) / rl.threads;                                                                \
+        const unsigned g1 = (unsigned)std::max<int64_t>(1, std::min<int64_t>(rl.grid, ceil_div(tiles_all, po.tile_step))); \
+        po.mode = 1;                                                                                                    \
+        kern1<<<g1, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, nullptr, nullptr, rl.stages, po); \
+        po.mode = 2;                                                                                                    \
+        kern2<<<rl.grid, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, po.meta, cs, rl.stages, po); \
+        po.mode = 3;                                                                                                    \
+        kern3<<<rl.grid, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, po.meta, cs, rl.stages, po); \
+      }                                                                                                                 \
     } while (0)
     f.prof.begin("rqs_bwd", f.stream);
     if (Ld.K <= 8) NF_RQS_BWD(8);
@@ -364,7 +399,7 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
     f.prof.end(f.stream);
 #undef NF_RQS_BWD
     NF_LAUNCH_CHECK();
-    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], (float*)gA, mR, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum, fused_bias));
+    if (tc) NF_TRY(tc_mlp_backward(f, Ld, 0, n, b.act0, b.acts[0], planes ? nullptr : (float*)gA, mR, c.ga[2], c.ga[3], need_input_grad ? (float*)G : nullptr, f.d_gsum, fused_bias));
     else NF_TRY(simt_mlp_backward<T>(f, Ld.mlps[0], theta, n, (const T*)b.act0, b.acts[0], gA, gC, gB, need_input_grad ? G : nullptr, d, Ld.d_idx2, f.d_gsum, fused_bias));
   }
   return NF_OK;

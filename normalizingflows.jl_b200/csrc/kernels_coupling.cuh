@@ -6,6 +6,7 @@
 // (src/flows/realnvp.jl:57-110), a12/a13 NeuralSplineCoupling + MonotonicSplines RQS
 // (src/flows/neuralspline.jl:65-140; App. A.4), a14 PartitionMask, a15 base logpdf, a16 targets.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "targets.cuh"
 
@@ -620,7 +621,9 @@ __global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict_
 template <typename T, int KMAX, bool INV>
 __device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int i, T* __restrict__ G, const T* __restrict__ Vsrc,
                                             const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int K, T B,
-                                            float& run_max) {
+                                            float& run_max, T* __restrict__ gdst, bool store_gin) {
+  // gdst: where d/d(spline input) goes (G[r, idx1[i]] itself for the in-place form; a side buffer for the speculative pass,
+  // which must leave G intact for a possible second pass); store_gin = false: nothing is stored (estimate pass)
   using Nm = Num<T>;
   const int P3 = 3 * K - 1;
   const int j = idx1[i];
@@ -668,7 +671,7 @@ __device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int 
     g_dy += g_s * idx_; g_dx += -g_s * s * idx_;
     const T g_y1 = g_dy; g_y0 -= g_dy;
     const T g_x1 = g_dx; g_x0 -= g_dx;
-    G[r * d + j] = g_in;
+    if (store_gin) *gdst = g_in;
     const T twoB = 2 * B;
     const T rSw = 1 / b.Sw, rSh = 1 / b.Sh;
     const int bk = b.k;
@@ -700,8 +703,71 @@ __device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int 
     for (int k = 1; k < KMAX; ++k) if (k < K)
       row[2 * K + k - 1] = (k == bk - 1) ? gd0 : ((k == bk) ? gd1 : T(0));
   } else {   // identity tails: dy/dx = 1, no parameter gradient; G unchanged
+    if (store_gin && gdst != G + (r * d + j)) *gdst = go;
 #pragma unroll
     for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) row[k] = 0;
+  }
+}
+
+// Optional second output form of the spline backward (Float32 tcgen05 path): the gradient w.r.t. the conditioner output goes
+// straight into the fp16 hi / lo planes the dgrad / weight-gradient GEMMs read, instead of an fp32 matrix that a separate
+// pass would re-read and split.  The planes need ONE power-of-two scale for the whole tensor, i.e. max |gradient| before the
+// first store.  It is predicted: a dry pass over every tile_step-th tile records the maximum of that sample (est), the
+// full pass scales with 2^8 of headroom over it and records the exact maximum, and a third launch either commits
+// (d/d input from the side buffer into G) or -- if the exact maximum would have overflowed the predicted scale -- redoes
+// the tile loop with the exact scale.  Every decision is a pure function of the inputs, so results stay reproducible;
+// a scale up to 2^8 below the ideal one costs nothing visible (error floor 2^-32 of the maximum instead of 2^-40).
+template <typename T> struct RqsPlanesOut {
+  __half* hi;             // hi plane [rows_pad, ld]; lo plane at + plane_elems
+  int64_t plane_elems;
+  int ld;
+  float* meta;            // {scale, bits of the exact max |gradient|} of the planes
+  float* est;             // est[1]: bits of the max over the sampled tiles
+  T* gside;               // [N, c] d/d(spline input) of the speculative pass
+  int mode;               // 0: fp32 graw (no planes); 1: estimate pass; 2: speculative pass; 3: commit or redo
+  int tile_step;          // mode 1: every tile_step-th tile
+  float headroom;         // predicted bound = headroom * sampled maximum (kRqsSpecHeadroom; tests force a redo with a tiny value)
+};
+constexpr float kRqsSpecHeadroom = 256.f;
+__device__ __forceinline__ float rqs_pow2_scale(float bound) {     // same rule as the tensor path: bound * s <= 2^14
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  int sh = 14 - (ilogbf(bound) + 1);
+  sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+  return ldexpf(1.f, sh);
+}
+__device__ __forceinline__ void rqs_split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// rows x ncol fp32 gradients of whole samples r0 .. r0 + rows - 1 (shared memory) -> scaled hi / lo planes (padding columns
+// zero), and the column sums (= bias gradient of the conditioner's last Dense): thread t owns column pairs t, t + blockDim
+template <typename T>
+__device__ __forceinline__ void rqs_store_planes(const T* __restrict__ tile, int rows, int64_t r0, int ncol, float s,
+                                                 const RqsPlanesOut<T>& po, T (&csum)[4], bool want_sums) {
+  const int half_ld = po.ld >> 1;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int cp = threadIdx.x + q * blockDim.x;
+    if (cp < half_ld) {
+      const int col = 2 * cp;
+      const bool live = col < ncol;          // ncol is even: a pair is all live or all padding
+      T a0 = 0, a1 = 0;
+      uint32_t* ph = reinterpret_cast<uint32_t*>(po.hi + r0 * po.ld + col);
+      uint32_t* pl = reinterpret_cast<uint32_t*>(po.hi + po.plane_elems + r0 * po.ld + col);
+      for (int rr = 0; rr < rows; ++rr) {
+        T v0 = 0, v1 = 0;
+        if (live) { v0 = tile[rr * ncol + col]; v1 = tile[rr * ncol + col + 1]; }
+        a0 += v0; a1 += v1;
+        uint32_t hi, lo;
+        rqs_split_pair((float)v0 * s, (float)v1 * s, hi, lo);
+        ph[(int64_t)rr * half_ld] = hi;
+        pl[(int64_t)rr * half_ld] = lo;
+      }
+      if (want_sums) { csum[2 * q] += a0; csum[2 * q + 1] += a1; }
+    }
   }
 }
 
@@ -710,11 +776,12 @@ __device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int 
 // thread rewrites its private row in place, and the tile streams back out with one bulk store.
 // colsum (optional, needs blockDim % c == 0 and c*(3K-1) <= 4*blockDim): sum over samples of every graw column = the
 // bias gradient of the conditioner's last Dense, accumulated per thread across the block's tiles and flushed once.
-template <typename T, int KMAX, bool INV>
-__global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restrict__ raw,
+template <typename T, int KMAX, bool INV, int MODE>
+__global__ void __launch_bounds__(128, (KMAX <= 16 && sizeof(T) == 4) ? 7 : 4)   // Float32, K <= 16: seven 128-thread blocks per SM fit the ring
+rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restrict__ raw,
                                const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int K, T B,
                                int64_t N, T* __restrict__ graw, float* __restrict__ amax_meta, double* __restrict__ colsum,
-                               int stages) {
+                               int stages, RqsPlanesOut<T> po) {
   extern __shared__ __align__(128) unsigned char rqs_smem[];
   __shared__ uint64_t full_bar[rq::kMaxStages];
   T* tiles = reinterpret_cast<T*>(rqs_smem);
@@ -724,6 +791,32 @@ __global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, co
   const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(T));
   const int64_t total = N * c;
   const int64_t nfull = total / blockDim.x;
+  constexpr int mode = MODE;      // a template parameter: the fp32 form keeps its register count (occupancy)
+  // planes modes: the scale of this pass, and (mode 3) whether the speculative pass has to be redone at all
+  float s_planes = 1.f;
+  if (mode == 2) s_planes = rqs_pow2_scale(__uint_as_float(reinterpret_cast<const unsigned int*>(po.est)[1]) * po.headroom);
+  if (mode == 3) {
+    const float s_spec = rqs_pow2_scale(__uint_as_float(reinterpret_cast<const unsigned int*>(po.est)[1]) * po.headroom);
+    s_planes = rqs_pow2_scale(__uint_as_float(reinterpret_cast<const unsigned int*>(po.meta)[1]));
+    const unsigned int est_bits = reinterpret_cast<const unsigned int*>(po.est)[1], exact_bits = reinterpret_cast<const unsigned int*>(po.meta)[1];
+    // redo when the exact maximum overflows the predicted scale, or when the sample saw only zeros (identity tails) and
+    // the prediction therefore says nothing about the magnitude
+    const bool redo = (s_planes < s_spec) || (est_bits == 0u && exact_bits != 0u);
+    if (!redo) {
+      // the predicted scale held: commit d/d(spline input) of the speculative pass into the transformed columns of G
+      for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / c;
+        G[r * d + idx1[(int)(e - r * c)]] = po.gside[e];
+      }
+      return;
+    }
+  }
+  if ((mode == 2 || mode == 3) && blockIdx.x == 0 && threadIdx.x == 0) po.meta[0] = s_planes;
+  const bool planes = mode >= 2;
+  const bool want_sums = colsum && mode != 3 && mode != 1;     // a redo repeats the planes, not the (scale-free) column sums
+  // mode 1 walks every tile_step-th tile and stores nothing
+  const int64_t step = mode == 1 ? (int64_t)(po.tile_step > 0 ? po.tile_step : 1) : 1;
+  const int64_t ntl = (nfull + step - 1) / step;
   float run_max = 0.f;
   T csum[4] = {0, 0, 0, 0};
   if (threadIdx.x == 0) {
@@ -731,38 +824,41 @@ __global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, co
     rq::bar_fence_init();
   }
   __syncthreads();
-  const int64_t n_my = blockIdx.x < nfull ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_my = blockIdx.x < ntl ? (ntl - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   if (threadIdx.x == 0)
     for (int q = 0; q < stages - 1 && q < n_my; ++q)
-      rq::load_tile(rq::s32(tiles + (size_t)q * tile_elems), raw + (blockIdx.x + (int64_t)q * gridDim.x) * tile_elems, tile_bytes,
+      rq::load_tile(rq::s32(tiles + (size_t)q * tile_elems), raw + (blockIdx.x + (int64_t)q * gridDim.x) * step * tile_elems, tile_bytes,
                     rq::s32(&full_bar[q]));
   const bool whole_rows = (blockDim.x % c) == 0;
   const int rows_per_tile = blockDim.x / c, t_row = threadIdx.x / c, t_col = threadIdx.x % c;
   for (int64_t it = 0; it < n_my; ++it) {
     const int buf = (int)(it % stages);
-    const int64_t blk = blockIdx.x + it * gridDim.x;
+    const int64_t blk = (blockIdx.x + it * gridDim.x) * step;
     T* tile = tiles + (size_t)buf * tile_elems;
     rq::wait(rq::s32(&full_bar[buf]), (uint32_t)((it / stages) & 1));
     {
       int64_t r; int i;
       if (whole_rows) { r = blk * rows_per_tile + t_row; i = t_col; }    // no 64-bit division on the hot path
       else { const int64_t e = blk * blockDim.x + threadIdx.x; r = e / c; i = (int)(e - r * c); }
-      rqs_bwd_row<T, KMAX, INV>(tile + threadIdx.x * P3, r, i, G, Vsrc, gld, idx1, c, d, K, B, run_max);
+      T* gdst = mode == 2 ? po.gside + (r * c + i) : G + (r * d + idx1[i]);
+      rqs_bwd_row<T, KMAX, INV>(tile + threadIdx.x * P3, r, i, G, Vsrc, gld, idx1, c, d, K, B, run_max, gdst, mode != 1);
     }
-    rq::fence_async();       // generic-proxy writes of the rows -> visible to the bulk store
+    rq::fence_async();       // generic-proxy accesses of the rows -> ordered before the bulk store / the refill of this buffer
     __syncthreads();
     if (threadIdx.x == 0) {
-      rq::store_tile(graw + blk * tile_elems, rq::s32(tile), tile_bytes);
+      if (mode == 0) rq::store_tile(graw + blk * tile_elems, rq::s32(tile), tile_bytes);
       if (it + stages - 1 < n_my) {
         // the buffer of tile it-1 is next in the ring: its store must have finished reading shared memory (every
-        // thread's column-sum reads of it completed before the barrier above)
-        rq::wait_stores_read<1>();
+        // thread's reads of it -- column sums, plane stores -- completed before the barrier above)
+        if (mode == 0) rq::wait_stores_read<1>();
         const int nb = (int)((it + stages - 1) % stages);
-        rq::load_tile(rq::s32(tiles + (size_t)nb * tile_elems), raw + (blk + (int64_t)(stages - 1) * gridDim.x) * tile_elems, tile_bytes,
+        rq::load_tile(rq::s32(tiles + (size_t)nb * tile_elems), raw + (blk + (int64_t)(stages - 1) * gridDim.x * step) * tile_elems, tile_bytes,
                       rq::s32(&full_bar[nb]));
       }
     }
-    if (colsum) {   // the tile is whole samples: blockDim / c rows of ncol columns
+    if (planes) {            // the tile is whole samples (the launcher checks): rows of ncol gradients -> planes (+ column sums)
+      rqs_store_planes<T>(tile, tile_elems / ncol, blk * rows_per_tile, ncol, s_planes, po, csum, want_sums);
+    } else if (want_sums) {   // the tile is whole samples: blockDim / c rows of ncol columns
       const int rows = tile_elems / ncol;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -775,34 +871,42 @@ __global__ void rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, co
       }
     }
   }
-  if (threadIdx.x == 0) rq::wait_stores_read<0>();
-  // ragged tail (total % blockDim.x pairs): plain staging by the block whose turn it would be
+  if (threadIdx.x == 0 && mode == 0) rq::wait_stores_read<0>();
+  // ragged tail (total % blockDim.x pairs): plain staging by the block whose turn it would be (not part of the estimate)
   const int rem = (int)(total - nfull * blockDim.x);
-  if (rem > 0 && blockIdx.x == (unsigned)(nfull % gridDim.x)) {
+  if (rem > 0 && mode != 1 && blockIdx.x == (unsigned)(nfull % gridDim.x)) {
     __syncthreads();
     const int64_t e0 = nfull * blockDim.x;
     for (int i = threadIdx.x; i < rem * P3; i += blockDim.x) tiles[i] = raw[e0 * P3 + i];
     __syncthreads();
     if ((int)threadIdx.x < rem) {
       const int64_t e = e0 + threadIdx.x;
-      rqs_bwd_row<T, KMAX, INV>(tiles + threadIdx.x * P3, e / c, (int)(e % c), G, Vsrc, gld, idx1, c, d, K, B, run_max);
+      const int64_t r = e / c; const int i = (int)(e % c);
+      T* gdst = mode == 2 ? po.gside + e : G + (r * d + idx1[i]);
+      rqs_bwd_row<T, KMAX, INV>(tiles + threadIdx.x * P3, r, i, G, Vsrc, gld, idx1, c, d, K, B, run_max, gdst, true);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < rem * P3; i += blockDim.x) graw[e0 * P3 + i] = tiles[i];
-    if (colsum) {
-      const int rows = rem * P3 / ncol;
+    if (planes) {
+      rqs_store_planes<T>(tiles, rem * P3 / ncol, e0 / c, ncol, s_planes, po, csum, want_sums);
+    } else {
+      for (int i = threadIdx.x; i < rem * P3; i += blockDim.x) graw[e0 * P3 + i] = tiles[i];
+      if (want_sums) {
+        const int rows = rem * P3 / ncol;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int col = threadIdx.x + q * blockDim.x;
-        if (col < ncol) for (int rr = 0; rr < rows; ++rr) csum[q] += tiles[rr * ncol + col];
+        for (int q = 0; q < 4; ++q) {
+          const int col = threadIdx.x + q * blockDim.x;
+          if (col < ncol) for (int rr = 0; rr < rows; ++rr) csum[q] += tiles[rr * ncol + col];
+        }
       }
     }
   }
-  if (amax_meta) amax_update(amax_meta, run_max);
-  if (colsum) {
+  if (mode == 1) { amax_update(po.est, run_max); return; }
+  if (amax_meta && mode != 3) amax_update(amax_meta, run_max);
+  if (want_sums) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int col = threadIdx.x + q * blockDim.x;
+      // fp32 form: thread t owns columns t + q * blockDim; planes form: column pairs t, t + blockDim (rqs_store_planes)
+      const int col = planes ? 2 * (threadIdx.x + (q >> 1) * blockDim.x) + (q & 1) : threadIdx.x + q * blockDim.x;
       if (col < ncol) atomicAdd(&colsum[col], (double)csum[q]);
     }
   }

@@ -16,6 +16,7 @@ int g_opt_hmc_warp = getenv("NFCUDA_HMC_WARP") ? atoi(getenv("NFCUDA_HMC_WARP"))
 // 0: two-team streaming kernel (fused_coupling.cuh, default), 1: 128-column-MMA kernel (fused_coupling_w128.cuh)
 int g_opt_fused_variant = getenv("NFCUDA_FUSED_VARIANT") ? atoi(getenv("NFCUDA_FUSED_VARIANT")) : 0;
 int g_opt_fused_coupling = !(getenv("NFCUDA_FUSED") && atoi(getenv("NFCUDA_FUSED")) == 0);
+int g_opt_rqs_planes = getenv("NFCUDA_RQS_PLANES") ? atoi(getenv("NFCUDA_RQS_PLANES")) : 1;
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -1029,6 +1030,7 @@ int nf_set_option(const char* name, int value) {
   if (name && !strcmp(name, "fused_coupling")) { g_opt_fused_coupling = value; return NF_OK; }
   if (name && !strcmp(name, "fused_variant")) { g_opt_fused_variant = value; return NF_OK; }
   if (name && !strcmp(name, "hmc_warp")) { g_opt_hmc_warp = value; return NF_OK; }
+  if (name && !strcmp(name, "rqs_planes")) { g_opt_rqs_planes = value; return NF_OK; }
   set_error("nf_set_option: unknown option '%s'", name ? name : "(null)");
   return NF_ERR_INVALID;
 }

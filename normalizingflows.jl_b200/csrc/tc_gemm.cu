@@ -1370,6 +1370,16 @@ int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx,
   return split_into_planes(f, get_state(f), X, d, d_idx, n_idx, n, act0, amax_src);
 }
 
+int tc_planes_out(Flow& f, void* buf, int64_t n, int width, TcPlanesOut* out) {
+  TcState* st = get_state(f);
+  NF_REQUIRE(st, "tcgen05 path: no state");
+  Planes P = planes_of(buf, n, width);
+  float* meta = new_meta(st, buf);
+  NF_REQUIRE(meta, "tcgen05 path: out of tensor metadata slots");
+  *out = TcPlanesOut{P.p, P.plane_elems(), P.ld, meta};
+  return NF_OK;
+}
+
 float* tc_alloc_meta(Flow& f) {
   TcState* st = get_state(f);
   if (!st || st->next_slot >= kMetaSlots) return nullptr;
@@ -1450,8 +1460,10 @@ int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, 
   static const bool wgrad_colsum = getenv("NFCUDA_WGRAD_COLSUM") && atoi(getenv("NFCUDA_WGRAD_COLSUM")) != 0;
   // gradient w.r.t. the last pre-activation -> split planes
   // ... and, in the same pass, the bias gradient of the last Dense (column sums of the fp32 gradient)
-  NF_TRY(split_into_planes(f, st, g_last, md.dims[nd], nullptr, md.dims[nd], n, gbuf, g_last_amax,
-                           last_bias_done ? nullptr : gsum + md.b_off[nd - 1]));
+  if (g_last)
+    NF_TRY(split_into_planes(f, st, g_last, md.dims[nd], nullptr, md.dims[nd], n, gbuf, g_last_amax,
+                             last_bias_done ? nullptr : gsum + md.b_off[nd - 1]));
+  else NF_REQUIRE(last_bias_done && meta_of(st, gbuf), "tc_mlp_backward: planes input without metadata / bias gradient");
   for (int i = nd - 1; i >= 0; --i) {
     const int pi = st->index[li][m][i];
     const DensePrep& dp = st->preps[pi];

@@ -19,9 +19,15 @@ int tc_gather_split(Flow& f, const float* X, int d, const int* d_idx, int n_idx,
 float* tc_alloc_meta(Flow& f);
 int tc_absmax(Flow& f, const float* X, int64_t count, float* meta);
 int tc_mlp_forward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts);
-// g_last: fp32 [n, out] gradient w.r.t. the last Dense's pre-activation; scratch0/1: activation-sized buffers
+// g_last: fp32 [n, out] gradient w.r.t. the last Dense's pre-activation; scratch0/1: activation-sized buffers.
+// g_last == nullptr: the producer has already written that gradient as split planes into scratch0 (tc_planes_out) together
+// with its bias-gradient column sums.
 int tc_mlp_backward(Flow& f, const LayerDesc& Ld, int m, int64_t n, void* act0, std::vector<void*>& acts, float* g_last,
                     const float* g_last_amax, void* scratch0, void* scratch1, float* G, double* gsum, bool last_bias_done = false);
+// where a producer kernel writes split planes of an [n, width] tensor into `buf` itself: plane pointers, row stride and a fresh
+// {scale, amax} slot the producer fills (scale = the power of two it multiplied with, amax = exact max |value|)
+struct TcPlanesOut { void* hi; int64_t plane_elems; int ld; float* meta; };
+int tc_planes_out(Flow& f, void* buf, int64_t n, int width, TcPlanesOut* out);
 // fused AffineCoupling forward (both conditioners + coupling arithmetic in one launch); writes the same stash
 // (x2 / hidden planes, sign bits, s) the layer-by-layer path writes, so tc_mlp_backward consumes it unchanged
 bool tc_fused_affine_ok(const Flow& f, const LayerDesc& Ld);

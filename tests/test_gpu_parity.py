@@ -229,3 +229,35 @@ def test_tc_gemm_accuracy(gpu):
         e = Y - ref
         assert np.linalg.norm(e) / np.linalg.norm(ref) < 4e-7, (n, K, N)
         assert abs(np.mean(e * np.sign(ref)) / np.mean(np.abs(ref))) < 1.5e-7, (n, K, N)
+
+
+
+@pytest.mark.parametrize("B,N", [(5.0, 3000), (1.0, 777)], ids=["B5", "B1-ragged"])
+def test_spline_backward_plane_forms_agree(gpu, B, N):
+    """The spline backward hands the conditioner-output gradient to the GEMMs either as an fp32 matrix plus a split pass
+    (rqs_planes = 0), as split planes written by the spline kernel under a predicted scale (1, the default), or -- forced here
+    by a deliberately wrong prediction -- through the redo pass with the exact scale (2).  Each form must meet the north_star
+    tolerances against the float64 oracle (neuralspline.jl:94-108 and its pullback), and the three agree far inside them.
+    N = 777 leaves a ragged last tile; B = 1 puts many inputs on the identity tails (zero gradients in the sampled tiles)."""
+    nf = gpu
+    lib = nf._capi.lib()
+    kw = dict(hdims=[32, 32], K=10, B=B, nlayers=3)
+    of = oracle_flow("nsf", 16, np.float32, **kw)
+    ot = oracle_target("cross", 16)
+    xs = z0(N, 16, np.float32)
+    v64, g64 = _f64_truth("nsf", 16, kw, of, ot, xs)
+    gt = gpu_target(nf, ot)
+    res = {}
+    try:
+        for mode in (0, 1, 2):
+            nf._capi.check(lib.nf_set_option(b"rqs_planes", mode))
+            gf = _set_mode(nf, gpu_flow(nf, of, np.float32), "f16x3")
+            v, g = nf.api._elbo_impl(gf, gt, xs, want_grad=True)
+            assert abs(v - v64) <= 1e-5 * max(abs(v64), 1.0), (mode, v, v64)
+            assert rel_err(g, g64) <= 1e-4, (mode, rel_err(g, g64))
+            res[mode] = (v, np.array(g, copy=True))
+    finally:
+        nf._capi.check(lib.nf_set_option(b"rqs_planes", 1))
+    for mode in (1, 2):
+        assert abs(res[mode][0] - res[0][0]) <= 2e-6 * max(abs(res[0][0]), 1.0)
+        assert rel_err(res[mode][1], res[0][1]) <= 5e-6, (mode, rel_err(res[mode][1], res[0][1]))
