@@ -742,12 +742,37 @@ __device__ __forceinline__ void rqs_split_pair(float a, float b, uint32_t& hi, u
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// quad form of rqs_store_planes: Float32 rows of a multiple of four columns, and the block covers whole rows of quads
+__device__ __forceinline__ bool rqs_planes_quads(int ncol, int ld) {
+  const int quads = ld >> 2;
+  return (ncol & 3) == 0 && quads <= (int)blockDim.x && (blockDim.x % quads) == 0;
+}
 // rows x ncol fp32 gradients of whole samples r0 .. r0 + rows - 1 (shared memory) -> scaled hi / lo planes (padding columns
 // zero), and the column sums (= bias gradient of the conditioner's last Dense): thread t owns column pairs t, t + blockDim
 template <typename T>
 __device__ __forceinline__ void rqs_store_planes(const T* __restrict__ tile, int rows, int64_t r0, int ncol, float s,
                                                  const RqsPlanesOut<T>& po, T (&csum)[4], bool want_sums) {
   const int half_ld = po.ld >> 1;
+  if (rqs_planes_quads(ncol, po.ld)) {
+    // four adjacent columns per thread (one 16-byte shared load, one 8-byte store per plane), blockDim / (ld / 4) rows per pass
+    const int quads = po.ld >> 2, qd = threadIdx.x % quads, rstep = blockDim.x / quads;
+    const int col = 4 * qd;
+    const bool live = col < ncol;
+    T a[4] = {0, 0, 0, 0};
+    for (int rr = threadIdx.x / quads; rr < rows; rr += rstep) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) v = *reinterpret_cast<const float4*>(tile + rr * ncol + col);
+      a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+      uint2 hi, lo;
+      rqs_split_pair(v.x * s, v.y * s, hi.x, lo.x);
+      rqs_split_pair(v.z * s, v.w * s, hi.y, lo.y);
+      const int64_t o = (r0 + rr) * po.ld + col;
+      *reinterpret_cast<uint2*>(po.hi + o) = hi;
+      *reinterpret_cast<uint2*>(po.hi + po.plane_elems + o) = lo;
+    }
+    if (want_sums) { csum[0] += a[0]; csum[1] += a[1]; csum[2] += a[2]; csum[3] += a[3]; }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const int cp = threadIdx.x + q * blockDim.x;
@@ -906,7 +931,9 @@ rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restric
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       // fp32 form: thread t owns columns t + q * blockDim; planes form: column pairs t, t + blockDim (rqs_store_planes)
-      const int col = planes ? 2 * (threadIdx.x + (q >> 1) * blockDim.x) + (q & 1) : threadIdx.x + q * blockDim.x;
+      const int col = !planes ? threadIdx.x + q * blockDim.x
+                      : (rqs_planes_quads(ncol, po.ld) ? 4 * (threadIdx.x % (po.ld >> 2)) + q
+                                                       : 2 * (threadIdx.x + (q >> 1) * blockDim.x) + (q & 1));
       if (col < ncol) atomicAdd(&colsum[col], (double)csum[q]);
     }
   }
