@@ -237,11 +237,10 @@ def run_side_config(args):
     if cfg in ("c4", "c4b", "c4ll") and prof.get("rqs_bwd", {}).get("launches"):
         # dominant spline kernel: reads the 3K-1 conditioner outputs of every (sample, transformed coordinate), writes the same
         # number of gradients, plus the coordinate, its incoming gradient (read + write) and the per-sample logdet gradient
-        c, P3 = d // 2, 3 * 10 - 1
-        bytes_per_launch = n * c * (2 * P3 * 4 + 12) + n * 4
+        bytes_per_launch = rqs_bwd_bytes(n, d)
         avg_ms = prof["rqs_bwd"]["total_ms"] / prof["rqs_bwd"]["launches"]
         ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "rqs_bwd_kernel<float,10> (spline backward: logits in, gradients out, bulk-copy ring)",
+        roof = {"bound": "hbm", "kernel": RQS_BWD_DESC,
                 "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "avg_launch_ms": avg_ms,
                 "launches_per_step": prof["rqs_bwd"]["launches"] / args.steps, "peak_source": src + " copy bandwidth", "traffic": None}
     elif "ew_flow" in prof and prof["ew_flow"]["launches"]:
@@ -380,16 +379,28 @@ def side_c4(nf, K, lib, torch, steps=5):
     _, _, hbm, src = peaks()
     roof = None
     if prof.get("rqs_bwd", {}).get("launches"):
-        c, P3 = d // 2, 3 * 10 - 1
-        bytes_per_launch = n * c * (2 * P3 * 4 + 12) + n * 4
+        bytes_per_launch = rqs_bwd_bytes(n, d)
         avg_ms = prof["rqs_bwd"]["total_ms"] / prof["rqs_bwd"]["launches"]
         ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "rqs_bwd_kernel<float,10>", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+        roof = {"bound": "hbm", "kernel": RQS_BWD_DESC, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                 "avg_launch_ms": avg_ms, "peak_source": src + " copy bandwidth", "traffic": None,
-                "note": "bytes = the kernel's own unfused traffic (logits in, gradients out); algorithmic bytes of the step are 64 B/sample"}
+                "note": "bytes = the kernels' own unfused traffic (logits in, gradient planes out); algorithmic bytes of the step are 64 B/sample"}
     return {"workload": "nsf_d16_K10_B5_mlp32x32_8xNeuralSplineCoupling_cross8_reverseKL_elbo+grad", "batch": n, "value": n * steps / dt,
             "unit": "samples/s", "ms_per_step": 1e3 * dt / steps, "device_ms_per_step": dev_ms / steps, "steps": steps, "loss": val.value,
             "roofline": roof, "kernel_classes": prof}
+
+
+RQS_BWD_DESC = ("rqs_bwd_kernel<float,10> (spline backward, K = 10: estimate pass over every 64th tile + full pass + commit; logits in through "
+                "the bulk-copy ring, gradient w.r.t. the conditioner output out as the fp16 hi/lo planes the GEMMs read)")
+
+
+def rqs_bwd_bytes(n, d, K=10):
+    """Bytes one spline-backward step moves for n samples (its own unfused traffic): per (sample, transformed coordinate) the
+    3K-1 logits in and their share of the two fp16 planes out (rows padded to 64 columns), the coordinate, its incoming gradient,
+    the outgoing gradient through the side buffer (write, read, write); per sample the logdet gradient."""
+    c, P3 = d // 2, 3 * K - 1
+    ld = ((c * P3 + 63) // 64) * 64
+    return n * (c * (P3 * 4 + 5 * 4) + ld * 4) + n * 4
 
 
 def main():
