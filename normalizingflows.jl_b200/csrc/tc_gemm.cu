@@ -234,7 +234,7 @@ template <int BN> struct GemmCfg {
 // K slab of 64: each slab accumulates into a fresh TMEM buffer (correction products first, while the
 // accumulator is still tiny), the epilogue warps drain it and carry the running sum in registers with
 // round-to-nearest adds, the same split Ootomo & Yokota use for fp32 emulation on tensor cores.
-template <int BN>
+template <int BN, bool SINGLE>      // SINGLE: the whole contraction accumulates in one TMEM buffer (one slab per tile)
 __global__ void __launch_bounds__(GemmCfg<BN>::THREADS, GemmCfg<BN>::CTAS)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                const __grid_constant__ CUtensorMap tmapO, GemmParams p) {
@@ -379,31 +379,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         const int col0 = n0 + cbase + c * 32;
         mask_pre[c] = (p.epi == EPI_PLANES_MASK && row_ok && col0 < p.n_store) ? __ldg(p.mask_bits + row * p.mask_ld + (col0 >> 5)) : 0u;
       }
-      const int nslabs = (nk + p.slab_stages - 1) / p.slab_stages;
-      for (int kc = 0; kc < nslabs; ++kc, ++it) {
-        const uint32_t acc = it & 1, accph = (it >> 1) & 1;
-        mbar_wait_relaxed(tfull_bar(acc), accph);
-        NF_DBG(2, 3 * it, threadIdx.x == 64);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cbase;
-#pragma unroll
-        for (int c = 0; c < CPT / 32; ++c) {
-          if (c * 32 < ncols_here) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        NF_DBG(2, 3 * it + 1, threadIdx.x == 64);
-      }
-#pragma unroll
-      for (int c = 0; c < CPT / 32; ++c) {
+      // one 32-column chunk of this thread's accumulator range (racc[c * 32 ..]): fused epilogue and store
+      auto process_chunk = [&](const int c) {
         const int col0 = n0 + cbase + c * 32;
-        if (col0 >= p.n_store) break;   // warp-uniform
+        if (col0 >= p.n_store) return;   // warp-uniform
         const float* v = racc + c * 32;
         const int bo = cbase + c * 32;     // offset into s_bias
         if (p.epi == EPI_PLANES_ACT || p.epi == EPI_PLANES_MASK) {
@@ -550,6 +529,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             __syncwarp();
           }
         }
+      };
+      const int nslabs = (nk + p.slab_stages - 1) / p.slab_stages;
+      if constexpr (SINGLE) {
+        // the whole contraction sits in one TMEM buffer (every backward GEMM, every K <= 64 forward GEMM): each 32-column chunk
+        // is loaded right before its epilogue instead of all chunks up front, which halves the registers held through the
+        // per-chunk math (no spills); the buffer goes back to the MMA warp after the last load
+        const uint32_t acc = it & 1, accph = (it >> 1) & 1;
+        mbar_wait_relaxed(tfull_bar(acc), accph);
+        NF_DBG(2, 3 * it, threadIdx.x == 64);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cbase;
+        bool released = false;
+#pragma unroll
+        for (int c = 0; c < CPT / 32; ++c) {
+          if (c * 32 < ncols_here) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[c * 32 + j] = __uint_as_float(v[j]);
+          }
+          if (!released && (c == CPT / 32 - 1 || (c + 1) * 32 >= ncols_here)) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            NF_DBG(2, 3 * it + 1, threadIdx.x == 64);
+            released = true;
+          }
+          process_chunk(c);
+        }
+        ++it;
+      } else {
+        for (int kc = 0; kc < nslabs; ++kc, ++it) {
+          const uint32_t acc = it & 1, accph = (it >> 1) & 1;
+          mbar_wait_relaxed(tfull_bar(acc), accph);
+          NF_DBG(2, 3 * it, threadIdx.x == 64);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cbase;
+  #pragma unroll
+          for (int c = 0; c < CPT / 32; ++c) {
+            if (c * 32 < ncols_here) {
+              uint32_t v[32];
+              tmem_ld32(taddr + c * 32, v);
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          NF_DBG(2, 3 * it + 1, threadIdx.x == 64);
+        }
+#pragma unroll
+        for (int c = 0; c < CPT / 32; ++c) process_chunk(c);
       }
       NF_DBG(2, 3 * (it - 1) + 2, threadIdx.x == 64);
     }
@@ -1202,10 +1234,12 @@ int make_map_mnmajor(TcState* st, const void* basep, int64_t rows, int64_t cols,
 template <int BN>
 int launch_gemm_bn(Flow& f, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmParams& p, int n_tiles_n) {
   using Cfg = GemmCfg<BN>;
-  auto kern = tc_gemm_kernel<BN>;
+  const bool single = p.slab_stages >= p.num_k_chunks;
+  auto kern = single ? tc_gemm_kernel<BN, true> : tc_gemm_kernel<BN, false>;
   static bool attr_set[64] = {};            // per device: function attributes belong to the context
   if (!attr_set[f.device & 63]) {
-    NF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    NF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    NF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set[f.device & 63] = true;
   }
   const int64_t tiles = ceil_div(p.M, 128);
