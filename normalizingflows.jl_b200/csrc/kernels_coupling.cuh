@@ -621,14 +621,16 @@ __global__ void rqs_apply_kernel(const T* __restrict__ Xin, const T* __restrict_
 template <typename T, int KMAX, bool INV>
 __device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int i, T* __restrict__ G, const T* __restrict__ Vsrc,
                                             const T* __restrict__ gld, const int* __restrict__ idx1, int c, int d, int K, T B,
-                                            float& run_max, T* __restrict__ gdst, bool store_gin) {
-  // gdst: where d/d(spline input) goes (G[r, idx1[i]] itself for the in-place form; a side buffer for the speculative pass,
-  // which must leave G intact for a possible second pass); store_gin = false: nothing is stored (estimate pass)
+                                            float& run_max, const T* __restrict__ gsrc, T* __restrict__ gkeep, bool store_gin) {
+  // gsrc: where the incoming gradient of this coordinate is read (G[r, idx1[i]]; the side buffer in a redo pass, because the
+  // speculative pass has already overwritten G); gkeep: optional copy of it for such a redo; d/d(spline input) always goes to
+  // G[r, idx1[i]] unless store_gin is false (estimate pass: nothing is stored)
   using Nm = Num<T>;
   const int P3 = 3 * K - 1;
   const int j = idx1[i];
   const T v = Vsrc[r * d + j];
-  const T go = G[r * d + j];
+  const T go = *gsrc;
+  if (gkeep) *gkeep = go;
   const T gl = gld ? gld[r] : T(1);
   RqsBin<T> b;
   rqs_locate_row<T, KMAX, INV>(row, K, B, v, b);
@@ -671,7 +673,7 @@ __device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int 
     g_dy += g_s * idx_; g_dx += -g_s * s * idx_;
     const T g_y1 = g_dy; g_y0 -= g_dy;
     const T g_x1 = g_dx; g_x0 -= g_dx;
-    if (store_gin) *gdst = g_in;
+    if (store_gin) G[r * d + j] = g_in;
     const T twoB = 2 * B;
     const T rSw = 1 / b.Sw, rSh = 1 / b.Sh;
     const int bk = b.k;
@@ -703,7 +705,7 @@ __device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int 
     for (int k = 1; k < KMAX; ++k) if (k < K)
       row[2 * K + k - 1] = (k == bk - 1) ? gd0 : ((k == bk) ? gd1 : T(0));
   } else {   // identity tails: dy/dx = 1, no parameter gradient; G unchanged
-    if (store_gin && gdst != G + (r * d + j)) *gdst = go;
+    if (store_gin && gsrc != G + (r * d + j)) G[r * d + j] = go;
 #pragma unroll
     for (int k = 0; k < 3 * KMAX - 1; ++k) if (k < P3) row[k] = 0;
   }
@@ -713,9 +715,9 @@ __device__ __forceinline__ void rqs_bwd_row(T* __restrict__ row, int64_t r, int 
 // straight into the fp16 hi / lo planes the dgrad / weight-gradient GEMMs read, instead of an fp32 matrix that a separate
 // pass would re-read and split.  The planes need ONE power-of-two scale for the whole tensor, i.e. max |gradient| before the
 // first store.  It is predicted: a dry pass over every tile_step-th tile records the maximum of that sample (est), the
-// full pass scales with 2^8 of headroom over it and records the exact maximum, and a third launch either commits
-// (d/d input from the side buffer into G) or -- if the exact maximum would have overflowed the predicted scale -- redoes
-// the tile loop with the exact scale.  Every decision is a pure function of the inputs, so results stay reproducible;
+// full pass scales with 2^8 of headroom over it, records the exact maximum and keeps a copy of the incoming gradients it
+// overwrites, and a third launch returns at once -- or, if the exact maximum would have overflowed the predicted scale,
+// redoes the tile loop with the exact scale from that copy.  Every decision is a pure function of the inputs, so results stay reproducible;
 // a scale up to 2^8 below the ideal one costs nothing visible (error floor 2^-32 of the maximum instead of 2^-40).
 template <typename T> struct RqsPlanesOut {
   __half* hi;             // hi plane [rows_pad, ld]; lo plane at + plane_elems
@@ -723,8 +725,8 @@ template <typename T> struct RqsPlanesOut {
   int ld;
   float* meta;            // {scale, bits of the exact max |gradient|} of the planes
   float* est;             // est[1]: bits of the max over the sampled tiles
-  T* gside;               // [N, c] d/d(spline input) of the speculative pass
-  int mode;               // 0: fp32 graw (no planes); 1: estimate pass; 2: speculative pass; 3: commit or redo
+  T* gside;               // [N, c] incoming gradient of every transformed coordinate, kept by the speculative pass for a redo
+  int mode;               // 0: fp32 graw (no planes); 1: estimate pass; 2: speculative pass; 3: nothing, or redo with the exact scale
   int tile_step;          // mode 1: every tile_step-th tile
   float headroom;         // predicted bound = headroom * sampled maximum (kRqsSpecHeadroom; tests force a redo with a tiny value)
 };
@@ -827,14 +829,7 @@ rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restric
     // redo when the exact maximum overflows the predicted scale, or when the sample saw only zeros (identity tails) and
     // the prediction therefore says nothing about the magnitude
     const bool redo = (s_planes < s_spec) || (est_bits == 0u && exact_bits != 0u);
-    if (!redo) {
-      // the predicted scale held: commit d/d(spline input) of the speculative pass into the transformed columns of G
-      for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / c;
-        G[r * d + idx1[(int)(e - r * c)]] = po.gside[e];
-      }
-      return;
-    }
+    if (!redo) return;       // the predicted scale held: nothing to do
   }
   if ((mode == 2 || mode == 3) && blockIdx.x == 0 && threadIdx.x == 0) po.meta[0] = s_planes;
   const bool planes = mode >= 2;
@@ -865,8 +860,10 @@ rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restric
       int64_t r; int i;
       if (whole_rows) { r = blk * rows_per_tile + t_row; i = t_col; }    // no 64-bit division on the hot path
       else { const int64_t e = blk * blockDim.x + threadIdx.x; r = e / c; i = (int)(e - r * c); }
-      T* gdst = mode == 2 ? po.gside + (r * c + i) : G + (r * d + idx1[i]);
-      rqs_bwd_row<T, KMAX, INV>(tile + threadIdx.x * P3, r, i, G, Vsrc, gld, idx1, c, d, K, B, run_max, gdst, mode != 1);
+      // speculative pass: keeps the incoming gradient in the side buffer; a redo reads it from there (G is already overwritten)
+      const T* gsrc = mode == 3 ? po.gside + (r * c + i) : G + (r * d + idx1[i]);
+      T* gkeep = mode == 2 ? po.gside + (r * c + i) : nullptr;
+      rqs_bwd_row<T, KMAX, INV>(tile + threadIdx.x * P3, r, i, G, Vsrc, gld, idx1, c, d, K, B, run_max, gsrc, gkeep, mode != 1);
     }
     rq::fence_async();       // generic-proxy accesses of the rows -> ordered before the bulk store / the refill of this buffer
     __syncthreads();
@@ -907,8 +904,9 @@ rqs_bwd_kernel(T* __restrict__ G, const T* __restrict__ Vsrc, const T* __restric
     if ((int)threadIdx.x < rem) {
       const int64_t e = e0 + threadIdx.x;
       const int64_t r = e / c; const int i = (int)(e % c);
-      T* gdst = mode == 2 ? po.gside + e : G + (r * d + idx1[i]);
-      rqs_bwd_row<T, KMAX, INV>(tiles + threadIdx.x * P3, r, i, G, Vsrc, gld, idx1, c, d, K, B, run_max, gdst, true);
+      const T* gsrc = mode == 3 ? po.gside + e : G + (r * d + idx1[i]);
+      T* gkeep = mode == 2 ? po.gside + e : nullptr;
+      rqs_bwd_row<T, KMAX, INV>(tiles + threadIdx.x * P3, r, i, G, Vsrc, gld, idx1, c, d, K, B, run_max, gsrc, gkeep, true);
     }
     __syncthreads();
     if (planes) {
