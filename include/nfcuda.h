@@ -272,6 +272,10 @@ NF_API void nf_shard_range(int64_t N_total, int n_ranks, int rank, int64_t* begi
  *   "hmc_warp"        1: every Hamiltonian flow the warp-per-sample kernels cover runs on them (csrc/hmc_warp.cu; default 0:
  *                     only flows the one-thread-per-sample kernels cannot take -- h not a power of two, h > 32, or h > 8 with
  *                     the logistic-regression score)
+ *   "rqs_planes"      1 (default): the spline-coupling backward kernel writes the gradient w.r.t. the conditioner output as
+ *                     the split fp16 planes the GEMMs read, under a predicted power-of-two scale (exact-scale redo as the safety
+ *                     net); 0: as an fp32 matrix plus a split pass; 2: planes with a deliberately wrong prediction, so that the
+ *                     redo pass runs (tests)
  * Returns NF_ERR_INVALID for an unknown name. */
 NF_API int nf_set_option(const char* name, int value);
 /* Duration (ms, CUDA events on the flow's stream) of the device work of the last value_and_grad call. */
