@@ -387,6 +387,7 @@ int coupling_backward(Flow& f, const LayerDesc& Ld, LayerBufs& b, const T* theta
         kern1<<<g1, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, nullptr, nullptr, rl.stages, po); \
         po.mode = 2;                                                                                                    \
         kern2<<<rl.grid, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, po.meta, cs, rl.stages, po); \
+        nf::g_launch_count += 2;      /* three launches, one NF_LAUNCH_CHECK below */                                   \
         po.mode = 3;                                                                                                    \
         kern3<<<rl.grid, rl.threads, rl.smem, f.stream>>>(G, Xin, raw, gld, Ld.d_idx1, cc, d, Ld.K, (T)Ld.B, n, gA, po.meta, cs, rl.stages, po); \
       }                                                                                                                 \
